@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixel/s of full SIFT detect (pyramid + DoG + extrema + refine).
+
+Workload (BASELINE.json configs[1]): 1920x1080 synthetic frames, 4 octaves x 3 scales per octave
+(6 blur levels), sigma0 = 1.6, assumed blur 0.5, the reference's thresholds, 2x-upsampled base octave
+(always, as in the reference).  A step = one pass of the whole path over FRAMES frames per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (own arm; torchrun for N > 1, weak scaling)
+  python bench.py --impl reference --gpus N --steps K ...  (reference's CPU algorithm on the host cores)
+
+Own arm, one JSON line on rank 0:
+  value    device-resident throughput (inputs already in HBM), CUDA events on the engine's stream, max over ranks
+  e2e      the same through sift_detect() (C ABI, HOST buffers): H2D of the u8 frame and D2H of the
+           keypoint records inside the timed region
+  roofline dominant kernel class (octave-0 blur+DoG) against the measured HBM peak, plus the whole-path figure
+  cpu_baseline  the float64 oracle (port of the reference's dense 2D algorithm) on one host core, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200"
+W, H = 1920, 1080
+N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
+FRAMES = 8                     # frames per GPU per step (distinct seeds)
+CPU_TILE = 128                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
+
+
+def algorithmic_bytes_per_input_px(n_oct: int = N_OCT) -> dict:
+    """SURVEY.md 8d, fp32 storage, every buffer touched the minimum number of times by the fused plan."""
+    n = {0: 4.0}                                  # octave sizes in units of input pixels
+    for o in range(1, n_oct):
+        n[o] = n[o - 1] / 4.0
+    blur0 = 4 * (1 + 6 * n[0] + 5 * n[0])         # read input, write 6 Gaussian + 5 DoG
+    scan = {o: 4 * 5 * n[o] for o in range(n_oct)}
+    blur = {0: blur0}
+    for o in range(1, n_oct):
+        blur[o] = 4 * (3 * n[o] + 10 * n[o])      # decimation read + seed write + seed read; 5 Gaussian + 5 DoG
+    total = sum(blur.values()) + sum(scan.values())
+    return {"blur": blur, "scan": scan, "total": total}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for i, nm in enumerate(names):
+                if f[2 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_frames(n: int, first_seed: int):
+    from sift_b200 import fixtures
+    return np.stack([fixtures.synthetic_u8(W, H, first_seed + i) for i in range(n)])
+
+
+# ------------------------------------------------------------------------------ CPU legs
+def cpu_tiles(n: int):
+    """n CPU_TILE^2 crops (float64 in [0,1]) of the benchmark's first frame."""
+    from sift_b200 import fixtures
+    frame = fixtures.to_float(fixtures.synthetic_u8(W, H, 1234))
+    tiles = []
+    for i in range(n):
+        y = (i * 97) % (H - CPU_TILE)
+        x = (i * 211) % (W - CPU_TILE)
+        tiles.append(np.ascontiguousarray(frame[y:y + CPU_TILE, x:x + CPU_TILE]))
+    return tiles
+
+
+def cpu_detect_tile(tile):
+    import oracle
+    r = oracle.detect(tile, numberOfOctaves=N_OCT, scalesPerOctave=SPO, minBlurLevel=MIN_BLUR, assumedBlur=ASSUMED,
+                      separable=False, keep_levels=False)
+    return len(r.keypoints)
+
+
+def cpu_baseline_leg() -> dict:
+    """One host core, the float64 port of the reference's dense 2D path, bounded sample."""
+    import oracle
+    oracle.build()
+    tiles = cpu_tiles(4)
+    cpu_detect_tile(tiles[0])
+    t0 = time.perf_counter()
+    for t in tiles:
+        cpu_detect_tile(t)
+    dt = time.perf_counter() - t0
+    return {"value": len(tiles) * CPU_TILE * CPU_TILE / 1e6 / dt, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+            "sample": f"{len(tiles)} crops {CPU_TILE}x{CPU_TILE} of frame 0, same params, dense 2D kernel, "
+                      f"{dt:.1f} s of CPU work (Node.js absent: float64 C restatement of the reference JS)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port: no Node.js on the box) on all host cores,
+    one image per thread, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import concurrent.futures as cf
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    tiles = cpu_tiles(cores)
+    ex = cf.ThreadPoolExecutor(max_workers=cores)   # ctypes releases the GIL inside the C call
+
+    def step():
+        list(ex.map(cpu_detect_tile, tiles))
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * cores * CPU_TILE * CPU_TILE / 1e6 / dt
+    sample = (f"{cores} crops {CPU_TILE}x{CPU_TILE} per step (one per thread) of the 1920x1080 frame, "
+              f"same params, dense 2D kernel")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": f"{W}x{H} synthetic frames (blobs+checkerboard+noise), {N_OCT} octaves x s={SPO} "
+                        f"(6 blur levels), sigma0={MIN_BLUR}, assumed blur {ASSUMED}, contrast 0.015 "
+                        f"(reference constant), edge r=10, 2x-upsampled base octave",
+            "frames_per_gpu_per_step": FRAMES, "sharding": f"images split by rank x{n_gpus}, no collective",
+            "l2": "no flush: one frame's pyramid (735 MB algorithmic) exceeds the 126 MB L2 and frames rotate"}
+
+
+# ------------------------------------------------------------------------------ own arm
+def run_own(args):
+    import torch
+    import sift_b200
+    from sift_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+
+    eng = sift_b200.Engine(local)
+    prm = L.default_params(numberOfOctaves=N_OCT, scalesPerOctave=SPO, minBlurLevel=MIN_BLUR, assumedBlur=ASSUMED)
+    frames_np = make_frames(FRAMES, 1234 + rank * FRAMES)
+    h_frames = torch.from_numpy(frames_np).pin_memory()
+    d_frames = h_frames.cuda()
+    cap = 1 << 15
+    d_out = torch.zeros(FRAMES, cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(FRAMES, dtype=torch.int32, device="cuda")
+    h_out = torch.zeros(cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.ExternalStream(eng.stream)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        for f in range(FRAMES):
+            eng.detect_device(d_frames[f].data_ptr(), L.SIFT_U8, W, H, 0, prm, d_out[f].data_ptr(), cap,
+                              d_cnt[f].data_ptr())
+
+    def step_e2e():
+        n = 0
+        for f in range(FRAMES):
+            k, _ = eng.detect_raw(h_frames[f].data_ptr(), L.SIFT_U8, W, H, 0, prm, h_out.data_ptr(), cap)
+            n += k
+        return n
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    launches = eng.kernel_launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    px_step_all = world * FRAMES * W * H
+    value = args.steps * px_step_all / 1e6 / (ms_total / 1e3)
+    n_kp = int(d_cnt.sum().item())
+
+    # ---- end to end through the C ABI with host buffers
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps * px_step_all / 1e6 / float(t_e2e.item())
+    d2h_per_frame = 64 + min(cap, 8192) * L.KEYPOINT_DTYPE.itemsize
+
+    # ---- per-kernel-class timing (separate instrumented pass, CUDA events on the engine's stream)
+    eng.set_profiling(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_device()
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+
+    if rank == 0:
+        ab = algorithmic_bytes_per_input_px()
+        peak, peak_src = measured_peak_gbs()
+        n_px = W * H
+        kinds = {}
+        for kind, (kms, cnt) in prof.items():
+            kinds[kind] = {"ms_per_frame": kms / (prof_steps * FRAMES), "launch_groups": cnt}
+        tot_ms = sum(k["ms_per_frame"] for k in kinds.values()) or 1.0
+        dom = "blur_octave0"
+        dom_ms = kinds[dom]["ms_per_frame"]
+        dom_bytes = ab["blur"][0] * n_px
+        achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        whole_gbs = ab["total"] * (value * 1e6 / world) / 1e9
+        for k in kinds.values():
+            k["share"] = k["ms_per_frame"] / tot_ms
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": FRAMES * W * H,
+                    "d2h_bytes_per_step": FRAMES * d2h_per_frame,
+                    "note": "sift_detect(): pinned host u8 frame in, ordered keypoint records out"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "octave-0 upsample+blur+DoG (" + dom + ")",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                         "whole_path": {"algorithmic_bytes_per_input_px": ab["total"],
+                                        "achieved": whole_gbs, "frac": whole_gbs / peak},
+                         "kernels": kinds},
+            "keypoints_per_step": n_kp,
+            "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg()
+            except Exception as ex:   # the baseline is a reported figure; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+                                        "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

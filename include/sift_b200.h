@@ -1,0 +1,244 @@
+/*
+ * sift_b200.h -- C ABI of the B200-native SIFT detection engine (libsift_b200.so).
+ *
+ * This is the drop-in boundary for the detection path of
+ * bingjetli/sift-scale-space-extrema-detection: what a Node N-API addon (see
+ * INTEGRATION.md), the Python host mirror (ctypes) and the parity tests bind.
+ * Plain C types only; no C++ types, exceptions or torch types cross it.
+ *
+ * Reference interfaces replaced (file:line into the reference tree):
+ *   coarse stage functions  background.js:71   computeGaussianScaleSpace
+ *                           background.js:258  computeDifferenceOfGaussians
+ *                           background.js:359  findCandidateKeypoints
+ *                           background.js:455  refineCandidateKeypoints
+ *   fine step functions     src/sift.js:72     SIFT_blurMatrix2DChunk
+ *                           src/sift.js:154    SIFT_subtractMatrix2DChunk
+ *                           src/sift.js:212    SIFT_findExtremas
+ *                           src/sift.js:333    SIFT_generateGradientVector
+ *                           src/sift.js:377    SIFT_generateHessianMatrix
+ *   helpers on the path     src/matrix2d.js:112 Matrix2D_linearResize
+ *                           src/matrix2d.js:464 Matrix2D_get3x3Inverse
+ *   transport replaced      src/worker.js:29-98 (postMessage requests) and
+ *                           background.js:14-50 (onmessage switch)
+ *
+ * Conventions
+ *   - every function returns an int status (SIFT_OK == 0); sift_last_error()
+ *     returns the text of the last failure on that context.
+ *   - the caller owns every host buffer; the library never retains a caller
+ *     pointer past the call.  Device pyramids are owned by the context and
+ *     stay valid until the next build/detect call on it.
+ *   - a context is single-threaded / non-reentrant: one context per GPU per
+ *     host thread (the reference's worker also handles one message at a time,
+ *     background.js:14-50).
+ *   - there is NO CPU fallback: without an sm_100 device sift_create fails.
+ *   - images are row-major; Matrix2D m[i][j] (row i, column j) == p[i*cols + j].
+ */
+#ifndef SIFT_B200_H
+#define SIFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SIFT_API __declspec(dllexport)
+#else
+#define SIFT_API __attribute__((visibility("default")))
+#endif
+
+/* ----------------------------------------------------------------- status */
+enum {
+  SIFT_OK = 0,
+  SIFT_ERR_BAD_ARGS = 1,       /* null pointer, non-positive size, sigma schedule not realisable */
+  SIFT_ERR_CUDA = 2,           /* a CUDA runtime call failed (text in sift_last_error) */
+  SIFT_ERR_CAPACITY = 3,       /* output capacity too small; *n_out holds the required count */
+  SIFT_ERR_UNSUPPORTED = 4,    /* size / parameter outside what the engine supports */
+  SIFT_ERR_NO_DEVICE = 5,      /* no CUDA device of compute capability 10.x */
+  SIFT_ERR_STATE = 6           /* stage called out of order (no pyramid built yet) */
+};
+
+/* ------------------------------------------------------------ pixel types */
+enum {
+  SIFT_U8 = 0,   /* grey bytes; float image = v / 255.0 (image-utils.js:114) */
+  SIFT_F32 = 1,  /* float image already in [0,1] */
+  SIFT_F64 = 2,  /* double image already in [0,1] (the reference's Matrix2D numbers) */
+  SIFT_RGBA8 = 3 /* ImageData bytes; grey = (0.299R + 0.587G + 0.114B) / 255.0 (image-utils.js:107-114) */
+};
+
+enum { SIFT_LEVEL_GAUSSIAN = 0, SIFT_LEVEL_DOG = 1 };
+
+/* ------------------------------------------------------------- parameters */
+/* Names follow the reference's request fields (worker.js:40-48, 90-98); the
+ * constants the reference hard-codes are defaulted fields. */
+typedef struct sift_params {
+  int32_t numberOfOctaves;       /* worker.js:33  default 5 */
+  int32_t scalesPerOctave;       /* worker.js:34  default 3 */
+  double minBlurLevel;           /* worker.js:35  default 0.8 */
+  double assumedBlur;            /* worker.js:36  default 0.5 */
+  double contrastThreshold;      /* sift.js:285 / background.js:572  0.015 */
+  double preFilterFactor;        /* sift.js:293  0.8 */
+  double edgeRatio;              /* background.js:598  10 */
+  int32_t maxIterations;         /* background.js:480  5 */
+  int32_t reserved0;
+  double offsetBound;            /* background.js:558  0.6 */
+  double minInterpixelDistance;  /* background.js:461  0.5 */
+} sift_params;
+
+/* ---------------------------------------------------------------- records */
+/* sift.js:274-278 extremum {x, y, value} plus where it was found
+ * (background.js:433-436 groups them per octave / scaleLevel). */
+typedef struct sift_candidate {
+  int32_t octave;
+  int32_t scaleLevel;
+  int32_t x;      /* column */
+  int32_t y;      /* row */
+  float value;    /* DoG value at the extremum */
+  int32_t reserved0;
+} sift_candidate; /* 24 bytes */
+
+/* background.js:619-628 refined keypoint record (octave, scaleLevel, localX,
+ * localY, absoluteSigma, absoluteX, absoluteY, interpolatedValue) plus the
+ * interpolation offsets in [s, m(row), n(col)] order, the DoG value of the
+ * originating extremum, and that extremum's position (the reference's output
+ * order is the candidate order: octave, scale, y, x). */
+typedef struct sift_keypoint {
+  int32_t octave;
+  int32_t scaleLevel;   /* post-move s */
+  int32_t localX;       /* post-move n (column) */
+  int32_t localY;       /* post-move m (row) */
+  double absoluteSigma;
+  double absoluteX;
+  double absoluteY;
+  double interpolatedValue;
+  float offset[3];      /* alpha: scale, row, column */
+  float dogValue;       /* extrema.value (background.js:565) */
+  int32_t candScale;
+  int32_t candX;
+  int32_t candY;
+  int32_t iterations;   /* quadratic-fit iterations before acceptance (0-based) */
+} sift_keypoint; /* 80 bytes */
+
+/* Per-call counters (the reference only console.logs these, background.js:581-672). */
+typedef struct sift_stats {
+  int32_t candidates;       /* extrema with abs(value) >= preFilterFactor * threshold */
+  int32_t lowContrastExtrema; /* extrema below it; -1 when not counted */
+  int32_t keypoints;        /* accepted */
+  int32_t rejLowContrast;   /* background.js:577 */
+  int32_t rejEdge;          /* background.js:599 */
+  int32_t rejLeftScale;     /* background.js:644 */
+  int32_t rejLeftRows;      /* background.js:651 */
+  int32_t rejLeftCols;      /* background.js:658 */
+  int32_t rejNoConvergence; /* loop ran out, background.js:480 */
+  int32_t rejSingular;      /* abs(det) < Number.EPSILON (matrix2d.js:482): the reference throws, we discard */
+  float msDevice;           /* CUDA-event time of the device work of this call */
+  int32_t kernelLaunches;   /* kernels launched by this call */
+} sift_stats;
+
+typedef struct sift_ctx sift_ctx;
+
+/* ------------------------------------------------------- context / errors */
+SIFT_API int sift_create(int device, sift_ctx **out);
+SIFT_API void sift_destroy(sift_ctx *ctx);
+SIFT_API const char *sift_last_error(const sift_ctx *ctx);   /* ctx may be NULL: last create error */
+SIFT_API const char *sift_version(void);
+SIFT_API void sift_default_params(sift_params *p);           /* worker.js:33-37 defaults */
+SIFT_API int sift_synchronize(sift_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of the context is issued on. */
+SIFT_API void *sift_stream(sift_ctx *ctx);
+SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for the context */
+
+/* Per-kernel-class device timing (CUDA events around each launch group on sift_stream).
+ * Off by default; bench.py turns it on for a separate instrumented pass. */
+enum {
+  SIFT_PROF_BLUR_OCT0 = 0,  /* octave 0: upsample + blur + DoG + seed */
+  SIFT_PROF_BLUR_OCT1 = 1,  /* octave 1 */
+  SIFT_PROF_BLUR_HIGH = 2,  /* octaves >= 2 */
+  SIFT_PROF_SCAN = 3,       /* extremum scan + compaction */
+  SIFT_PROF_REFINE = 4,     /* refinement */
+  SIFT_PROF_NKINDS = 5
+};
+SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled);
+/* Sums (ms) and counts of the spans recorded since the last call; synchronises the stream. */
+SIFT_API int sift_get_profile(sift_ctx *ctx, float *ms_by_kind, int *launch_groups_by_kind, int n_kinds);
+
+/* ----------------------------------------------------- fused detect (hot) */
+/* Whole path: 2x upsample, pyramid, DoG, extrema, refinement; HOST buffers in
+ * and out (copies inside).  Keypoints come back in the reference's order.
+ * pitch_bytes == 0 means dense rows.  out may be NULL with cap 0 to count. */
+SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width, int height,
+                         size_t pitch_bytes, const sift_params *params,
+                         sift_keypoint *out, int cap, int *n_out, sift_stats *stats);
+
+/* Same, image already in device memory; keypoints stay in device memory
+ * (d_out, unordered unless `ordered` != 0) and *d_count (device int) receives
+ * the count.  Asynchronous on sift_stream(ctx). */
+SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
+                                size_t pitch_bytes, const sift_params *params,
+                                sift_keypoint *d_out, int cap, int *d_count, int ordered);
+
+/* n_images equally sized host images, image i at image + i*image_stride_bytes.
+ * Keypoints of image i are out[offsets[i] .. offsets[i+1]) (offsets has
+ * n_images+1 entries). */
+SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int width, int height,
+                               size_t pitch_bytes, size_t image_stride_bytes, int n_images,
+                               const sift_params *params, sift_keypoint *out, int cap,
+                               int *offsets, sift_stats *stats);
+
+/* -------------------------------------------------- coarse stage functions */
+/* background.js:71  -- builds Gaussian levels (and, fused, the DoG levels) on the device. */
+SIFT_API int sift_build_scale_space(sift_ctx *ctx, const void *image, int dtype, int width, int height,
+                                    size_t pitch_bytes, const sift_params *params);
+/* background.js:258 -- DoG of the pyramid held by the context (already formed
+ * from the unrounded accumulators by sift_build_scale_space; this validates state). */
+SIFT_API int sift_build_dog(sift_ctx *ctx);
+/* background.js:359 -- candidates in reference order. low / n_low may be NULL.  params may be
+ * NULL (the context's); only contrastThreshold and preFilterFactor are read from it. */
+SIFT_API int sift_find_candidates(sift_ctx *ctx, const sift_params *params, sift_candidate *out, int cap,
+                                  int *n_out, sift_candidate *low, int low_cap, int *n_low);
+/* background.js:455 -- refine a caller-supplied candidate list against the DoG held by the context.
+ * params may be NULL; only the threshold / position fields are read (contrastThreshold, edgeRatio,
+ * maxIterations, offsetBound, minBlurLevel, minInterpixelDistance): the reference passes minBlurLevel
+ * and minInterpixelDistance with this request (worker.js:90-98). */
+SIFT_API int sift_refine(sift_ctx *ctx, const sift_params *params, const sift_candidate *cands, int n_cands,
+                         sift_keypoint *out, int cap, int *n_out, sift_stats *stats);
+
+/* Pyramid inspection (scale_space[o][s] = {blurLevel, image}, background.js:57-70). */
+SIFT_API int sift_get_pyramid_info(const sift_ctx *ctx, int *octaves, int *levels_per_octave);
+SIFT_API int sift_get_octave_size(const sift_ctx *ctx, int octave, int *width, int *height);
+SIFT_API int sift_get_blur_level(const sift_ctx *ctx, int kind, int octave, int level, double *blur_level);
+SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, float *dst /* h*w dense */);
+/* Replace a DoG level of the held pyramid with caller data (used by the host mirror
+ * when refineCandidateKeypoints / findCandidateKeypoints receive foreign matrices). */
+SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, const sift_params *params);
+SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, const float *src);
+
+/* ----------------------------------------------------- fine step functions */
+/* src/sift.js:72  float64 in / out like Matrix2D; half-open chunk; writes only the chunk of output. */
+SIFT_API int sift_blur_chunk(sift_ctx *ctx, const double *input, int rows, int cols, double *output,
+                             double sigma, int x1, int y1, int x2, int y2);
+/* src/sift.js:154  output = a - b over the chunk. */
+SIFT_API int sift_subtract_chunk(sift_ctx *ctx, const double *a, const double *b, int rows, int cols,
+                                 double *output, int x1, int y1, int x2, int y2);
+/* src/sift.js:212  strict 26-neighbour extrema of the middle image, raster order. */
+SIFT_API int sift_find_extremas(sift_ctx *ctx, const double *d0, const double *d1, const double *d2,
+                                int rows, int cols, int scales_per_octave, double contrast_threshold,
+                                double prefilter_factor,
+                                int32_t *cand_xy, double *cand_value, int cand_cap, int *n_cand,
+                                int32_t *low_xy, double *low_value, int low_cap, int *n_low);
+/* src/sift.js:333 and :377 on three consecutive DoG images (s-1, s, s+1): g[3] in
+ * [s, m, n] order and the symmetric 3x3 Hessian, row-major. */
+SIFT_API int sift_gradient_hessian(sift_ctx *ctx, const double *dm, const double *dc, const double *dp,
+                                   int rows, int cols, int m, int n, double g[3], double h[9]);
+/* src/matrix2d.js:112  nearest-neighbour resample; out must hold the resized image
+ * (sift_resize_dims gives its shape). */
+SIFT_API int sift_resize_dims(int rows, int cols, double sampling_rate, int *out_rows, int *out_cols);
+SIFT_API int sift_linear_resize(sift_ctx *ctx, const double *input, int rows, int cols,
+                                double sampling_rate, double *output);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFT_B200_H */

@@ -1,0 +1,84 @@
+// common.cuh -- shared declarations between the engine (engine.cu) and the kernel
+// translation units.  sm_100a only; no fallbacks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sift_b200.h"
+
+#define SIFT_MAX_OCTAVES 12
+#define SIFT_MAX_LEVELS 12   // scalesPerOctave + 3 <= 12
+
+// Device-side description of one octave of the pyramid held by a context.
+// All planes are fp32 with a common pitch (in elements, multiple of 32 so that
+// every row starts on a 128-byte line); the seed (level 0 of octaves >= 1,
+// background.js:114-130) is additionally kept unrounded in fp64 so that the next
+// octave is blurred from the same numbers the reference blurs from.
+struct OctaveDev {
+  int w, h;            // columns, rows of this octave
+  int pitch;           // elements per row of the fp32 planes
+  int nlev;            // Gaussian levels (spo + 3)
+  float *gauss[SIFT_MAX_LEVELS];
+  float *dog[SIFT_MAX_LEVELS];
+  double *seed64;      // h * w dense, octaves >= 1 (nullptr for octave 0)
+};
+
+// Per-level blur description (host computed, background.js:156-177 + sift.js:38).
+struct LevelPlan {
+  double blurLevel;    // target sigma (scale_space[o][s].blurLevel)
+  double offsetSigma;  // sigma of the kernel applied to the octave base (0 for a seed level)
+  int radius;          // round(3 * offsetSigma), sift.js:38
+  int woff;            // offset of this level's padded 1D weights in the weight buffer
+};
+
+// Counter block in device memory (one per context).
+struct Counters {
+  int n_cand;          // candidates appended
+  int n_low;           // low-contrast extrema (when counted)
+  int n_kp;            // keypoints appended
+  int outcomes[8];     // refine outcomes, index = REFINE_* below
+  int pad[5];
+};
+
+enum {
+  REFINE_ACCEPTED = 0, REFINE_LOW_CONTRAST = 1, REFINE_EDGE = 2, REFINE_LEFT_SCALE = 3,
+  REFINE_LEFT_ROWS = 4, REFINE_LEFT_COLS = 5, REFINE_NO_CONVERGENCE = 6, REFINE_SINGULAR = 7
+};
+
+// Number of zero weights appended after each level's 2R+1 taps so that the
+// register-rotating inner loops can run past the end branch-free.
+#define SIFT_WPAD 16
+
+// ---- launchers implemented in the kernel translation units --------------------
+// blur_generic.cu
+void launch_hblur(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int src_h,
+                  int upsample, int w, int hrows, const double *d_weights, const LevelPlan *plans, int first_level,
+                  int nlev, double *const *T /* nlev device planes hrows*w */, double **d_Tptrs);
+void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
+                  const LevelPlan *plans, int first_level, double *const *d_Tptrs_dev,
+                  const OctaveDev *next /* may be null */, int spo, int keep_gauss);
+void launch_blur_plane_f64(cudaStream_t st, const double *d_in, int rows, int cols, double *d_tmp, double *d_out,
+                           const double *d_w, int radius, int x1, int y1, int x2, int y2);
+void launch_subtract_f64(cudaStream_t st, const double *a, const double *b, double *out, int cols,
+                         int x1, int y1, int x2, int y2);
+void launch_resize_f64(cudaStream_t st, const double *in, int rows, int cols, double rate, double *out,
+                       int orows, int ocols);
+void launch_seed_to_f32(cudaStream_t st, const double *seed, int w, int h, float *dst, int pitch);
+
+// scan.cu
+void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int spo, double pix_threshold,
+                        int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,
+                        Counters *ctr);
+void launch_scan_f64(cudaStream_t st, const double *d0, const double *d1, const double *d2, int rows, int cols,
+                     double pix_threshold, int32_t *cand_xy, double *cand_val, int cand_cap,
+                     int32_t *low_xy, double *low_val, int low_cap, int *counts /* [2] */);
+
+// refine.cu (compiled with --fmad=false: the reference never fuses multiply-add)
+struct RefineParams {
+  int spo, ndog, max_iter;
+  double offset_bound, contrast_thr, edge_thr, min_blur, min_interpixel;
+};
+void launch_refine(cudaStream_t st, const OctaveDev *d_octs, int n_octs, const sift_candidate *cand,
+                   const int *d_ncand, int n_cand_host /* -1: read d_ncand */, int cand_cap, RefineParams rp,
+                   sift_keypoint *out, int cap, Counters *ctr);
+void launch_grad_hess_f64(cudaStream_t st, const double *dm, const double *dc, const double *dp, int cols,
+                          int m, int n, double *out12);

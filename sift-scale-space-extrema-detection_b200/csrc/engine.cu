@@ -1,0 +1,1020 @@
+// engine.cu -- context, planning (sigma schedule, radii, weights), device memory
+// and the C ABI of include/sift_b200.h.  Host-side restatement of the reference's
+// pipeline driver (background.js:71-237 octave/scale loop, :258 DoG loop, :359
+// candidate loop, :455 refinement loop); the arithmetic lives in the kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+#define SIFT_B200_VERSION "sift_b200 0.1.0 (sm_100a)"
+
+static std::string g_create_error;
+
+struct Scratch {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct sift_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- optional per-kernel-class CUDA-event profiling (sift_set_profiling)
+  bool profiling = false;
+  struct ProfSpan { int kind; cudaEvent_t a, b; };
+  std::vector<ProfSpan> spans;
+  size_t spans_used = 0;
+
+  // ---- plan (depends on params + input size)
+  bool plan_valid = false;
+  sift_params prm;
+  int in_w = 0, in_h = 0;
+  int n_oct = 0, nlev = 0;
+  LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
+  double dog_blur[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
+  std::vector<double> h_weights;
+  double *d_weights = nullptr;
+  size_t d_weights_cap = 0;
+  OctaveDev octs[SIFT_MAX_OCTAVES];
+  OctaveDev *d_octs = nullptr;
+
+  // ---- device arenas (grow only)
+  Scratch planes, seeds, tbuf, image, cand, low, outbuf, misc[6];
+  int cand_cap = 0, low_cap = 0, kp_cap = 0;
+  void *h_out = nullptr;      // pinned mirror of outbuf
+  size_t h_out_cap = 0;
+  void *h_cand = nullptr;     // pinned candidate staging
+  size_t h_cand_cap = 0;
+
+  bool pyramid_built = false;
+  int keep_gauss = 1;
+  Counters last;
+};
+
+// ------------------------------------------------------------------ helpers ----
+static int fail(sift_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, SIFT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int grow(sift_ctx *ctx, Scratch &s, size_t bytes)
+{
+  if (bytes <= s.cap) return SIFT_OK;
+  if (s.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
+  bytes = (bytes + 255) & ~(size_t)255;
+  CK(cudaMalloc(&s.p, bytes));
+  s.cap = bytes;
+  return SIFT_OK;
+}
+
+static int grow_pinned(sift_ctx *ctx, void **p, size_t *cap, size_t bytes)
+{
+  if (bytes <= *cap) return SIFT_OK;
+  if (*p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
+  CK(cudaMallocHost(p, bytes));
+  *cap = bytes;
+  return SIFT_OK;
+}
+
+// Per-kernel-class timing: a pair of events around each launch group, summed at read-out.
+static void prof_begin(sift_ctx *ctx, int kind)
+{
+  if (!ctx->profiling) return;
+  if (ctx->spans_used == ctx->spans.size()) {
+    sift_ctx::ProfSpan sp; sp.kind = kind;
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    ctx->spans.push_back(sp);
+  }
+  ctx->spans[ctx->spans_used].kind = kind;
+  cudaEventRecord(ctx->spans[ctx->spans_used].a, ctx->stream);
+}
+static void prof_end(sift_ctx *ctx)
+{
+  if (!ctx->profiling) return;
+  cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->stream);
+  ctx->spans_used++;
+}
+
+static double js_round(double x) { double f = std::floor(x); return (x - f >= 0.5) ? f + 1.0 : f; }
+
+static size_t dtype_size(int dtype)
+{
+  switch (dtype) {
+    case SIFT_U8: return 1;
+    case SIFT_F32: return 4;
+    case SIFT_F64: return 8;
+    case SIFT_RGBA8: return 4;
+  }
+  return 0;
+}
+
+// Normalised 1D Gaussian taps w[0..2R]: the reference's 2D kernel (sift.js:31-67) is
+// g(i,j)/sum with g = exp(-(i^2+j^2)/(2 sigma^2))/(2 pi sigma^2) = outer product of these.
+static void gaussian_taps(double sigma, int R, double *w)
+{
+  double s = 0;
+  for (int i = 0; i <= 2 * R; i++) {
+    const double d = (double)(i - R);
+    w[i] = std::exp(((d * d) / (sigma * sigma)) * -0.5);
+    s += w[i];
+  }
+  for (int i = 0; i <= 2 * R; i++) w[i] /= s;
+}
+
+static bool same_params(const sift_params &a, const sift_params &b)
+{
+  return a.numberOfOctaves == b.numberOfOctaves && a.scalesPerOctave == b.scalesPerOctave &&
+         a.minBlurLevel == b.minBlurLevel && a.assumedBlur == b.assumedBlur;
+}
+
+// background.js:84-177: sizes, blur levels, offset sigmas, radii; allocates the pyramid.
+static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
+{
+  if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "params is NULL");
+  if (w < 1 || h < 1) return fail(ctx, SIFT_ERR_BAD_ARGS, "image size %dx%d", w, h);
+  if (p->numberOfOctaves < 1 || p->numberOfOctaves > SIFT_MAX_OCTAVES)
+    return fail(ctx, SIFT_ERR_UNSUPPORTED, "numberOfOctaves %d outside 1..%d", p->numberOfOctaves, SIFT_MAX_OCTAVES);
+  if (p->scalesPerOctave < 1 || p->scalesPerOctave + 3 > SIFT_MAX_LEVELS)
+    return fail(ctx, SIFT_ERR_UNSUPPORTED, "scalesPerOctave %d outside 1..%d", p->scalesPerOctave, SIFT_MAX_LEVELS - 3);
+  if ((int64_t)w * 2 > (1 << 30) || (int64_t)h * 2 > (1 << 30))
+    return fail(ctx, SIFT_ERR_UNSUPPORTED, "image too large");
+  if (ctx->plan_valid && ctx->in_w == w && ctx->in_h == h && same_params(ctx->prm, *p)) {
+    ctx->prm = *p;   // thresholds may differ; they do not affect the plan
+    return SIFT_OK;
+  }
+  ctx->plan_valid = false;
+  ctx->pyramid_built = false;
+  const int spo = p->scalesPerOctave, nlev = spo + 3, n_oct = p->numberOfOctaves;
+  const double k = std::pow(2.0, 1.0 / spo);                                   // background.js:100
+
+  // sizes: octave 0 is the 2x nearest-neighbour upsample (background.js:84), then ceil halves (matrix2d.js:119)
+  int ow[SIFT_MAX_OCTAVES], oh[SIFT_MAX_OCTAVES];
+  ow[0] = 2 * w; oh[0] = 2 * h;
+  for (int o = 1; o < n_oct; o++) { ow[o] = (ow[o - 1] + 1) / 2; oh[o] = (oh[o - 1] + 1) / 2; }
+
+  ctx->h_weights.clear();
+  double base_blur = p->minBlurLevel;                                          // background.js:89
+  for (int o = 0; o < n_oct; o++) {
+    for (int s = 0; s < nlev; s++) {
+      LevelPlan &lp = ctx->plans[o][s];
+      if (o > 0 && s == 0) {
+        base_blur = ctx->plans[o - 1][spo].blurLevel;                          // background.js:122
+        lp.blurLevel = base_blur; lp.offsetSigma = 0; lp.radius = 0; lp.woff = -1;
+        continue;
+      }
+      const double current_k = std::pow(k, (double)s);                         // :157
+      const double target = base_blur * current_k;                             // :173
+      const double base_sigma = (o == 0) ? p->assumedBlur : base_blur;         // :174-176
+      const double off = std::sqrt((target * target) - (base_sigma * base_sigma));   // :177
+      if (!(off > 0) || !std::isfinite(off))
+        return fail(ctx, SIFT_ERR_BAD_ARGS,
+                    "sigma schedule not realisable at octave %d level %d (target %g, base %g)", o, s, target, base_sigma);
+      lp.blurLevel = target; lp.offsetSigma = off;
+      lp.radius = (int)js_round(3 * off);                                      // sift.js:38
+      if (lp.radius > 4096) return fail(ctx, SIFT_ERR_UNSUPPORTED, "kernel radius %d too large", lp.radius);
+      lp.woff = (int)ctx->h_weights.size();
+      ctx->h_weights.resize(ctx->h_weights.size() + 2 * lp.radius + 1 + SIFT_WPAD, 0.0);
+      gaussian_taps(off, lp.radius, ctx->h_weights.data() + lp.woff);
+    }
+    for (int s = 1; s < nlev; s++) ctx->dog_blur[o][s - 1] = ctx->plans[o][s - 1].blurLevel;   // background.js:327
+  }
+
+  // ---- device memory
+  size_t plane_elems = 0, seed_elems = 0, t_bytes = 0;
+  for (int o = 0; o < n_oct; o++) {
+    const int pitch = (ow[o] + 31) & ~31;
+    plane_elems += (size_t)(2 * nlev - 1) * oh[o] * pitch;
+    if (o > 0) seed_elems += (size_t)ow[o] * oh[o];
+    const size_t trows = (o == 0) ? (size_t)h : (size_t)oh[o];
+    const size_t tl = (o == 0) ? nlev : nlev - 1;
+    t_bytes = std::max(t_bytes, tl * trows * ow[o] * sizeof(double));
+  }
+  int rc;
+  if ((rc = grow(ctx, ctx->planes, plane_elems * sizeof(float)))) return rc;
+  if ((rc = grow(ctx, ctx->seeds, std::max<size_t>(seed_elems, 1) * sizeof(double)))) return rc;
+  if ((rc = grow(ctx, ctx->tbuf, t_bytes))) return rc;
+  const size_t wbytes = ctx->h_weights.size() * sizeof(double);
+  if (wbytes > ctx->d_weights_cap) {
+    if (ctx->d_weights) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->d_weights)); }
+    CK(cudaMalloc((void **)&ctx->d_weights, wbytes));
+    ctx->d_weights_cap = wbytes;
+  }
+  CK(cudaMemcpyAsync(ctx->d_weights, ctx->h_weights.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
+
+  float *pp = (float *)ctx->planes.p;
+  double *sp = (double *)ctx->seeds.p;
+  for (int o = 0; o < n_oct; o++) {
+    OctaveDev &od = ctx->octs[o];
+    memset(&od, 0, sizeof od);
+    od.w = ow[o]; od.h = oh[o]; od.pitch = (ow[o] + 31) & ~31; od.nlev = nlev;
+    const size_t pe = (size_t)od.h * od.pitch;
+    for (int s = 0; s < nlev; s++) { od.gauss[s] = pp; pp += pe; }
+    for (int s = 0; s < nlev - 1; s++) { od.dog[s] = pp; pp += pe; }
+    if (o > 0) { od.seed64 = sp; sp += (size_t)od.w * od.h; }
+  }
+  if (!ctx->d_octs) CK(cudaMalloc((void **)&ctx->d_octs, sizeof(OctaveDev) * SIFT_MAX_OCTAVES));
+  CK(cudaMemcpyAsync(ctx->d_octs, ctx->octs, sizeof(OctaveDev) * n_oct, cudaMemcpyHostToDevice, ctx->stream));
+  // cudaMemcpyAsync from pageable memory is staged before returning, so h_weights / octs may change afterwards.
+
+  // candidate / keypoint capacity: extrema are ~3e-4 of the voxels on the synthetic frames
+  const int want = (int)std::min<int64_t>(std::max<int64_t>(16384, ((int64_t)w * h) / 8), 1 << 26);
+  if (want > ctx->cand_cap) {
+    if ((rc = grow(ctx, ctx->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
+    ctx->cand_cap = want;
+  }
+  if (want > ctx->kp_cap) {
+    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    ctx->kp_cap = want;
+  }
+  ctx->prm = *p; ctx->in_w = w; ctx->in_h = h; ctx->n_oct = n_oct; ctx->nlev = nlev;
+  ctx->plan_valid = true;
+  return SIFT_OK;
+}
+
+static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->outbuf.p; }
+static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->outbuf.p + sizeof(Counters)); }
+
+// Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
+static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
+{
+  const int spo = ctx->prm.scalesPerOctave;
+  cudaStream_t st = ctx->stream;
+  for (int o = 0; o < ctx->n_oct; o++) {
+    const OctaveDev &od = ctx->octs[o];
+    const int first = (o == 0) ? 0 : 1;
+    const int hrows = (o == 0) ? ctx->in_h : od.h;
+    double *T[SIFT_MAX_LEVELS];
+    for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->tbuf.p + (size_t)i * hrows * od.w;
+    prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
+    if (o == 0)
+      launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
+                   ctx->plans[o], first, ctx->nlev, T, nullptr);
+    else
+      launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
+                   ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
+    launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T,
+                 (o + 1 < ctx->n_oct) ? &ctx->octs[o + 1] : nullptr, spo, ctx->keep_gauss);
+    ctx->launches += 2;
+    prof_end(ctx);
+  }
+  CK(cudaGetLastError());
+  ctx->pyramid_built = true;
+  return SIFT_OK;
+}
+
+static double contrast_threshold(const sift_params &p)
+{
+  // sift.js:285 / background.js:572
+  return ((std::pow(2.0, 1.0 / p.scalesPerOctave) - 1) / (std::pow(2.0, 1.0 / 3) - 1)) * p.contrastThreshold;
+}
+
+static int run_scan(sift_ctx *ctx, int count_low, const sift_params *thr = nullptr)
+{
+  sift_params tp = ctx->prm;
+  if (thr) { tp.contrastThreshold = thr->contrastThreshold; tp.preFilterFactor = thr->preFilterFactor; }
+  const double pix_thr = contrast_threshold(tp) * tp.preFilterFactor;               // sift.js:293
+  prof_begin(ctx, SIFT_PROF_SCAN);
+  for (int o = 0; o < ctx->n_oct; o++) {
+    launch_scan_octave(ctx->stream, ctx->octs[o], o, ctx->prm.scalesPerOctave, pix_thr, count_low,
+                       (sift_candidate *)ctx->cand.p, ctx->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
+                       dev_counters(ctx));
+    ctx->launches += 1;
+  }
+  prof_end(ctx);
+  CK(cudaGetLastError());
+  return SIFT_OK;
+}
+
+static RefineParams refine_params(const sift_ctx *ctx, const sift_params *over)
+{
+  sift_params p = ctx->prm;
+  if (over) {
+    p.contrastThreshold = over->contrastThreshold; p.edgeRatio = over->edgeRatio;
+    p.maxIterations = over->maxIterations; p.offsetBound = over->offsetBound;
+    p.minBlurLevel = over->minBlurLevel; p.minInterpixelDistance = over->minInterpixelDistance;
+  }
+  RefineParams rp;
+  rp.spo = ctx->prm.scalesPerOctave;
+  rp.ndog = ctx->nlev - 1;
+  rp.max_iter = p.maxIterations;
+  rp.offset_bound = p.offsetBound;
+  rp.contrast_thr = contrast_threshold(p);
+  rp.edge_thr = ((p.edgeRatio + 1) * (p.edgeRatio + 1)) / p.edgeRatio;   // background.js:598
+  rp.min_blur = p.minBlurLevel;
+  rp.min_interpixel = p.minInterpixelDistance;
+  return rp;
+}
+
+static int run_refine(sift_ctx *ctx, int n_cand_host, sift_keypoint *d_out, int cap, const sift_params *over = nullptr)
+{
+  prof_begin(ctx, SIFT_PROF_REFINE);
+  launch_refine(ctx->stream, ctx->d_octs, ctx->n_oct, (const sift_candidate *)ctx->cand.p,
+                &dev_counters(ctx)->n_cand, n_cand_host, ctx->cand_cap, refine_params(ctx, over), d_out, cap,
+                dev_counters(ctx));
+  prof_end(ctx);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return SIFT_OK;
+}
+
+static void fill_stats(sift_stats *s, const Counters &c, int count_low, float ms, int launches)
+{
+  if (!s) return;
+  s->candidates = c.n_cand;
+  s->lowContrastExtrema = count_low ? c.n_low : -1;
+  s->keypoints = c.outcomes[REFINE_ACCEPTED];
+  s->rejLowContrast = c.outcomes[REFINE_LOW_CONTRAST];
+  s->rejEdge = c.outcomes[REFINE_EDGE];
+  s->rejLeftScale = c.outcomes[REFINE_LEFT_SCALE];
+  s->rejLeftRows = c.outcomes[REFINE_LEFT_ROWS];
+  s->rejLeftCols = c.outcomes[REFINE_LEFT_COLS];
+  s->rejNoConvergence = c.outcomes[REFINE_NO_CONVERGENCE];
+  s->rejSingular = c.outcomes[REFINE_SINGULAR];
+  s->msDevice = ms;
+  s->kernelLaunches = launches;
+}
+
+static inline uint64_t cand_key(int o, int s, int y, int x)
+{
+  return ((uint64_t)(uint32_t)o << 58) | ((uint64_t)(uint32_t)s << 52) | ((uint64_t)(uint32_t)y << 26) | (uint64_t)(uint32_t)x;
+}
+
+// Reference output order = candidate order: octave, scale, row, column (background.js:468-471, sift.js:221-222).
+static void sort_keypoints(sift_keypoint *k, int n)
+{
+  std::sort(k, k + n, [](const sift_keypoint &a, const sift_keypoint &b) {
+    return cand_key(a.octave, a.candScale, a.candY, a.candX) < cand_key(b.octave, b.candScale, b.candY, b.candX);
+  });
+}
+
+static void sort_candidates(sift_candidate *c, int n)
+{
+  std::sort(c, c + n, [](const sift_candidate &a, const sift_candidate &b) {
+    return cand_key(a.octave, a.scaleLevel, a.y, a.x) < cand_key(b.octave, b.scaleLevel, b.y, b.x);
+  });
+}
+
+// Upload a host image into ctx->image (dense rows).
+static int upload_image(sift_ctx *ctx, const void *image, int dtype, int w, int h, size_t pitch_bytes,
+                        size_t *dev_pitch)
+{
+  const size_t es = dtype_size(dtype);
+  if (!es) return fail(ctx, SIFT_ERR_BAD_ARGS, "unknown dtype %d", dtype);
+  const size_t row = (size_t)w * es;
+  if (pitch_bytes == 0) pitch_bytes = row;
+  if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
+  int rc;
+  if ((rc = grow(ctx, ctx->image, row * h))) return rc;
+  if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->image.p, image, row * h, cudaMemcpyHostToDevice, ctx->stream));
+  else CK(cudaMemcpy2DAsync(ctx->image.p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->stream));
+  *dev_pitch = row;
+  return SIFT_OK;
+}
+
+// Download counters + keypoints (one copy in the common case), returns them sorted in h_out.
+#define FIRST_CHUNK 8192
+static int download_keypoints(sift_ctx *ctx, Counters *c, sift_keypoint **kps)
+{
+  int rc;
+  const size_t first = sizeof(Counters) + (size_t)std::min(ctx->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+  if ((rc = grow_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->h_out, ctx->outbuf.p, first, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *c = *(Counters *)ctx->h_out;
+  const int n = std::min(c->n_kp, ctx->kp_cap);
+  if (n > FIRST_CHUNK) {
+    CK(cudaMemcpyAsync((char *)ctx->h_out + first, (char *)ctx->outbuf.p + first,
+                       (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *kps = (sift_keypoint *)((char *)ctx->h_out + sizeof(Counters));
+  return SIFT_OK;
+}
+
+// scan + refine with automatic growth of the candidate buffer; leaves sorted keypoints in h_out.
+static int scan_refine_download(sift_ctx *ctx, Counters *c, sift_keypoint **kps, int count_low)
+{
+  int rc;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+    if ((rc = run_scan(ctx, count_low))) return rc;
+    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->kp_cap))) return rc;
+    if ((rc = download_keypoints(ctx, c, kps))) return rc;
+    if (c->n_cand <= ctx->cand_cap && c->n_kp <= ctx->kp_cap) {
+      sort_keypoints(*kps, c->n_kp);
+      return SIFT_OK;
+    }
+    const int want = std::max(c->n_cand, c->n_kp) + 1024;
+    if ((rc = grow(ctx, ctx->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
+    ctx->cand_cap = want;
+    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    ctx->kp_cap = want;
+  }
+  return fail(ctx, SIFT_ERR_CAPACITY, "candidate buffer kept overflowing");
+}
+
+// ------------------------------------------------------------------- C ABI ----
+extern "C" {
+
+SIFT_API const char *sift_version(void) { return SIFT_B200_VERSION; }
+
+SIFT_API void sift_default_params(sift_params *p)
+{
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  p->numberOfOctaves = 5;          // worker.js:33
+  p->scalesPerOctave = 3;          // worker.js:34
+  p->minBlurLevel = 0.8;           // worker.js:35
+  p->assumedBlur = 0.5;            // worker.js:36
+  p->contrastThreshold = 0.015;    // sift.js:285
+  p->preFilterFactor = 0.8;        // sift.js:293
+  p->edgeRatio = 10.0;             // background.js:598
+  p->maxIterations = 5;            // background.js:480
+  p->offsetBound = 0.6;            // background.js:558
+  p->minInterpixelDistance = 0.5;  // background.js:461
+}
+
+SIFT_API int sift_create(int device, sift_ctx **out)
+{
+  if (!out) return fail(nullptr, SIFT_ERR_BAD_ARGS, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SIFT_ERR_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, SIFT_ERR_BAD_ARGS, "device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return fail(nullptr, SIFT_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, SIFT_ERR_NO_DEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major,
+                prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SIFT_ERR_CUDA, "cudaSetDevice failed");
+  sift_ctx *c = new sift_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, SIFT_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  sift_default_params(&c->prm);
+  *out = c;
+  return SIFT_OK;
+}
+
+SIFT_API void sift_destroy(sift_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  Scratch *all[] = { &c->planes, &c->seeds, &c->tbuf, &c->image, &c->cand, &c->low, &c->outbuf,
+                     &c->misc[0], &c->misc[1], &c->misc[2], &c->misc[3], &c->misc[4], &c->misc[5] };
+  for (Scratch *s : all) if (s->p) cudaFree(s->p);
+  if (c->d_weights) cudaFree(c->d_weights);
+  if (c->d_octs) cudaFree(c->d_octs);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_cand) cudaFreeHost(c->h_cand);
+  for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+SIFT_API const char *sift_last_error(const sift_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+SIFT_API int sift_synchronize(sift_ctx *ctx)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->profiling = enabled != 0;
+  ctx->spans_used = 0;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_get_profile(sift_ctx *ctx, float *ms_by_kind, int *launch_groups_by_kind, int n_kinds)
+{
+  if (!ctx || !ms_by_kind || n_kinds < SIFT_PROF_NKINDS) return SIFT_ERR_BAD_ARGS;
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_kinds; i++) { ms_by_kind[i] = 0.f; if (launch_groups_by_kind) launch_groups_by_kind[i] = 0; }
+  for (size_t i = 0; i < ctx->spans_used; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b);
+    ms_by_kind[ctx->spans[i].kind] += ms;
+    if (launch_groups_by_kind) launch_groups_by_kind[ctx->spans[i].kind]++;
+  }
+  ctx->spans_used = 0;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width, int height, size_t pitch_bytes,
+                         const sift_params *params, sift_keypoint *out, int cap, int *n_out, sift_stats *stats)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!image || !n_out) return fail(ctx, SIFT_ERR_BAD_ARGS, "image / n_out is NULL");
+  if (cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "out is NULL with cap %d", cap);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  const int64_t l0 = ctx->launches;
+  size_t dpitch;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
+  if ((rc = run_pyramid(ctx, ctx->image.p, dtype, dpitch))) return rc;
+  Counters c;
+  sift_keypoint *kps;
+  if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->last = c;
+  fill_stats(stats, c, 0, ms, (int)(ctx->launches - l0));
+  *n_out = c.n_kp;
+  if (c.n_kp > cap) {
+    if (cap > 0) memcpy(out, kps, (size_t)cap * sizeof(sift_keypoint));
+    return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
+  }
+  if (c.n_kp) memcpy(out, kps, (size_t)c.n_kp * sizeof(sift_keypoint));
+  return SIFT_OK;
+}
+
+__global__ void copy_count_kernel(const Counters *c, int *dst) { *dst = c->n_kp; }
+
+SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
+                                size_t pitch_bytes, const sift_params *params, sift_keypoint *d_out, int cap,
+                                int *d_count, int ordered)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!d_image || !d_out || !d_count || cap <= 0) return fail(ctx, SIFT_ERR_BAD_ARGS, "NULL device pointer or cap <= 0");
+  if (ordered) return fail(ctx, SIFT_ERR_UNSUPPORTED, "device-side ordering is not implemented yet; use sift_detect");
+  const size_t es = dtype_size(dtype);
+  if (!es) return fail(ctx, SIFT_ERR_BAD_ARGS, "unknown dtype %d", dtype);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  if (pitch_bytes == 0) pitch_bytes = (size_t)width * es;
+  if ((rc = run_pyramid(ctx, d_image, dtype, pitch_bytes))) return rc;
+  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+  if ((rc = run_scan(ctx, 0))) return rc;
+  if ((rc = run_refine(ctx, -1, d_out, cap))) return rc;
+  copy_count_kernel<<<1, 1, 0, ctx->stream>>>(dev_counters(ctx), d_count);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return SIFT_OK;
+}
+
+SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int width, int height,
+                               size_t pitch_bytes, size_t image_stride_bytes, int n_images,
+                               const sift_params *params, sift_keypoint *out, int cap, int *offsets,
+                               sift_stats *stats)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!images || !offsets || n_images < 0) return fail(ctx, SIFT_ERR_BAD_ARGS, "images / offsets NULL or n_images < 0");
+  sift_stats total;
+  memset(&total, 0, sizeof total);
+  total.lowContrastExtrema = -1;
+  int n = 0, rc = SIFT_OK, overflow = 0;
+  offsets[0] = 0;
+  for (int i = 0; i < n_images; i++) {
+    int ni = 0;
+    sift_stats si;
+    const void *img = (const char *)images + (size_t)i * image_stride_bytes;
+    const int room = overflow ? 0 : std::max(0, cap - n);
+    rc = sift_detect(ctx, img, dtype, width, height, pitch_bytes, params, room ? out + n : nullptr, room, &ni, &si);
+    if (rc == SIFT_ERR_CAPACITY) overflow = 1;
+    else if (rc != SIFT_OK) return rc;
+    n += ni;
+    offsets[i + 1] = n;
+    total.candidates += si.candidates; total.keypoints += si.keypoints;
+    total.rejLowContrast += si.rejLowContrast; total.rejEdge += si.rejEdge;
+    total.rejLeftScale += si.rejLeftScale; total.rejLeftRows += si.rejLeftRows; total.rejLeftCols += si.rejLeftCols;
+    total.rejNoConvergence += si.rejNoConvergence; total.rejSingular += si.rejSingular;
+    total.msDevice += si.msDevice; total.kernelLaunches += si.kernelLaunches;
+  }
+  if (stats) *stats = total;
+  if (overflow) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints in the batch, capacity %d", n, cap);
+  return SIFT_OK;
+}
+
+// ------------------------------------------------------------- stage calls ----
+SIFT_API int sift_build_scale_space(sift_ctx *ctx, const void *image, int dtype, int width, int height,
+                                    size_t pitch_bytes, const sift_params *params)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!image) return fail(ctx, SIFT_ERR_BAD_ARGS, "image is NULL");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  size_t dpitch;
+  if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
+  if ((rc = run_pyramid(ctx, ctx->image.p, dtype, dpitch))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_build_dog(sift_ctx *ctx)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "no scale space: call sift_build_scale_space first");
+  return SIFT_OK;   // DoG levels were formed from the unrounded accumulators by the blur kernels
+}
+
+SIFT_API int sift_find_candidates(sift_ctx *ctx, const sift_params *params, sift_candidate *out, int cap,
+                                  int *n_out, sift_candidate *low, int low_cap, int *n_low)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!n_out) return fail(ctx, SIFT_ERR_BAD_ARGS, "n_out is NULL");
+  if (cap < 0 || low_cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad capacity / NULL out");
+  if (!ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "no pyramid: call sift_build_scale_space first");
+  CK(cudaSetDevice(ctx->device));
+  const int count_low = (low != nullptr || n_low != nullptr) ? 1 : 0;
+  int rc;
+  Counters c;
+  if (low && low_cap > ctx->low_cap) {
+    if ((rc = grow(ctx, ctx->low, (size_t)low_cap * sizeof(sift_candidate)))) return rc;
+    ctx->low_cap = low_cap;
+  }
+  for (int attempt = 0;; attempt++) {
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+    const int saved_low_cap = ctx->low_cap;
+    if (!low) ctx->low_cap = 0;                      // count only
+    rc = run_scan(ctx, count_low, params);
+    ctx->low_cap = saved_low_cap;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(&c, dev_counters(ctx), sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (c.n_cand <= ctx->cand_cap || attempt >= 2) break;
+    if ((rc = grow(ctx, ctx->cand, (size_t)(c.n_cand + 1024) * sizeof(sift_candidate)))) return rc;
+    ctx->cand_cap = c.n_cand + 1024;
+  }
+  ctx->last = c;
+  *n_out = c.n_cand;
+  if (n_low) *n_low = c.n_low;
+  int status = SIFT_OK;
+  const int nc = std::min(std::min(c.n_cand, ctx->cand_cap), cap);
+  if (nc > 0 && out) {
+    // sort needs the whole list: stage through pinned memory
+    const int all = std::min(c.n_cand, ctx->cand_cap);
+    if ((rc = grow_pinned(ctx, &ctx->h_cand, &ctx->h_cand_cap, (size_t)all * sizeof(sift_candidate)))) return rc;
+    CK(cudaMemcpyAsync(ctx->h_cand, ctx->cand.p, (size_t)all * sizeof(sift_candidate), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    sort_candidates((sift_candidate *)ctx->h_cand, all);
+    memcpy(out, ctx->h_cand, (size_t)nc * sizeof(sift_candidate));
+  }
+  if (c.n_cand > cap) status = fail(ctx, SIFT_ERR_CAPACITY, "%d candidates, capacity %d", c.n_cand, cap);
+  if (low && c.n_low > 0) {
+    const int nl = std::min(std::min(c.n_low, ctx->low_cap), low_cap);
+    std::vector<sift_candidate> tmp((size_t)std::min(c.n_low, ctx->low_cap));
+    CK(cudaMemcpy(tmp.data(), ctx->low.p, tmp.size() * sizeof(sift_candidate), cudaMemcpyDeviceToHost));
+    sort_candidates(tmp.data(), (int)tmp.size());
+    memcpy(low, tmp.data(), (size_t)nl * sizeof(sift_candidate));
+    if (c.n_low > low_cap) status = fail(ctx, SIFT_ERR_CAPACITY, "%d low-contrast extrema, capacity %d", c.n_low, low_cap);
+  }
+  return status;
+}
+
+SIFT_API int sift_refine(sift_ctx *ctx, const sift_params *params, const sift_candidate *cands, int n_cands,
+                         sift_keypoint *out, int cap, int *n_out, sift_stats *stats)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!n_out || n_cands < 0 || (n_cands > 0 && !cands)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad candidate list");
+  if (!ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "no pyramid: call sift_build_scale_space first");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const int ndog = ctx->nlev - 1;
+  for (int i = 0; i < n_cands; i++) {
+    const sift_candidate &c = cands[i];
+    if (c.octave < 0 || c.octave >= ctx->n_oct || c.scaleLevel < 1 || c.scaleLevel > ndog - 2 || c.x < 1 ||
+        c.y < 1 || c.x > ctx->octs[c.octave].w - 2 || c.y > ctx->octs[c.octave].h - 2)
+      return fail(ctx, SIFT_ERR_BAD_ARGS, "candidate %d (o%d s%d x%d y%d) outside the DoG interior", i, c.octave,
+                  c.scaleLevel, c.x, c.y);
+  }
+  if (n_cands > ctx->cand_cap) {
+    if ((rc = grow(ctx, ctx->cand, (size_t)n_cands * sizeof(sift_candidate)))) return rc;
+    ctx->cand_cap = n_cands;
+  }
+  if (n_cands > ctx->kp_cap) {
+    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)n_cands * sizeof(sift_keypoint)))) return rc;
+    ctx->kp_cap = n_cands;
+  }
+  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+  Counters c;
+  sift_keypoint *kps = nullptr;
+  if (n_cands > 0) {
+    CK(cudaMemcpyAsync(ctx->cand.p, cands, (size_t)n_cands * sizeof(sift_candidate), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_refine(ctx, n_cands, dev_keypoints(ctx), ctx->kp_cap, params))) return rc;
+  }
+  if ((rc = download_keypoints(ctx, &c, &kps))) return rc;
+  c.n_cand = n_cands;
+  // output order = order of the caller's list (background.js:468-471 iterates it as given)
+  std::unordered_map<uint64_t, int> pos;
+  pos.reserve((size_t)n_cands * 2);
+  for (int i = n_cands - 1; i >= 0; i--) pos[cand_key(cands[i].octave, cands[i].scaleLevel, cands[i].y, cands[i].x)] = i;
+  std::stable_sort(kps, kps + c.n_kp, [&](const sift_keypoint &a, const sift_keypoint &b) {
+    return pos[cand_key(a.octave, a.candScale, a.candY, a.candX)] < pos[cand_key(b.octave, b.candScale, b.candY, b.candX)];
+  });
+  ctx->last = c;
+  fill_stats(stats, c, 0, 0.f, 1);
+  *n_out = c.n_kp;
+  if (c.n_kp > cap) {
+    if (cap > 0 && out) memcpy(out, kps, (size_t)cap * sizeof(sift_keypoint));
+    return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
+  }
+  if (c.n_kp && out) memcpy(out, kps, (size_t)c.n_kp * sizeof(sift_keypoint));
+  return SIFT_OK;
+}
+
+// -------------------------------------------------------- pyramid inspection ----
+SIFT_API int sift_get_pyramid_info(const sift_ctx *ctx, int *octaves, int *levels_per_octave)
+{
+  if (!ctx || !ctx->plan_valid) return SIFT_ERR_STATE;
+  if (octaves) *octaves = ctx->n_oct;
+  if (levels_per_octave) *levels_per_octave = ctx->nlev;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_get_octave_size(const sift_ctx *ctx, int octave, int *width, int *height)
+{
+  if (!ctx || !ctx->plan_valid || octave < 0 || octave >= ctx->n_oct) return SIFT_ERR_BAD_ARGS;
+  if (width) *width = ctx->octs[octave].w;
+  if (height) *height = ctx->octs[octave].h;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_get_blur_level(const sift_ctx *ctx, int kind, int octave, int level, double *blur_level)
+{
+  if (!ctx || !ctx->plan_valid || !blur_level || octave < 0 || octave >= ctx->n_oct) return SIFT_ERR_BAD_ARGS;
+  const int nl = (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->nlev : ctx->nlev - 1;
+  if (level < 0 || level >= nl) return SIFT_ERR_BAD_ARGS;
+  *blur_level = (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->plans[octave][level].blurLevel : ctx->dog_blur[octave][level];
+  return SIFT_OK;
+}
+
+static float *plane_ptr(sift_ctx *ctx, int kind, int octave, int level)
+{
+  if (!ctx->plan_valid || octave < 0 || octave >= ctx->n_oct) return nullptr;
+  const int nl = (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->nlev : ctx->nlev - 1;
+  if (level < 0 || level >= nl) return nullptr;
+  return (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->octs[octave].gauss[level] : ctx->octs[octave].dog[level];
+}
+
+SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, float *dst)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!dst) return fail(ctx, SIFT_ERR_BAD_ARGS, "dst is NULL");
+  if (!ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "no pyramid built");
+  float *p = plane_ptr(ctx, kind, octave, level);
+  if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "no level kind %d octave %d level %d", kind, octave, level);
+  CK(cudaSetDevice(ctx->device));
+  const OctaveDev &od = ctx->octs[octave];
+  CK(cudaMemcpy2DAsync(dst, (size_t)od.w * 4, p, (size_t)od.pitch * 4, (size_t)od.w * 4, od.h,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, const sift_params *params)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  // width0/height0 are the OCTAVE-0 dimensions (2x the input): foreign pyramids arrive already upsampled.
+  if (width0 < 2 || height0 < 2 || (width0 & 1) || (height0 & 1))
+    return fail(ctx, SIFT_ERR_BAD_ARGS, "octave-0 size %dx%d must be even (2x upsampled)", width0, height0);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_plan(ctx, width0 / 2, height0 / 2, params))) return rc;
+  ctx->pyramid_built = true;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, const float *src)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!src) return fail(ctx, SIFT_ERR_BAD_ARGS, "src is NULL");
+  float *p = plane_ptr(ctx, kind, octave, level);
+  if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "no level kind %d octave %d level %d", kind, octave, level);
+  CK(cudaSetDevice(ctx->device));
+  const OctaveDev &od = ctx->octs[octave];
+  CK(cudaMemcpy2DAsync(p, (size_t)od.pitch * 4, src, (size_t)od.w * 4, (size_t)od.w * 4, od.h,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+// ----------------------------------------------------- fine step functions ----
+SIFT_API int sift_blur_chunk(sift_ctx *ctx, const double *input, int rows, int cols, double *output, double sigma,
+                             int x1, int y1, int x2, int y2)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!input || !output || rows < 1 || cols < 1) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad image");
+  if (x1 < 0 || y1 < 0 || x2 > cols || y2 > rows) return fail(ctx, SIFT_ERR_BAD_ARGS, "chunk outside the image");
+  if (!(sigma > 0) || !std::isfinite(sigma)) return fail(ctx, SIFT_ERR_BAD_ARGS, "sigma %g", sigma);
+  if (x1 >= x2 || y1 >= y2) return SIFT_OK;                      // empty chunk: the loops do not run (sift.js:96-99)
+  CK(cudaSetDevice(ctx->device));
+  const int R = (int)js_round(3 * sigma);                        // sift.js:38
+  std::vector<double> w((size_t)2 * R + 1);
+  gaussian_taps(sigma, R, w.data());
+  const size_t n = (size_t)rows * cols * sizeof(double);
+  int rc;
+  if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n)) ||
+      (rc = grow(ctx, ctx->misc[3], w.size() * sizeof(double))))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->misc[0].p, input, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc[3].p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));                        // w is a local
+  launch_blur_plane_f64(ctx->stream, (const double *)ctx->misc[0].p, rows, cols, (double *)ctx->misc[1].p,
+                        (double *)ctx->misc[2].p, (const double *)ctx->misc[3].p, R, x1, y1, x2, y2);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  const size_t rowb = (size_t)(x2 - x1) * sizeof(double);
+  CK(cudaMemcpy2DAsync(output + (size_t)y1 * cols + x1, (size_t)cols * 8,
+                       (const double *)ctx->misc[2].p + (size_t)y1 * cols + x1, (size_t)cols * 8, rowb, y2 - y1,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_subtract_chunk(sift_ctx *ctx, const double *a, const double *b, int rows, int cols, double *output,
+                                 int x1, int y1, int x2, int y2)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!a || !b || !output || rows < 1 || cols < 1) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad image");
+  if (x1 < 0 || y1 < 0 || x2 > cols || y2 > rows) return fail(ctx, SIFT_ERR_BAD_ARGS, "chunk outside the image");
+  if (x1 >= x2 || y1 >= y2) return SIFT_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)rows * cols * sizeof(double);
+  int rc;
+  if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n))) return rc;
+  CK(cudaMemcpyAsync(ctx->misc[0].p, a, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc[1].p, b, n, cudaMemcpyHostToDevice, ctx->stream));
+  launch_subtract_f64(ctx->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
+                      (double *)ctx->misc[2].p, cols, x1, y1, x2, y2);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  const size_t rowb = (size_t)(x2 - x1) * sizeof(double);
+  CK(cudaMemcpy2DAsync(output + (size_t)y1 * cols + x1, (size_t)cols * 8,
+                       (const double *)ctx->misc[2].p + (size_t)y1 * cols + x1, (size_t)cols * 8, rowb, y2 - y1,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_find_extremas(sift_ctx *ctx, const double *d0, const double *d1, const double *d2, int rows,
+                                int cols, int scales_per_octave, double contrast_threshold_c, double prefilter_factor,
+                                int32_t *cand_xy, double *cand_value, int cand_cap, int *n_cand, int32_t *low_xy,
+                                double *low_value, int low_cap, int *n_low)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!d0 || !d1 || !d2 || rows < 1 || cols < 1 || !n_cand || !n_low || scales_per_octave < 1)
+    return fail(ctx, SIFT_ERR_BAD_ARGS, "bad arguments");
+  if ((cand_cap > 0 && (!cand_xy || !cand_value)) || (low_cap > 0 && (!low_xy || !low_value)))
+    return fail(ctx, SIFT_ERR_BAD_ARGS, "NULL output with non-zero capacity");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)rows * cols * sizeof(double);
+  const size_t npx = (size_t)rows * cols;
+  int rc;
+  // misc[0..2]: images; misc[3]: counts + xy + values for both lists (capacity = all pixels)
+  const size_t list_bytes = npx * (2 * sizeof(int32_t) + sizeof(double));
+  if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n)) ||
+      (rc = grow(ctx, ctx->misc[3], 256 + 2 * list_bytes)))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->misc[0].p, d0, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc[1].p, d1, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc[2].p, d2, n, cudaMemcpyHostToDevice, ctx->stream));
+  char *base = (char *)ctx->misc[3].p;
+  int *counts = (int *)base;
+  double *cv = (double *)(base + 256);
+  double *lv = cv + npx;
+  int32_t *cxy = (int32_t *)(lv + npx);
+  int32_t *lxy = cxy + 2 * npx;
+  CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->stream));
+  sift_params tmp;
+  sift_default_params(&tmp);
+  tmp.scalesPerOctave = scales_per_octave;
+  tmp.contrastThreshold = contrast_threshold_c;
+  const double pix_thr = contrast_threshold(tmp) * prefilter_factor;              // sift.js:285-293
+  launch_scan_f64(ctx->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
+                  (const double *)ctx->misc[2].p, rows, cols, pix_thr, cxy, cv, (int)npx, lxy, lv, (int)npx, counts);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  int hc[2];
+  CK(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n_cand = hc[0];
+  *n_low = hc[1];
+  auto fetch = [&](int cnt, const int32_t *dxy, const double *dv, int32_t *oxy, double *ov, int ocap) -> int {
+    if (cnt == 0 || ocap == 0) return SIFT_OK;
+    std::vector<int32_t> xy((size_t)cnt * 2);
+    std::vector<double> v((size_t)cnt);
+    CK(cudaMemcpy(xy.data(), dxy, xy.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v.data(), dv, v.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<int> idx((size_t)cnt);
+    for (int i = 0; i < cnt; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) {                           // raster order, sift.js:221-222
+      return xy[2 * a + 1] != xy[2 * b + 1] ? xy[2 * a + 1] < xy[2 * b + 1] : xy[2 * a] < xy[2 * b];
+    });
+    const int m = std::min(cnt, ocap);
+    for (int i = 0; i < m; i++) { oxy[2 * i] = xy[2 * idx[i]]; oxy[2 * i + 1] = xy[2 * idx[i] + 1]; ov[i] = v[idx[i]]; }
+    return SIFT_OK;
+  };
+  if ((rc = fetch(hc[0], cxy, cv, cand_xy, cand_value, cand_cap))) return rc;
+  if ((rc = fetch(hc[1], lxy, lv, low_xy, low_value, low_cap))) return rc;
+  if (hc[0] > cand_cap || hc[1] > low_cap)
+    return fail(ctx, SIFT_ERR_CAPACITY, "%d candidates / %d low-contrast, capacities %d / %d", hc[0], hc[1], cand_cap, low_cap);
+  return SIFT_OK;
+}
+
+SIFT_API int sift_gradient_hessian(sift_ctx *ctx, const double *dm, const double *dc, const double *dp, int rows,
+                                   int cols, int m, int n, double g[3], double h[9])
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!dm || !dc || !dp || !g || !h) return fail(ctx, SIFT_ERR_BAD_ARGS, "NULL argument");
+  if (m < 1 || n < 1 || m > rows - 2 || n > cols - 2) return fail(ctx, SIFT_ERR_BAD_ARGS, "(m=%d, n=%d) has no 3x3 neighbourhood", m, n);
+  CK(cudaSetDevice(ctx->device));
+  // only the 3x3 neighbourhoods are needed: ship 3 rows x 3 cols of each image
+  double win[3][3][3];
+  const double *src[3] = { dm, dc, dp };
+  for (int p = 0; p < 3; p++)
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) win[p][a][b] = src[p][(size_t)(m - 1 + a) * cols + (n - 1 + b)];
+  int rc;
+  if ((rc = grow(ctx, ctx->misc[4], sizeof win + 12 * sizeof(double)))) return rc;
+  double *dwin = (double *)ctx->misc[4].p;
+  CK(cudaMemcpyAsync(dwin, win, sizeof win, cudaMemcpyHostToDevice, ctx->stream));
+  launch_grad_hess_f64(ctx->stream, dwin, dwin + 9, dwin + 18, 3, 1, 1, dwin + 27);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  double out12[12];
+  CK(cudaMemcpyAsync(out12, dwin + 27, sizeof out12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 3; i++) g[i] = out12[i];
+  for (int i = 0; i < 9; i++) h[i] = out12[3 + i];
+  return SIFT_OK;
+}
+
+SIFT_API int sift_resize_dims(int rows, int cols, double rate, int *out_rows, int *out_cols)
+{
+  if (rows < 0 || cols < 0 || !(rate > 0) || !out_rows || !out_cols) return SIFT_ERR_BAD_ARGS;
+  int r = 0, c = 0;
+  for (double i = 0; i < rows; i += rate) r++;                    // matrix2d.js:119
+  for (double j = 0; j < cols; j += rate) c++;                    // matrix2d.js:124
+  *out_rows = r; *out_cols = c;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_linear_resize(sift_ctx *ctx, const double *input, int rows, int cols, double rate, double *output)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!input || !output || rows < 1 || cols < 1 || !(rate > 0)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad arguments");
+  // exact only when a*rate reproduces the reference's accumulated counter: dyadic rates (0.5, 2, 1, 4, ...)
+  int e; const double mant = std::frexp(rate, &e);
+  if (mant != 0.5) return fail(ctx, SIFT_ERR_UNSUPPORTED, "sampling rate %g is not a power of two", rate);
+  CK(cudaSetDevice(ctx->device));
+  int orows, ocols;
+  sift_resize_dims(rows, cols, rate, &orows, &ocols);
+  int rc;
+  const size_t nin = (size_t)rows * cols * 8, nout = (size_t)orows * ocols * 8;
+  if ((rc = grow(ctx, ctx->misc[0], nin)) || (rc = grow(ctx, ctx->misc[1], nout))) return rc;
+  CK(cudaMemcpyAsync(ctx->misc[0].p, input, nin, cudaMemcpyHostToDevice, ctx->stream));
+  launch_resize_f64(ctx->stream, (const double *)ctx->misc[0].p, rows, cols, rate, (double *)ctx->misc[1].p, orows, ocols);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(output, ctx->misc[1].p, nout, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SIFT_OK;
+}
+
+}  // extern "C"

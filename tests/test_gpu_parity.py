@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA path (through the C ABI / host mirror) against the float64 oracle."""
+import numpy as np
+import pytest
+
+import oracle
+import sift_b200
+from sift_b200 import _lib as L, fixtures
+from parity import check_candidates, check_keypoints, check_levels
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (width, height, octaves, seed, dense oracle?)
+    (128, 96, 3, 1234, True),
+    (97, 61, 3, 7, True),          # odd sizes: ceil halving (matrix2d.js:119)
+    (64, 64, 4, 99, True),
+    (256, 192, 4, 5, False),
+    (512, 512, 4, 1234, False),    # BASELINE configs[0]
+]
+
+
+def _run_case(engine, w, h, n_oct, seed, dense, min_blur=1.6, dtype="u8"):
+    u8 = fixtures.synthetic_u8(w, h, seed)
+    img = fixtures.to_float(u8)
+    ora = oracle.detect(img, numberOfOctaves=n_oct, minBlurLevel=min_blur, separable=not dense)
+    assert ora.outcomes["singular"] == 0, "fixture would crash the reference (SURVEY.md Q7)"
+    prm = L.default_params(numberOfOctaves=n_oct, minBlurLevel=min_blur)
+    src = {"u8": u8, "f32": img.astype(np.float32), "f64": img}[dtype]
+    engine.build_scale_space(src, prm)
+    if dtype != "f32":
+        check_levels(engine, ora, L)
+    cands, _ = engine.find_candidates()
+    kps, stats = engine.detect(src, prm)
+    return ora, cands, kps, stats
+
+
+@pytest.mark.parametrize("w,h,n_oct,seed,dense", CASES)
+def test_detect_matches_oracle(engine, w, h, n_oct, seed, dense):
+    ora, cands, kps, stats = _run_case(engine, w, h, n_oct, seed, dense)
+    check_candidates(cands, ora)
+    matched, total, worst = check_keypoints(kps, ora)
+    assert stats["candidates"] == len(cands)
+    assert stats["keypoints"] == len(kps)
+    assert stats["rejSingular"] == 0
+
+
+def test_reference_default_blur_level(engine):
+    """worker.js:35 default min_blur_level = 0.8 (BASELINE configs use 1.6)."""
+    ora, cands, kps, _ = _run_case(engine, 96, 80, 3, 42, True, min_blur=0.8)
+    check_candidates(cands, ora)
+    check_keypoints(kps, ora)
+
+
+def test_f64_input_matches_u8(engine):
+    ora, cands, kps, _ = _run_case(engine, 96, 80, 3, 43, True, dtype="f64")
+    check_candidates(cands, ora)
+    check_keypoints(kps, ora)
+
+
+def test_constant_image_has_no_extrema(engine):
+    """KAT 1: constant image -> every level equals the constant, ties are never extrema (sift.js:261,266)."""
+    img = np.full((40, 56), 0.37, np.float64)
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    engine.build_scale_space(img, prm)
+    for o in range(3):
+        for s in range(6):
+            g = engine.get_level(L.SIFT_LEVEL_GAUSSIAN, o, s)
+            assert np.abs(g.astype(np.float64) - 0.37).max() <= 0.37 * 1e-6
+    kps, stats = engine.detect(img, prm)
+    assert len(kps) == 0 and stats["candidates"] == 0
+
+
+def test_impulse_support_is_kernel_radius(engine):
+    """KAT 2: unit impulse -> outer product of the normalised 1D kernel, support (2R+1)^2, R = round(3 sigma)."""
+    img = np.zeros((64, 64), np.float64)
+    img[32, 32] = 1.0
+    prm = L.default_params(numberOfOctaves=1, minBlurLevel=1.6)
+    engine.build_scale_space(img, prm)
+    ora = oracle.detect(img, numberOfOctaves=1, minBlurLevel=1.6)
+    for s in range(6):
+        g = engine.get_level(L.SIFT_LEVEL_GAUSSIAN, 0, s).astype(np.float64)
+        R = oracle.kernel_radius(ora.offset_sigma[0][s])
+        nz = np.argwhere(g != 0)
+        # the impulse is a 2x2 block at (64..65, 64..65) after the nearest-neighbour upsample
+        assert nz[:, 0].min() == 64 - R and nz[:, 0].max() == 65 + R
+        assert nz[:, 1].min() == 64 - R and nz[:, 1].max() == 65 + R
+        assert np.abs(g - ora.gauss[0][s]).max() <= 1e-7
+
+
+def test_narrow_image_clamps(engine):
+    """KAT 3: image narrower than the kernel radius: clamp-to-edge per axis (sift.js:116-119)."""
+    u8 = fixtures.synthetic_u8(5, 37, 3)
+    img = fixtures.to_float(u8)
+    prm = L.default_params(numberOfOctaves=2, minBlurLevel=1.6)
+    engine.build_scale_space(u8, prm)
+    ora = oracle.detect(img, numberOfOctaves=2, minBlurLevel=1.6)
+    check_levels(engine, ora, L)
+
+
+def test_one_pixel_image(engine):
+    img = np.array([[0.25]])
+    prm = L.default_params(numberOfOctaves=2, minBlurLevel=1.6)
+    kps, stats = engine.detect(img, prm)
+    assert len(kps) == 0
+    assert engine.octave_size(0) == (2, 2) and engine.octave_size(1) == (1, 1)
+
+
+def test_detect_is_deterministic_and_ordered(engine):
+    u8 = fixtures.synthetic_u8(320, 240, 11)
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    a, _ = engine.detect(u8, prm)
+    b, _ = engine.detect(u8, prm)
+    assert len(a) > 50
+    assert a.tobytes() == b.tobytes()
+
+
+def test_batch_equals_single(engine):
+    frames = np.stack([fixtures.synthetic_u8(160, 120, 1234 + i) for i in range(3)])
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    kps, offs, _ = engine.detect_batch(frames, prm)
+    for i in range(3):
+        single, _ = engine.detect(frames[i], prm)
+        assert kps[offs[i]:offs[i + 1]].tobytes() == single.tobytes()
+
+
+def test_capacity_overflow_is_reported(engine):
+    u8 = fixtures.synthetic_u8(320, 240, 11)
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    full, _ = engine.detect(u8, prm)
+    with pytest.raises(sift_b200.SiftError) as e:
+        engine.detect(u8, prm, capacity=3)
+    assert e.value.status == L.SIFT_ERR_CAPACITY
+
+
+def test_bad_arguments(engine):
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=0.4)   # below assumedBlur: sqrt of a negative
+    with pytest.raises(sift_b200.SiftError) as e:
+        engine.detect(np.zeros((16, 16)), prm)
+    assert e.value.status == L.SIFT_ERR_BAD_ARGS
+    with pytest.raises(sift_b200.SiftError):
+        engine.detect(np.zeros((16, 16)), L.default_params(numberOfOctaves=0))
+
+
+def test_full_hd_properties(engine):
+    """BASELINE configs[1] at full size: size-independent properties (the oracle is too slow here).
+    Horizontal mirror symmetry: mirrored input -> mirrored keypoints (the kernels are symmetric and the
+    2x upsample / decimation commute with a flip when the octave widths are even)."""
+    w, h = 1920, 1080
+    u8 = fixtures.synthetic_u8(w, h, 1234)
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    a, sa = engine.detect(u8, prm)
+    b, sb = engine.detect(np.ascontiguousarray(u8[::-1, :]), prm)   # vertical flip: h = 1080 -> 2160,1080,540,270 all even
+    assert len(a) > 1000
+    # only octave 0 is flip-symmetric: the decimation in[2a][2b] (matrix2d.js:129) keeps EVEN rows, which a
+    # flip of an even-height image maps to odd rows
+    ka = {(int(k["scaleLevel"]), int(k["localX"]), int(k["localY"])) for k in a if k["octave"] == 0}
+    kb = {(int(k["scaleLevel"]), int(k["localX"]), 2160 - 1 - int(k["localY"])) for k in b if k["octave"] == 0}
+    assert len(ka) > 500
+    assert len(ka & kb) >= 0.995 * max(len(ka), len(kb))
