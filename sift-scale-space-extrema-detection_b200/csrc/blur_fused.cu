@@ -1,0 +1,281 @@
+// blur_fused.cu -- octave 0 in ONE kernel: 2x nearest-neighbour upsample, all Gaussian
+// levels, DoG and the seed of octave 1, each output written once.
+//
+// Reference path restated: Matrix2D_linearResize(input, 0.5) (background.js:84,
+// matrix2d.js:112-138), then for every level SIFT_blurMatrix2DChunk of that
+// upsampled base (background.js:145-210, sift.js:72-149), SIFT_subtractMatrix2DChunk
+// between neighbouring levels (sift.js:154-188) and the rate-2.0 resize of level
+// `spo` that seeds the next octave (background.js:114-130).
+//
+// Polyphase form: the base is a pixel-doubled image, so for an
+// output X = 2a+p the 2R+1 taps w[i] over u[X+i] = src[(X+i)>>1] collapse onto
+// source samples src[a+c] with merged weights
+//     phase 0: W0[c] = w[2c] + w[2c+1]      c in [floor(-R/2), floor(R/2)]
+//     phase 1: W1[c] = w[2c-1] + w[2c]      c in [floor((1-R)/2), floor((1+R)/2)]
+// (R+1 taps per phase, W1[c] = W0[-c]); clamping in the doubled domain equals
+// clamping source coordinates.  The same holds vertically, so a level costs
+// 6(R+1) fp64 FMAs per SOURCE pixel instead of 8(2R+1).
+//
+// One CTA = 32x32 source pixels = 64x64 outputs of every level.  Per level:
+//   H pass  smem source tile (fp64, clamped halo of 8) -> Ts[row][X] (both phases)
+//   V pass  Ts -> 16 outputs per thread (8 source rows x 2 phases), fp64
+//   epilogue: G_s (fp32), D_{s-1} = G_{s-1} - G_s from the unrounded accumulators
+//   (kept in registers across levels), seed of the next octave (fp64 + fp32).
+// The tap loop is a runtime loop over a register-resident sliding window of 8
+// samples (static rotation, no moves): every loaded sample feeds 16 DFMAs, the hot
+// code is a few KB (a first version unrolled per radius stalled 32 % on instruction
+// fetch), and any radius <= 16 runs the same code.
+#include "common.cuh"
+
+#define F0_SW 32
+#define F0_SH 32
+#define F0_HALO 8                               // supports R <= 16
+#define F0_SROWS (F0_SH + 2 * F0_HALO)          // 48
+#define F0_SCOLS (F0_SW + 2 * F0_HALO)          // 48
+#define F0_SPITCH (F0_SCOLS + 1)                // 49: odd pitch -> lanes along rows are conflict-free
+#define F0_TROWS (F0_SROWS + 1)                 // +1 slack row for the window prefetch
+#define F0_TPITCH (2 * F0_SW + 1)               // 65
+#define F0_THREADS 256
+#define F0_MAXR 16
+#define F0_WSTRIDE 24                           // padded taps per phase per level (n <= 18)
+
+struct Fused0Args {
+  const void *src;
+  size_t src_pitch;
+  int src_w, src_h, dtype;
+  OctaveDev oct, next;
+  int has_next, spo, keep_gauss, nlev;
+  int radius[SIFT_MAX_LEVELS];
+  int woff;                       // offset of the staged tap table [nlev][2][F0_WSTRIDE] in the weight buffer
+  const double *u8lut;            // 256 doubles v/255.0
+};
+
+// v / 255.0 exactly as the reference computes it (image-utils.js:114) without a divide: one Newton
+// correction of v * (1/255) is the correctly rounded quotient for every v in 0..255
+// (tests/test_u8_conversion.py checks all 256 values with exact rational arithmetic).
+__device__ __forceinline__ double u8_over_255(unsigned char v)
+{
+  const double r = 1.0 / 255.0;
+  const double x = (double)v;
+  const double q = x * r;
+  return fma(fma(-q, 255.0, x), r, q);
+}
+
+__device__ __forceinline__ double src0_at(const Fused0Args &A, const char *p)
+{
+  switch (A.dtype) {
+    case SIFT_F32: return (double)*(const float *)p;
+    case SIFT_F64: return *(const double *)p;
+    default: {
+      const uchar4 c = *(const uchar4 *)p;
+      const double g = __dadd_rn(__dadd_rn(__dmul_rn((double)c.x, 0.299), __dmul_rn((double)c.y, 0.587)),
+                                 __dmul_rn((double)c.z, 0.114));                              // image-utils.js:107
+      return g / 255.0;
+    }
+  }
+}
+
+// Two-phase sliding window over 8 neighbouring positions:
+//   a0[k] = sum_{j<n} w0[j] v[k+j],  a1[k] = sum_{j<n} w1[j] v[k+j]
+// v[p] = base[p * stride]; positions up to n+7 are read (n+6 used).
+__device__ __forceinline__ void poly_window(const double *__restrict__ base, const int stride,
+                                            const double *__restrict__ w0, const double *__restrict__ w1,
+                                            const int n, double (&a0)[8], double (&a1)[8])
+{
+  double vw[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { vw[k] = base[k * stride]; a0[k] = 0.0; a1[k] = 0.0; }
+  const double *nxt = base + 8 * stride;
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const double c0 = w0[j + u], c1 = w1[j + u];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        a0[k] = fma(c0, vw[(k + u) & 7], a0[k]);
+        a1[k] = fma(c1, vw[(k + u) & 7], a1[k]);
+      }
+      vw[u] = nxt[(j + u) * stride];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 7; u++) {
+    if (j + u < n) {
+      const double c0 = w0[j + u], c1 = w1[j + u];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        a0[k] = fma(c0, vw[(k + u) & 7], a0[k]);
+        a1[k] = fma(c1, vw[(k + u) & 7], a1[k]);
+      }
+      vw[u] = nxt[(j + u) * stride];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(F0_THREADS, 2)
+fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
+{
+  extern __shared__ double smem[];
+  double *S = smem;                                   // [48][49] source tile, fp64
+  double *Ts = S + F0_SROWS * F0_SPITCH;              // [49][65] horizontally blurred rows, both phases
+  double *Wt = Ts + F0_TROWS * F0_TPITCH;             // [nlev][2][F0_WSTRIDE] zero-padded merged taps
+  const int tid = threadIdx.x;
+  const int a_tile = blockIdx.x * F0_SW, b_tile = blockIdx.y * F0_SH;
+
+  for (int e = tid; e < A.nlev * 2 * F0_WSTRIDE; e += F0_THREADS) Wt[e] = __ldg(weights + A.woff + e);
+  // source tile: 48*48 = 9 samples per thread, all loads in flight before the first use
+  {
+    static_assert(F0_SROWS * F0_SCOLS == 9 * F0_THREADS, "tile load assumes 9 samples per thread");
+    int so[9];
+    size_t go[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const int e = tid + i * F0_THREADS;
+      const int rr = e / F0_SCOLS, cc = e - rr * F0_SCOLS;
+      const int gy = min(max(b_tile - F0_HALO + rr, 0), A.src_h - 1);        // clamp-to-edge, sift.js:116-119
+      const int gx = min(max(a_tile - F0_HALO + cc, 0), A.src_w - 1);
+      so[i] = rr * F0_SPITCH + cc;
+      go[i] = (size_t)gy * A.src_pitch;
+      go[i] += (size_t)gx * (A.dtype == SIFT_U8 ? 1 : (A.dtype == SIFT_F64 ? 8 : 4));
+    }
+    if (A.dtype == SIFT_U8) {
+      unsigned char raw[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) raw[i] = __ldg((const unsigned char *)A.src + go[i]);
+#pragma unroll
+      for (int i = 0; i < 9; i++) S[so[i]] = u8_over_255(raw[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; i++) S[so[i]] = src0_at(A, (const char *)A.src + go[i]);
+    }
+  }
+  for (int e = tid; e < F0_TPITCH; e += F0_THREADS) Ts[(F0_TROWS - 1) * F0_TPITCH + e] = 0.0;   // slack row
+  if (tid < F0_SROWS) S[tid * F0_SPITCH + F0_SCOLS] = 0.0;                                       // pad column
+  __syncthreads();
+
+  // V-pass ownership: output column X of the tile, source rows 8*rg .. 8*rg+7, both row phases
+  const int X = tid & (2 * F0_SW - 1), rg = tid / (2 * F0_SW);
+  const int x = 2 * a_tile + X;
+  const int w = A.oct.w, h = A.oct.h;
+  const size_t pitch = A.oct.pitch;
+  const int y_first = 2 * (b_tile + 8 * rg);
+  const size_t o_first = (size_t)y_first * pitch + x;
+  const bool col_ok = x < w;
+  const bool rows_full = y_first + 16 <= h;
+  const bool seed_lane = A.has_next && (X & 1) == 0 && col_ok;
+  const size_t seed_first = (size_t)(b_tile + 8 * rg) * A.next.w + (x >> 1);
+  const size_t g0_first = (size_t)(b_tile + 8 * rg) * A.next.pitch + (x >> 1);
+
+  double prev[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) prev[i] = 0.0;
+
+  for (int s = 0; s < A.nlev; s++) {                 // octave 0 blurs every level from the base (background.js:110)
+    const int R = A.radius[s];
+    const int clo0 = -((R + 1) / 2);
+    const int n = R + 1 + (R & 1);                   // taps per phase incl. the phase-1 shift for odd R
+    const double *w0 = Wt + (s * 2) * F0_WSTRIDE, *w1 = w0 + F0_WSTRIDE;
+
+    // ---- H pass: rows needed by this level's vertical window; 8 source columns x 2 phases per item
+    const int nrows = F0_SH + n - 1;                 // = 32 + chi1 - clo0
+    const int row_first = F0_HALO + clo0;
+    for (int i = tid; i < nrows * (F0_SW / 8); i += F0_THREADS) {
+      const int g = i / nrows, rr = row_first + (i - g * nrows);
+      double a0[8], a1[8];
+      poly_window(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, w0, w1, n, a0, a1);
+      double *t = Ts + rr * F0_TPITCH + 16 * g;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { t[2 * k] = a0[k]; t[2 * k + 1] = a1[k]; }
+    }
+    __syncthreads();
+
+    // ---- V pass
+    double a0[8], a1[8];
+    poly_window(Ts + (F0_HALO + 8 * rg + clo0) * F0_TPITCH + X, F0_TPITCH, w0, w1, n, a0, a1);
+
+    // ---- epilogue: G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172), seed of the next octave
+    if (col_ok) {
+      float *gp = A.oct.gauss[s] + o_first;
+      float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o_first;
+      const bool wg = A.keep_gauss != 0, wd = s > 0;
+      if (rows_full) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (wg) { gp[(2 * k) * pitch] = (float)a0[k]; gp[(2 * k + 1) * pitch] = (float)a1[k]; }
+          if (wd) {
+            dp[(2 * k) * pitch] = (float)(prev[2 * k] - a0[k]);
+            dp[(2 * k + 1) * pitch] = (float)(prev[2 * k + 1] - a1[k]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            if (y_first + 2 * k + q < h) {
+              const double v = q ? a1[k] : a0[k];
+              if (wg) gp[(2 * k + q) * pitch] = (float)v;
+              if (wd) dp[(2 * k + q) * pitch] = (float)(prev[2 * k + q] - v);
+            }
+          }
+        }
+      }
+      if (s == A.spo && seed_lane) {                 // in[2a][2b] (matrix2d.js:129): even rows (phase 0), even columns
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (y_first + 2 * k < h) {
+            A.next.seed64[seed_first + (size_t)k * A.next.w] = a0[k];
+            A.next.gauss[0][g0_first + (size_t)k * A.next.pitch] = (float)a0[k];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { prev[2 * k] = a0[k]; prev[2 * k + 1] = a1[k]; }
+    __syncthreads();                                 // Ts is rewritten by the next level
+  }
+}
+
+// Host: zero-padded merged polyphase taps of one level into out[2][F0_WSTRIDE].
+//   phase 0: out[0][j] = W0[j], j = c - floor(-R/2);  phase 1: out[1][j + d] = W0[R - j], d = R & 1.
+void fused0_merge_taps(const double *w, int R, double *out)
+{
+  for (int i = 0; i < 2 * F0_WSTRIDE; i++) out[i] = 0.0;
+  const int clo0 = -((R + 1) / 2), d = R & 1;
+  for (int j = 0; j <= R; j++) {
+    const int c = clo0 + j;
+    const int i0 = 2 * c, i1 = 2 * c + 1;
+    const double t0 = (i0 >= -R && i0 <= R) ? w[i0 + R] : 0.0;
+    const double t1 = (i1 >= -R && i1 <= R) ? w[i1 + R] : 0.0;
+    out[j] = t0 + t1;
+  }
+  for (int j = 0; j <= R; j++) out[F0_WSTRIDE + j + d] = out[R - j];
+}
+
+int fused0_taps_per_level(void) { return 2 * F0_WSTRIDE; }
+
+bool fused0_supported(const LevelPlan *plans, int nlev)
+{
+  for (int s = 0; s < nlev; s++)
+    if (plans[s].radius < 1 || plans[s].radius > F0_MAXR) return false;
+  return true;
+}
+
+void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                          const OctaveDev &oct, const OctaveDev *next, const double *d_weights,
+                          const LevelPlan *plans, int poly_woff, int nlev, int spo, int keep_gauss,
+                          const double *d_u8lut)
+{
+  Fused0Args A;
+  A.src = src; A.src_pitch = src_pitch; A.src_w = src_w; A.src_h = src_h; A.dtype = dtype;
+  A.oct = oct; A.next = next ? *next : oct; A.has_next = next ? 1 : 0;
+  A.spo = spo; A.keep_gauss = keep_gauss; A.nlev = nlev;
+  for (int s = 0; s < nlev; s++) A.radius[s] = plans[s].radius;
+  A.woff = poly_woff;
+  A.u8lut = d_u8lut;
+  dim3 grid((src_w + F0_SW - 1) / F0_SW, (src_h + F0_SH - 1) / F0_SH);
+  const size_t smem = (size_t)(F0_SROWS * F0_SPITCH + F0_TROWS * F0_TPITCH + nlev * 2 * F0_WSTRIDE) * sizeof(double);
+  cudaFuncSetAttribute(fused_octave0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fused_octave0_kernel<<<grid, F0_THREADS, smem, st>>>(d_weights, A);
+}

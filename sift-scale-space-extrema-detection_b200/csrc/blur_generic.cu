@@ -5,18 +5,21 @@
 // to the octave base (background.js:103-224), the DoG subtraction
 // SIFT_subtractMatrix2DChunk (src/sift.js:154-188, finer minus coarser) and the
 // 2x decimation that seeds the next octave (matrix2d.js:112-138 with rate 2.0,
-// background.js:114-130).  The 2x nearest-neighbour upsample of the input
-// (background.js:84) is folded into the octave-0 loads.
+// background.js:114-130).  Used for octaves >= 1 (any radius, also wider than the
+// image) and as the octave-0 path for radii the fused polyphase kernel
+// (blur_fused.cu) does not cover; the 2x nearest-neighbour upsample of the input
+// (background.js:84) is then folded into the loads.
 //
-// Two passes through an fp64 intermediate T (L2 resident for the small, high
-// octaves this path is kept for; see blur_fused.cu for octaves 0 and 1):
-//   hblur: T_s[y][x]  = sum_i w_s[i] * base[y][clamp(x + i - R_s)]
-//   vblur: G_s[y][x]  = sum_j w_s[j] * T_s[clamp(y + j - R_s)][x]
-//          D_{s-1}    = G_{s-1} - G_s  formed from the UNROUNDED fp64 accumulators,
-//          both stored fp32; level `spo` is also decimated into the next seed (fp64 + fp32).
+// Two passes through an fp64 intermediate T (L2 resident for these octaves):
+//   hblur: T_s[y][x]  = sum_i w_s[i] * base[y][clamp(x + i - R_s)]     one level per CTA (blockIdx.z)
+//   vblur: G_s[y][x]  = sum_j w_s[j] * T_s[clamp(y + j - R_s)][x]      levels across threadIdx.z
+//          D_{s-1}    = G_{s-1} - G_s  formed from the UNROUNDED fp64 accumulators (exchanged
+//          through shared memory), both stored fp32; level `spo` is also decimated into
+//          the next seed (fp64 + fp32).
 // Accumulation is fp64 in both passes (fp32 accumulation fails the
-// 1e-5 / 1e-3 px parity bars).  Each thread produces NOUT=8 neighbouring outputs
-// from a sliding window so every loaded sample feeds 8 DFMAs.
+// 1e-5 / 1e-3 px parity bars).  Every thread slides a register window of 8 samples
+// over its 8 neighbouring outputs (static rotation, runtime tap count, exact: no
+// padded taps), so each loaded sample feeds 8 DFMAs.
 #include "common.cuh"
 
 #define NOUT 8
@@ -29,116 +32,100 @@ struct BlurLevels {
   double *T[SIFT_MAX_LEVELS];
 };
 
-// acc[k] += sum_t w[t-k] * v(t),  t = 0 .. 2R+NOUT-1; wpad holds w[0..2R] then >= SIFT_WPAD zeros.
+// a[k] = sum_{j<n} w[j] * v(k + j), k < 8.  loadv(p) is called for p in [0, n+7] (p <= n+6 used).
 template <typename LoadV>
-__device__ __forceinline__ void conv_window(const double *__restrict__ wpad, int R, LoadV loadv, double acc[NOUT])
+__device__ __forceinline__ void window8(const double *__restrict__ w, const int n, LoadV loadv, double (&a)[NOUT])
 {
-  double wr[NOUT];
+  double vw[NOUT];
 #pragma unroll
-  for (int k = 0; k < NOUT; k++) { wr[k] = 0.0; acc[k] = 0.0; }
-  const int T = 2 * R + NOUT;
-  for (int t0 = 0; t0 < T; t0 += NOUT) {
+  for (int k = 0; k < NOUT; k++) { vw[k] = loadv(k); a[k] = 0.0; }
+  int j = 0;
+  for (; j + NOUT <= n; j += NOUT) {
 #pragma unroll
     for (int u = 0; u < NOUT; u++) {
-      const int t = t0 + u;
-      const double v = loadv(t);
-      wr[u] = __ldg(wpad + t);
+      const double c = w[j + u];
 #pragma unroll
-      for (int k = 0; k < NOUT; k++) acc[k] = fma(wr[(u - k + NOUT) % NOUT], v, acc[k]);
+      for (int k = 0; k < NOUT; k++) a[k] = fma(c, vw[(k + u) & 7], a[k]);
+      vw[u] = loadv(j + u + NOUT);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NOUT - 1; u++) {
+    if (j + u < n) {
+      const double c = w[j + u];
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) a[k] = fma(c, vw[(k + u) & 7], a[k]);
+      vw[u] = loadv(j + u + NOUT);
     }
   }
 }
 
 // ---- source pixel -> double, exactly the reference's float64 image value ------
-template <int DTYPE> struct SrcLoad;
-template <> struct SrcLoad<SIFT_U8> {
-  static __device__ __forceinline__ double at(const void *row, int x) {
-    return (double)((const unsigned char *)row)[x] / 255.0;                     // image-utils.js:114
+__device__ __forceinline__ double src_at(const void *row, int x, int dtype)
+{
+  switch (dtype) {
+    case SIFT_U8: return (double)((const unsigned char *)row)[x] / 255.0;        // image-utils.js:114
+    case SIFT_F32: return (double)((const float *)row)[x];
+    case SIFT_F64: return ((const double *)row)[x];
+    default: {
+      const uchar4 p = ((const uchar4 *)row)[x];
+      // (R*0.299) + (G*0.587) + (B*0.114), then / 255.0 -- image-utils.js:107-114, unfused
+      const double g = __dadd_rn(__dadd_rn(__dmul_rn((double)p.x, 0.299), __dmul_rn((double)p.y, 0.587)),
+                                 __dmul_rn((double)p.z, 0.114));
+      return g / 255.0;
+    }
   }
-};
-template <> struct SrcLoad<SIFT_F32> {
-  static __device__ __forceinline__ double at(const void *row, int x) { return (double)((const float *)row)[x]; }
-};
-template <> struct SrcLoad<SIFT_F64> {
-  static __device__ __forceinline__ double at(const void *row, int x) { return ((const double *)row)[x]; }
-};
-template <> struct SrcLoad<SIFT_RGBA8> {
-  static __device__ __forceinline__ double at(const void *row, int x) {
-    const uchar4 p = ((const uchar4 *)row)[x];
-    // (R*0.299) + (G*0.587) + (B*0.114), then / 255.0 -- image-utils.js:107-114, unfused
-    const double g = __dadd_rn(__dadd_rn(__dmul_rn((double)p.x, 0.299), __dmul_rn((double)p.y, 0.587)),
-                               __dmul_rn((double)p.z, 0.114));
-    return g / 255.0;
-  }
-};
+}
 
 // ------------------------------------------------------------------- hblur ----
-#define HB_ROWS 4
-#define HB_THREADS_X 32
-#define HB_TW (HB_THREADS_X * NOUT)   // 256 outputs per row per CTA
+#define HB_WARPS 8                    // rows per CTA (one warp per row)
+#define HB_TW (32 * NOUT)             // 256 outputs per row per CTA
 
 __device__ __forceinline__ int padidx(int e) { return e + (e >> 3); }   // 9-double stride per 8: conflict-free LDS.64
 
-template <int DTYPE, int UPS>
-__global__ void __launch_bounds__(HB_THREADS_X *HB_ROWS)
-hblur_kernel(const void *__restrict__ src, size_t src_pitch, int src_w, int w, int hrows, int rmax,
+__global__ void __launch_bounds__(32 * HB_WARPS)
+hblur_kernel(const void *__restrict__ src, size_t src_pitch, int src_w, int dtype, int ups, int w, int hrows,
              const double *__restrict__ weights, BlurLevels L)
 {
   extern __shared__ double smem[];
-  const int span = HB_TW + 2 * rmax + NOUT;          // samples staged per row (NOUT slack for the window tail)
+  const int li = blockIdx.z;
+  const int R = L.radius[li], n = 2 * R + 1;
+  const int span = HB_TW + 2 * R + NOUT;            // samples staged per row (window prefetch reads n+7 past the first)
   const int rowstride = padidx(span) + 1;
+  double *wsm = smem;                               // n taps
+  double *rows = smem + ((n + 1) & ~1);
   const int x_tile = blockIdx.x * HB_TW;
-  const int row0 = blockIdx.y * HB_ROWS;
-  const int tid = threadIdx.y * HB_THREADS_X + threadIdx.x;
+  const int row0 = blockIdx.y * HB_WARPS;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
 
-  for (int r = 0; r < HB_ROWS; r++) {
+  for (int e = tid; e < n; e += 32 * HB_WARPS) wsm[e] = __ldg(weights + L.woff[li] + e);
+  for (int r = 0; r < HB_WARPS; r++) {
     const int y = row0 + r;
     if (y >= hrows) break;
     const char *rowp = (const char *)src + (size_t)y * src_pitch;
-    for (int e = tid; e < span; e += HB_THREADS_X * HB_ROWS) {
-      int col = x_tile - rmax + e;
+    for (int e = tid; e < span; e += 32 * HB_WARPS) {
+      int col = x_tile - R + e;
       col = min(max(col, 0), w - 1);                                           // sift.js:116-117 clamp
-      const int sc = UPS ? (col >> 1) : col;                                   // matrix2d.js:129 floor(j*0.5)
-      smem[r * rowstride + padidx(e)] = SrcLoad<DTYPE>::at(rowp, min(sc, src_w - 1));
+      const int sc = ups ? (col >> 1) : col;                                   // matrix2d.js:129 floor(j*0.5)
+      rows[r * rowstride + padidx(e)] = src_at(rowp, min(sc, src_w - 1), dtype);
     }
   }
   __syncthreads();
 
   const int y = row0 + threadIdx.y;
-  if (y >= hrows) return;
   const int x0 = x_tile + threadIdx.x * NOUT;
-  if (x0 >= w) return;
-  const double *rowsm = smem + threadIdx.y * rowstride;
-  for (int li = 0; li < L.nlev; li++) {
-    const int R = L.radius[li];
-    const int e0 = threadIdx.x * NOUT + rmax - R;     // smem sample feeding tap 0 of output 0
-    double acc[NOUT];
-    conv_window(weights + L.woff[li], R, [&](int t) { return rowsm[padidx(e0 + t)]; }, acc);
-    double *out = L.T[li] + (size_t)y * w + x0;
-    if (x0 + NOUT <= w && ((w & 1) == 0)) {
+  if (y >= hrows || x0 >= w) return;
+  const double *rowsm = rows + threadIdx.y * rowstride;
+  const int e0 = threadIdx.x * NOUT;                 // sample feeding tap 0 of output 0
+  double acc[NOUT];
+  window8(wsm, n, [&](int p) { return rowsm[padidx(e0 + p)]; }, acc);
+  double *out = L.T[li] + (size_t)y * w + x0;
+  if (x0 + NOUT <= w && ((w & 1) == 0)) {
 #pragma unroll
-      for (int k = 0; k < NOUT; k += 2) *reinterpret_cast<double2 *>(out + k) = make_double2(acc[k], acc[k + 1]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) if (x0 + k < w) out[k] = acc[k];
-    }
-  }
-}
-
-template <int DTYPE>
-static void hblur_dispatch(cudaStream_t st, const void *src, size_t src_pitch, int src_w, int upsample, int w,
-                           int hrows, int rmax, const double *d_weights, const BlurLevels &L)
-{
-  dim3 block(HB_THREADS_X, HB_ROWS);
-  dim3 grid((w + HB_TW - 1) / HB_TW, (hrows + HB_ROWS - 1) / HB_ROWS);
-  const int span = HB_TW + 2 * rmax + NOUT;
-  const size_t smem = (size_t)HB_ROWS * ((span + (span >> 3)) + 1) * sizeof(double);
-  if (upsample) {
-    cudaFuncSetAttribute(hblur_kernel<DTYPE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    hblur_kernel<DTYPE, 1><<<grid, block, smem, st>>>(src, src_pitch, src_w, w, hrows, rmax, d_weights, L);
+    for (int k = 0; k < NOUT; k += 2) *reinterpret_cast<double2 *>(out + k) = make_double2(acc[k], acc[k + 1]);
   } else {
-    cudaFuncSetAttribute(hblur_kernel<DTYPE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    hblur_kernel<DTYPE, 0><<<grid, block, smem, st>>>(src, src_pitch, src_w, w, hrows, rmax, d_weights, L);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) if (x0 + k < w) out[k] = acc[k];
   }
 }
 
@@ -165,60 +152,82 @@ void launch_hblur(cudaStream_t st, const void *src, int dtype, size_t src_pitch_
   (void)src_h;
   int rmax;
   BlurLevels L = make_levels(plans, first_level, nlev, T, &rmax);
-  switch (dtype) {
-    case SIFT_U8: hblur_dispatch<SIFT_U8>(st, src, src_pitch_bytes, src_w, upsample, w, hrows, rmax, d_weights, L); break;
-    case SIFT_F32: hblur_dispatch<SIFT_F32>(st, src, src_pitch_bytes, src_w, upsample, w, hrows, rmax, d_weights, L); break;
-    case SIFT_F64: hblur_dispatch<SIFT_F64>(st, src, src_pitch_bytes, src_w, upsample, w, hrows, rmax, d_weights, L); break;
-    case SIFT_RGBA8: hblur_dispatch<SIFT_RGBA8>(st, src, src_pitch_bytes, src_w, upsample, w, hrows, rmax, d_weights, L); break;
-  }
+  dim3 block(32, HB_WARPS);
+  dim3 grid((w + HB_TW - 1) / HB_TW, (hrows + HB_WARPS - 1) / HB_WARPS, L.nlev);
+  const int span = HB_TW + 2 * rmax + NOUT;
+  const size_t smem = ((size_t)((2 * rmax + 2) & ~1) + (size_t)HB_WARPS * ((span + (span >> 3)) + 1)) * sizeof(double);
+  cudaFuncSetAttribute(hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hblur_kernel<<<grid, block, smem, st>>>(src, src_pitch_bytes, src_w, dtype, upsample, w, hrows, d_weights, L);
 }
 
 // ------------------------------------------------------------------- vblur ----
-#define VB_THREADS 128
+#define VB_COLS 32
+#define VB_RG 2                        // row groups of 8 per CTA -> 16 rows
 
 struct VBlurArgs {
   OctaveDev oct;
   OctaveDev next;        // valid when has_next
-  int has_next, spo, keep_gauss, seed_is_level0;
+  int has_next, spo, keep_gauss, seed_is_level0, ups;
   BlurLevels L;
 };
 
-template <int UPS>
-__global__ void __launch_bounds__(VB_THREADS)
+__global__ void __launch_bounds__(VB_COLS *VB_RG *SIFT_MAX_LEVELS)
 vblur_kernel(const double *__restrict__ weights, VBlurArgs A)
 {
-  const int x = blockIdx.x * VB_THREADS + threadIdx.x;
-  const int y0 = blockIdx.y * NOUT;
-  const int w = A.oct.w, h = A.oct.h, pitch = A.oct.pitch;
-  if (x >= w) return;
-
-  double prev[NOUT];
-  if (A.seed_is_level0) {                               // octaves >= 1: level 0 is the unblurred seed
-#pragma unroll
-    for (int k = 0; k < NOUT; k++) prev[k] = A.oct.seed64[(size_t)min(y0 + k, h - 1) * w + x];
+  extern __shared__ double smem[];
+  // G64[li][row][col]: unrounded level values of the tile, for D_{s-1} = G_{s-1} - G_s
+  double *G64 = smem;
+  const int nl = A.L.nlev;
+  double *wsm = smem + nl * (VB_RG * NOUT) * VB_COLS;     // per level: taps at wsm + wbase[li]
+  const int li = threadIdx.z;
+  const int tid = (threadIdx.z * VB_RG + threadIdx.y) * VB_COLS + threadIdx.x;
+  const int nthreads = VB_COLS * VB_RG * nl;
+  int wbase = 0;
+  for (int i = 0; i < li; i++) wbase += 2 * A.L.radius[i] + 1;
+  int wtotal = 0;
+  for (int i = 0; i < nl; i++) {
+    const int n_i = 2 * A.L.radius[i] + 1;
+    for (int e = tid; e < n_i; e += nthreads) wsm[wtotal + e] = __ldg(weights + A.L.woff[i] + e);
+    wtotal += n_i;
   }
-  for (int li = 0; li < A.L.nlev; li++) {
-    const int R = A.L.radius[li];
-    const int s = A.L.level[li];
+  __syncthreads();
+
+  const int w = A.oct.w, h = A.oct.h, pitch = A.oct.pitch;
+  const int x = blockIdx.x * VB_COLS + threadIdx.x;
+  const int y0 = (blockIdx.y * VB_RG + threadIdx.y) * NOUT;
+  const int R = A.L.radius[li], s = A.L.level[li];
+  const bool active = x < w && y0 < h;
+  double acc[NOUT];
+  if (active) {
     const double *__restrict__ T = A.L.T[li];
-    double acc[NOUT];
-    conv_window(weights + A.L.woff[li], R, [&](int t) {
-      int yy = min(max(y0 + t - R, 0), h - 1);                                 // sift.js:118-119 clamp
-      if (UPS) yy >>= 1;                                                       // rows 2b and 2b+1 are equal
+    const int ups = A.ups;
+    window8(wsm + wbase, 2 * R + 1, [&](int p) {
+      int yy = min(max(y0 + p - R, 0), h - 1);                                 // sift.js:118-119 clamp
+      if (ups) yy >>= 1;                                                       // rows 2b and 2b+1 are equal
       return __ldg(T + (size_t)yy * w + x);
     }, acc);
+    double *g = G64 + ((li * VB_RG + threadIdx.y) * NOUT) * VB_COLS + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < NOUT; k++) {
-      const int y = y0 + k;
-      if (y < h) {
-        if (A.keep_gauss) A.oct.gauss[s][(size_t)y * pitch + x] = (float)acc[k];
-        if (s > 0) A.oct.dog[s - 1][(size_t)y * pitch + x] = (float)(prev[k] - acc[k]);   // sift.js:172
-        if (A.has_next && s == A.spo && ((y | x) & 1) == 0) {                  // matrix2d.js:129 in[2a][2b]
-          A.next.seed64[(size_t)(y >> 1) * A.next.w + (x >> 1)] = acc[k];
-          A.next.gauss[0][(size_t)(y >> 1) * A.next.pitch + (x >> 1)] = (float)acc[k];
-        }
-      }
-      prev[k] = acc[k];
+    for (int k = 0; k < NOUT; k++) g[k * VB_COLS] = acc[k];
+  }
+  __syncthreads();
+  if (!active) return;
+
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+    const int y = y0 + k;
+    if (y >= h) break;
+    const size_t o = (size_t)y * pitch + x;
+    if (A.keep_gauss) A.oct.gauss[s][o] = (float)acc[k];
+    if (s > 0) {
+      double prev;
+      if (li > 0) prev = G64[(((li - 1) * VB_RG + threadIdx.y) * NOUT + k) * VB_COLS + threadIdx.x];
+      else prev = A.oct.seed64[(size_t)y * w + x];                             // level 0 of octaves >= 1 is the seed
+      A.oct.dog[s - 1][o] = (float)(prev - acc[k]);                            // sift.js:172
+    }
+    if (A.has_next && s == A.spo && ((y | x) & 1) == 0) {                      // matrix2d.js:129 in[2a][2b]
+      A.next.seed64[(size_t)(y >> 1) * A.next.w + (x >> 1)] = acc[k];
+      A.next.gauss[0][(size_t)(y >> 1) * A.next.pitch + (x >> 1)] = (float)acc[k];
     }
   }
 }
@@ -234,11 +243,16 @@ void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const dou
   A.spo = spo;
   A.keep_gauss = keep_gauss;
   A.seed_is_level0 = first_level > 0;
+  A.ups = upsample;
   int rmax;
   A.L = make_levels(plans, first_level, oct.nlev, T, &rmax);
-  dim3 grid((oct.w + VB_THREADS - 1) / VB_THREADS, (oct.h + NOUT - 1) / NOUT);
-  if (upsample) vblur_kernel<1><<<grid, VB_THREADS, 0, st>>>(d_weights, A);
-  else vblur_kernel<0><<<grid, VB_THREADS, 0, st>>>(d_weights, A);
+  int wtotal = 0;
+  for (int i = 0; i < A.L.nlev; i++) wtotal += 2 * A.L.radius[i] + 1;
+  dim3 block(VB_COLS, VB_RG, A.L.nlev);
+  dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VB_RG * NOUT - 1) / (VB_RG * NOUT));
+  const size_t smem = ((size_t)A.L.nlev * VB_RG * NOUT * VB_COLS + wtotal + 1) * sizeof(double);
+  cudaFuncSetAttribute(vblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  vblur_kernel<<<grid, block, smem, st>>>(d_weights, A);
 }
 
 // ------------------------------------------------ step-function helpers (fp64) --

@@ -64,6 +64,15 @@ void launch_resize_f64(cudaStream_t st, const double *in, int rows, int cols, do
                        int orows, int ocols);
 void launch_seed_to_f32(cudaStream_t st, const double *seed, int w, int h, float *dst, int pitch);
 
+// blur_fused.cu
+void fused0_merge_taps(const double *w, int R, double *out /* fused0_taps_per_level() doubles */);
+int fused0_taps_per_level(void);
+bool fused0_supported(const LevelPlan *plans, int nlev);
+void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                          const OctaveDev &oct, const OctaveDev *next, const double *d_weights,
+                          const LevelPlan *plans, int poly_woff, int nlev, int spo, int keep_gauss,
+                          const double *d_u8lut);
+
 // scan.cu
 void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int spo, double pix_threshold,
                         int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -42,7 +43,10 @@ struct sift_ctx {
   int n_oct = 0, nlev = 0;
   LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   double dog_blur[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
-  std::vector<double> h_weights;
+  std::vector<double> h_weights;   // [0,256): u8 -> v/255.0 table, then per-level taps
+  int poly_woff = 0;               // octave 0: merged polyphase tap table (blur_fused.cu)
+  bool fused0 = false;             // octave 0 runs the fused polyphase kernel
+  bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
   double *d_weights = nullptr;
   size_t d_weights_cap = 0;
   OctaveDev octs[SIFT_MAX_OCTAVES];
@@ -176,6 +180,7 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
   for (int o = 1; o < n_oct; o++) { ow[o] = (ow[o - 1] + 1) / 2; oh[o] = (oh[o - 1] + 1) / 2; }
 
   ctx->h_weights.clear();
+  for (int v = 0; v < 256; v++) ctx->h_weights.push_back((double)v / 255.0);   // image-utils.js:114
   double base_blur = p->minBlurLevel;                                          // background.js:89
   for (int o = 0; o < n_oct; o++) {
     for (int s = 0; s < nlev; s++) {
@@ -200,6 +205,16 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
       gaussian_taps(off, lp.radius, ctx->h_weights.data() + lp.woff);
     }
     for (int s = 1; s < nlev; s++) ctx->dog_blur[o][s - 1] = ctx->plans[o][s - 1].blurLevel;   // background.js:327
+  }
+  ctx->fused0 = !ctx->force_generic && fused0_supported(ctx->plans[0], nlev);
+  if (ctx->fused0) {
+    const int per = fused0_taps_per_level();
+    ctx->poly_woff = (int)ctx->h_weights.size();
+    ctx->h_weights.resize(ctx->h_weights.size() + (size_t)nlev * per, 0.0);
+    for (int s = 0; s < nlev; s++) {
+      const LevelPlan &lp = ctx->plans[0][s];
+      fused0_merge_taps(ctx->h_weights.data() + lp.woff, lp.radius, ctx->h_weights.data() + ctx->poly_woff + (size_t)s * per);
+    }
   }
 
   // ---- device memory
@@ -264,6 +279,15 @@ static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pit
   cudaStream_t st = ctx->stream;
   for (int o = 0; o < ctx->n_oct; o++) {
     const OctaveDev &od = ctx->octs[o];
+    if (o == 0 && ctx->fused0) {
+      prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
+      launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od,
+                           (ctx->n_oct > 1) ? &ctx->octs[1] : nullptr, ctx->d_weights, ctx->plans[0],
+                           ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
+      ctx->launches += 1;
+      prof_end(ctx);
+      continue;
+    }
     const int first = (o == 0) ? 0 : 1;
     const int hrows = (o == 0) ? ctx->in_h : od.h;
     double *T[SIFT_MAX_LEVELS];
@@ -481,6 +505,8 @@ SIFT_API int sift_create(int device, sift_ctx **out)
     return fail(nullptr, SIFT_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   sift_default_params(&c->prm);
+  const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
+  c->force_generic = fg && fg[0] == '1';
   *out = c;
   return SIFT_OK;
 }
