@@ -78,37 +78,61 @@ __device__ __forceinline__ double src_at(const void *row, int x, int dtype)
 }
 
 // ------------------------------------------------------------------- hblur ----
-#define HB_WARPS 8                    // rows per CTA (one warp per row)
+#define HB_WARPS 4                    // rows per CTA (one warp per row)
 #define HB_TW (32 * NOUT)             // 256 outputs per row per CTA
+#define HB_THREADS (32 * HB_WARPS)
 
 __device__ __forceinline__ int padidx(int e) { return e + (e >> 3); }   // 9-double stride per 8: conflict-free LDS.64
 
-__global__ void __launch_bounds__(32 * HB_WARPS)
+// grid.z == 1: the CTA loops over all levels (rows staged once with the largest halo);
+// grid.z == nlev: one level per CTA (small octaves: more CTAs in flight).
+__global__ void __launch_bounds__(HB_THREADS)
 hblur_kernel(const void *__restrict__ src, size_t src_pitch, int src_w, int dtype, int ups, int w, int hrows,
-             const double *__restrict__ weights, BlurLevels L)
+             int rmax, int wtotal, const double *__restrict__ weights, BlurLevels L)
 {
   extern __shared__ double smem[];
-  const int li = blockIdx.z;
-  const int R = L.radius[li], n = 2 * R + 1;
-  const int span = HB_TW + 2 * R + NOUT;            // samples staged per row (window prefetch reads n+7 past the first)
+  const bool all_levels = gridDim.z == 1;
+  const int li_first = all_levels ? 0 : blockIdx.z;
+  const int li_last = all_levels ? L.nlev : blockIdx.z + 1;
+  const int RS = all_levels ? rmax : L.radius[li_first];   // staged halo
+  const int span = HB_TW + 2 * RS + NOUT;           // samples staged per row (window prefetch reads n+7 past the first)
   const int rowstride = padidx(span) + 1;
-  double *wsm = smem;                               // n taps
-  double *rows = smem + ((n + 1) & ~1);
+  double *wsm = smem;                               // taps of the handled levels, back to back
+  double *rows = smem + ((wtotal + 1) & ~1);
   const int x_tile = blockIdx.x * HB_TW;
   const int row0 = blockIdx.y * HB_WARPS;
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
-  for (int e = tid; e < n; e += 32 * HB_WARPS) wsm[e] = __ldg(weights + L.woff[li] + e);
-  for (int r = 0; r < HB_WARPS; r++) {
-    const int y = row0 + r;
-    if (y >= hrows) break;
-    const char *rowp = (const char *)src + (size_t)y * src_pitch;
-    for (int e = tid; e < span; e += 32 * HB_WARPS) {
-      int col = x_tile - R + e;
-      col = min(max(col, 0), w - 1);                                           // sift.js:116-117 clamp
-      const int sc = ups ? (col >> 1) : col;                                   // matrix2d.js:129 floor(j*0.5)
-      rows[r * rowstride + padidx(e)] = src_at(rowp, min(sc, src_w - 1), dtype);
+  {
+    int wo = 0;
+    for (int li = li_first; li < li_last; li++) {
+      const int n = 2 * L.radius[li] + 1;
+      for (int e = tid; e < n; e += HB_THREADS) wsm[wo + e] = __ldg(weights + L.woff[li] + e);
+      wo += n;
     }
+  }
+  // flat staging loop, 4 independent loads in flight per thread
+  const int nrow = min(HB_WARPS, hrows - row0);
+  const int total = nrow * span;
+  for (int f0 = tid; f0 < total; f0 += 4 * HB_THREADS) {
+    double v[4];
+    int so[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int f = f0 + i * HB_THREADS;
+      const int r = f / span, e = f - r * span;
+      so[i] = -1;
+      v[i] = 0.0;
+      if (f < total) {
+        int col = x_tile - RS + e;
+        col = min(max(col, 0), w - 1);                                           // sift.js:116-117 clamp
+        const int sc = ups ? (col >> 1) : col;                                   // matrix2d.js:129 floor(j*0.5)
+        v[i] = src_at((const char *)src + (size_t)(row0 + r) * src_pitch, min(sc, src_w - 1), dtype);
+        so[i] = r * rowstride + padidx(e);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (so[i] >= 0) rows[so[i]] = v[i];
   }
   __syncthreads();
 
@@ -116,16 +140,21 @@ hblur_kernel(const void *__restrict__ src, size_t src_pitch, int src_w, int dtyp
   const int x0 = x_tile + threadIdx.x * NOUT;
   if (y >= hrows || x0 >= w) return;
   const double *rowsm = rows + threadIdx.y * rowstride;
-  const int e0 = threadIdx.x * NOUT;                 // sample feeding tap 0 of output 0
-  double acc[NOUT];
-  window8(wsm, n, [&](int p) { return rowsm[padidx(e0 + p)]; }, acc);
-  double *out = L.T[li] + (size_t)y * w + x0;
-  if (x0 + NOUT <= w && ((w & 1) == 0)) {
+  int wo = 0;
+  for (int li = li_first; li < li_last; li++) {
+    const int R = L.radius[li], n = 2 * R + 1;
+    const int e0 = threadIdx.x * NOUT + RS - R;      // sample feeding tap 0 of output 0
+    double acc[NOUT];
+    window8(wsm + wo, n, [&](int p) { return rowsm[padidx(e0 + p)]; }, acc);
+    wo += n;
+    double *out = L.T[li] + (size_t)y * w + x0;
+    if (x0 + NOUT <= w && ((w & 1) == 0)) {
 #pragma unroll
-    for (int k = 0; k < NOUT; k += 2) *reinterpret_cast<double2 *>(out + k) = make_double2(acc[k], acc[k + 1]);
-  } else {
+      for (int k = 0; k < NOUT; k += 2) *reinterpret_cast<double2 *>(out + k) = make_double2(acc[k], acc[k + 1]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < NOUT; k++) if (x0 + k < w) out[k] = acc[k];
+      for (int k = 0; k < NOUT; k++) if (x0 + k < w) out[k] = acc[k];
+    }
   }
 }
 
@@ -145,6 +174,8 @@ static BlurLevels make_levels(const LevelPlan *plans, int first_level, int nlev,
   return L;
 }
 
+#define SIFT_BIG_OCTAVE_WARPS (148 * 16)   // enough warps to fill the chip with one thread per 8 outputs of all levels
+
 void launch_hblur(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int src_h,
                   int upsample, int w, int hrows, const double *d_weights, const LevelPlan *plans, int first_level,
                   int nlev, double *const *T, double **)
@@ -153,16 +184,22 @@ void launch_hblur(cudaStream_t st, const void *src, int dtype, size_t src_pitch_
   int rmax;
   BlurLevels L = make_levels(plans, first_level, nlev, T, &rmax);
   dim3 block(32, HB_WARPS);
-  dim3 grid((w + HB_TW - 1) / HB_TW, (hrows + HB_WARPS - 1) / HB_WARPS, L.nlev);
+  dim3 grid((w + HB_TW - 1) / HB_TW, (hrows + HB_WARPS - 1) / HB_WARPS, 1);
+  const bool all_levels = (size_t)grid.x * grid.y * HB_WARPS >= SIFT_BIG_OCTAVE_WARPS;
+  int wtotal = 0;
+  for (int i = 0; i < L.nlev; i++) wtotal += 2 * L.radius[i] + 1;
+  if (!all_levels) { grid.z = L.nlev; }
   const int span = HB_TW + 2 * rmax + NOUT;
-  const size_t smem = ((size_t)((2 * rmax + 2) & ~1) + (size_t)HB_WARPS * ((span + (span >> 3)) + 1)) * sizeof(double);
+  const size_t smem = ((size_t)((wtotal + 2) & ~1) + (size_t)HB_WARPS * ((span + (span >> 3)) + 1)) * sizeof(double);
   cudaFuncSetAttribute(hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  hblur_kernel<<<grid, block, smem, st>>>(src, src_pitch_bytes, src_w, dtype, upsample, w, hrows, d_weights, L);
+  hblur_kernel<<<grid, block, smem, st>>>(src, src_pitch_bytes, src_w, dtype, upsample, w, hrows, rmax,
+                                          all_levels ? wtotal : 2 * rmax + 1, d_weights, L);
 }
 
 // ------------------------------------------------------------------- vblur ----
 #define VB_COLS 32
-#define VB_RG 2                        // row groups of 8 per CTA -> 16 rows
+#define VB_RG 2                        // level-parallel variant: row groups of 8 per CTA -> 16 rows
+#define VS_RG 8                        // level-sequential variant: 64 rows per CTA
 
 struct VBlurArgs {
   OctaveDev oct;
@@ -171,14 +208,90 @@ struct VBlurArgs {
   BlurLevels L;
 };
 
+// Write one thread's 8 outputs of level s: G_s, D_{s-1} = prev - G_s (sift.js:172), seed of the next octave.
+__device__ __forceinline__ void vblur_store(const VBlurArgs &A, int s, int x, int y0, const double (&acc)[NOUT],
+                                            const double (&prev)[NOUT])
+{
+  const int h = A.oct.h, pitch = A.oct.pitch;
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+    const int y = y0 + k;
+    if (y >= h) break;
+    const size_t o = (size_t)y * pitch + x;
+    if (A.keep_gauss) A.oct.gauss[s][o] = (float)acc[k];
+    if (s > 0) A.oct.dog[s - 1][o] = (float)(prev[k] - acc[k]);
+    if (A.has_next && s == A.spo && ((y | x) & 1) == 0) {                      // matrix2d.js:129 in[2a][2b]
+      A.next.seed64[(size_t)(y >> 1) * A.next.w + (x >> 1)] = acc[k];
+      A.next.gauss[0][(size_t)(y >> 1) * A.next.pitch + (x >> 1)] = (float)acc[k];
+    }
+  }
+}
+
+__device__ __forceinline__ void vblur_window(const VBlurArgs &A, const double *__restrict__ wsm, int li, int x, int y0,
+                                             double (&acc)[NOUT])
+{
+  const int w = A.oct.w, h = A.oct.h;
+  const int R = A.L.radius[li];
+  const double *__restrict__ T = A.L.T[li] + x;
+  if (!A.ups && y0 - R >= 0 && y0 + R + 2 * NOUT <= h) {        // interior: no clamping, plain strides
+    const double *base = T + (size_t)(y0 - R) * w;
+    window8(wsm, 2 * R + 1, [&](int p) { return __ldg(base + (size_t)p * w); }, acc);
+  } else {
+    const int ups = A.ups;
+    window8(wsm, 2 * R + 1, [&](int p) {
+      int yy = min(max(y0 + p - R, 0), h - 1);                                 // sift.js:118-119 clamp
+      if (ups) yy >>= 1;                                                       // rows 2b and 2b+1 are equal
+      return __ldg(T + (size_t)yy * w);
+    }, acc);
+  }
+}
+
+// Level-sequential: one thread = one column x 8 rows x all levels, previous level kept in registers.
+__global__ void __launch_bounds__(VB_COLS *VS_RG)
+vblur_seq_kernel(const double *__restrict__ weights, VBlurArgs A, int wtotal)
+{
+  extern __shared__ double wsm[];
+  const int tid = threadIdx.y * VB_COLS + threadIdx.x;
+  {
+    int wo = 0;
+    for (int i = 0; i < A.L.nlev; i++) {
+      const int n_i = 2 * A.L.radius[i] + 1;
+      for (int e = tid; e < n_i; e += VB_COLS * VS_RG) wsm[wo + e] = __ldg(weights + A.L.woff[i] + e);
+      wo += n_i;
+    }
+  }
+  __syncthreads();
+  const int w = A.oct.w, h = A.oct.h;
+  const int x = blockIdx.x * VB_COLS + threadIdx.x;
+  const int y0 = (blockIdx.y * VS_RG + threadIdx.y) * NOUT;
+  if (x >= w || y0 >= h) return;
+  double prev[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) prev[k] = 0.0;
+  if (A.seed_is_level0) {                               // octaves >= 1: level 0 is the unblurred seed
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) prev[k] = A.oct.seed64[(size_t)min(y0 + k, h - 1) * w + x];
+  }
+  int wo = 0;
+  for (int li = 0; li < A.L.nlev; li++) {
+    double acc[NOUT];
+    vblur_window(A, wsm + wo, li, x, y0, acc);
+    wo += 2 * A.L.radius[li] + 1;
+    vblur_store(A, A.L.level[li], x, y0, acc, prev);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) prev[k] = acc[k];
+  }
+  (void)wtotal;
+}
+
+// Level-parallel (small octaves): levels across threadIdx.z, unrounded values exchanged through shared memory.
 __global__ void __launch_bounds__(VB_COLS *VB_RG *SIFT_MAX_LEVELS)
-vblur_kernel(const double *__restrict__ weights, VBlurArgs A)
+vblur_par_kernel(const double *__restrict__ weights, VBlurArgs A)
 {
   extern __shared__ double smem[];
-  // G64[li][row][col]: unrounded level values of the tile, for D_{s-1} = G_{s-1} - G_s
-  double *G64 = smem;
+  double *G64 = smem;                                     // [li][row][col]
   const int nl = A.L.nlev;
-  double *wsm = smem + nl * (VB_RG * NOUT) * VB_COLS;     // per level: taps at wsm + wbase[li]
+  double *wsm = smem + nl * (VB_RG * NOUT) * VB_COLS;
   const int li = threadIdx.z;
   const int tid = (threadIdx.z * VB_RG + threadIdx.y) * VB_COLS + threadIdx.x;
   const int nthreads = VB_COLS * VB_RG * nl;
@@ -192,44 +305,25 @@ vblur_kernel(const double *__restrict__ weights, VBlurArgs A)
   }
   __syncthreads();
 
-  const int w = A.oct.w, h = A.oct.h, pitch = A.oct.pitch;
+  const int w = A.oct.w, h = A.oct.h;
   const int x = blockIdx.x * VB_COLS + threadIdx.x;
   const int y0 = (blockIdx.y * VB_RG + threadIdx.y) * NOUT;
-  const int R = A.L.radius[li], s = A.L.level[li];
   const bool active = x < w && y0 < h;
-  double acc[NOUT];
+  double acc[NOUT], prev[NOUT];
   if (active) {
-    const double *__restrict__ T = A.L.T[li];
-    const int ups = A.ups;
-    window8(wsm + wbase, 2 * R + 1, [&](int p) {
-      int yy = min(max(y0 + p - R, 0), h - 1);                                 // sift.js:118-119 clamp
-      if (ups) yy >>= 1;                                                       // rows 2b and 2b+1 are equal
-      return __ldg(T + (size_t)yy * w + x);
-    }, acc);
+    vblur_window(A, wsm + wbase, li, x, y0, acc);
     double *g = G64 + ((li * VB_RG + threadIdx.y) * NOUT) * VB_COLS + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < NOUT; k++) g[k * VB_COLS] = acc[k];
   }
   __syncthreads();
   if (!active) return;
-
 #pragma unroll
   for (int k = 0; k < NOUT; k++) {
-    const int y = y0 + k;
-    if (y >= h) break;
-    const size_t o = (size_t)y * pitch + x;
-    if (A.keep_gauss) A.oct.gauss[s][o] = (float)acc[k];
-    if (s > 0) {
-      double prev;
-      if (li > 0) prev = G64[(((li - 1) * VB_RG + threadIdx.y) * NOUT + k) * VB_COLS + threadIdx.x];
-      else prev = A.oct.seed64[(size_t)y * w + x];                             // level 0 of octaves >= 1 is the seed
-      A.oct.dog[s - 1][o] = (float)(prev - acc[k]);                            // sift.js:172
-    }
-    if (A.has_next && s == A.spo && ((y | x) & 1) == 0) {                      // matrix2d.js:129 in[2a][2b]
-      A.next.seed64[(size_t)(y >> 1) * A.next.w + (x >> 1)] = acc[k];
-      A.next.gauss[0][(size_t)(y >> 1) * A.next.pitch + (x >> 1)] = (float)acc[k];
-    }
+    if (li > 0) prev[k] = G64[(((li - 1) * VB_RG + threadIdx.y) * NOUT + k) * VB_COLS + threadIdx.x];
+    else prev[k] = A.seed_is_level0 ? A.oct.seed64[(size_t)min(y0 + k, h - 1) * w + x] : 0.0;
   }
+  vblur_store(A, A.L.level[li], x, y0, acc, prev);
 }
 
 void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
@@ -248,11 +342,20 @@ void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const dou
   A.L = make_levels(plans, first_level, oct.nlev, T, &rmax);
   int wtotal = 0;
   for (int i = 0; i < A.L.nlev; i++) wtotal += 2 * A.L.radius[i] + 1;
-  dim3 block(VB_COLS, VB_RG, A.L.nlev);
-  dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VB_RG * NOUT - 1) / (VB_RG * NOUT));
-  const size_t smem = ((size_t)A.L.nlev * VB_RG * NOUT * VB_COLS + wtotal + 1) * sizeof(double);
-  cudaFuncSetAttribute(vblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  vblur_kernel<<<grid, block, smem, st>>>(d_weights, A);
+  const size_t warps = ((size_t)(oct.w + 31) / 32) * ((oct.h + NOUT - 1) / NOUT);
+  if (warps >= SIFT_BIG_OCTAVE_WARPS) {
+    dim3 block(VB_COLS, VS_RG);
+    dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VS_RG * NOUT - 1) / (VS_RG * NOUT));
+    const size_t smem = (size_t)(wtotal + 1) * sizeof(double);
+    cudaFuncSetAttribute(vblur_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vblur_seq_kernel<<<grid, block, smem, st>>>(d_weights, A, wtotal);
+  } else {
+    dim3 block(VB_COLS, VB_RG, A.L.nlev);
+    dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VB_RG * NOUT - 1) / (VB_RG * NOUT));
+    const size_t smem = ((size_t)A.L.nlev * VB_RG * NOUT * VB_COLS + wtotal + 1) * sizeof(double);
+    cudaFuncSetAttribute(vblur_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vblur_par_kernel<<<grid, block, smem, st>>>(d_weights, A);
+  }
 }
 
 // ------------------------------------------------ step-function helpers (fp64) --

@@ -77,6 +77,9 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
 void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int spo, double pix_threshold,
                         int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,
                         Counters *ctr);
+void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
+                     double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
+                     int low_cap, Counters *ctr);
 void launch_scan_f64(cudaStream_t st, const double *d0, const double *d1, const double *d2, int rows, int cols,
                      double pix_threshold, int32_t *cand_xy, double *cand_val, int cand_cap,
                      int32_t *low_xy, double *low_val, int low_cap, int *counts /* [2] */);

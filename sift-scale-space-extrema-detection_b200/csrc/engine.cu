@@ -321,12 +321,10 @@ static int run_scan(sift_ctx *ctx, int count_low, const sift_params *thr = nullp
   if (thr) { tp.contrastThreshold = thr->contrastThreshold; tp.preFilterFactor = thr->preFilterFactor; }
   const double pix_thr = contrast_threshold(tp) * tp.preFilterFactor;               // sift.js:293
   prof_begin(ctx, SIFT_PROF_SCAN);
-  for (int o = 0; o < ctx->n_oct; o++) {
-    launch_scan_octave(ctx->stream, ctx->octs[o], o, ctx->prm.scalesPerOctave, pix_thr, count_low,
-                       (sift_candidate *)ctx->cand.p, ctx->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
-                       dev_counters(ctx));
-    ctx->launches += 1;
-  }
+  launch_scan_all(ctx->stream, ctx->octs, ctx->d_octs, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
+                  (sift_candidate *)ctx->cand.p, ctx->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
+                  dev_counters(ctx));
+  ctx->launches += 1;
   prof_end(ctx);
   CK(cudaGetLastError());
   return SIFT_OK;

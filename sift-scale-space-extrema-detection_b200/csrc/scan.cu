@@ -97,6 +97,135 @@ void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int s
                                              low_cap, ctr);
 }
 
+// ---- whole pyramid in one launch: 4 pixels per thread (one 16-byte load per scale), the 26
+// neighbours are only fetched for pixels that pass the pre-filter, in-plane ring first.
+#define SA_PX 4
+#define SA_TW (32 * SA_PX)    // 128 pixels per tile row
+#define SA_TH 8
+
+struct ScanAllArgs {
+  int n_oct, spo, count_low;
+  int tile_start[SIFT_MAX_OCTAVES + 1];
+  int tiles_x[SIFT_MAX_OCTAVES];
+  double pix_threshold;
+};
+
+__device__ __forceinline__ bool is_extremum_ring_first(const float *__restrict__ p0, const float *__restrict__ p1,
+                                                       const float *__restrict__ p2, size_t pitch, int x, int y,
+                                                       float c)
+{
+  const float *r1 = p1 + (size_t)y * pitch + x;
+  bool is_min = true, is_max = true;
+  {
+    const float a = r1[-1], b = r1[1];
+    is_min = (a > c) && (b > c);
+    is_max = (a < c) && (b < c);
+    if (!(is_min || is_max)) return false;
+  }
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy += 2) {
+    const float *row = r1 + (ptrdiff_t)dy * (ptrdiff_t)pitch;
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const float v = row[dx];
+      is_min = is_min && (v > c);
+      is_max = is_max && (v < c);
+    }
+    if (!(is_min || is_max)) return false;
+  }
+  const float *pl[2] = { p0, p2 };
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+      const float *row = pl[p] + (size_t)(y + dy) * pitch + x;
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        const float v = row[dx];
+        is_min = is_min && (v > c);
+        is_max = is_max && (v < c);
+      }
+    }
+    if (!(is_min || is_max)) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(32 * SA_TH)
+scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidate *__restrict__ cand, int cand_cap,
+                sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
+{
+  int o = 0;
+  while (o + 1 < A.n_oct && (int)blockIdx.x >= A.tile_start[o + 1]) o++;
+  const int t = blockIdx.x - A.tile_start[o];
+  const int ty = t / A.tiles_x[o], tx = t - ty * A.tiles_x[o];
+  const OctaveDev &oc = octs[o];
+  const int w = oc.w, h = oc.h;
+  const size_t pitch = oc.pitch;
+  const int x0 = tx * SA_TW + threadIdx.x * SA_PX;
+  const int y = ty * SA_TH + threadIdx.y;
+  const bool row_ok = (y >= 1 && y < h - 1) && x0 < w;                                // sift.js:221
+  for (int s = 1; s <= A.spo; s++) {                                                  // background.js:377
+    const float *p1 = oc.dog[s];
+    float c[SA_PX] = { 0.f, 0.f, 0.f, 0.f };
+    if (row_ok) {
+      const float4 v = *reinterpret_cast<const float4 *>(p1 + (size_t)y * pitch + x0);
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    }
+    unsigned hit = 0, hit_low = 0;
+#pragma unroll
+    for (int i = 0; i < SA_PX; i++) {
+      const int x = x0 + i;
+      if (row_ok && x >= 1 && x < w - 1) {                                            // sift.js:222
+        const bool strong = (double)fabsf(c[i]) >= A.pix_threshold;                   // sift.js:294
+        if (strong || A.count_low) {
+          if (is_extremum_ring_first(oc.dog[s - 1], p1, oc.dog[s + 1], pitch, x, y, c[i])) {
+            if (strong) hit |= 1u << i; else hit_low |= 1u << i;
+          }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, hit != 0)) {
+#pragma unroll
+      for (int i = 0; i < SA_PX; i++) {
+        const int slot = warp_append((hit >> i) & 1u, &ctr->n_cand);
+        if (slot >= 0 && slot < cand_cap) {
+          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = y; r.value = c[i]; r.reserved0 = 0;
+          cand[slot] = r;
+        }
+      }
+    }
+    if (A.count_low && __any_sync(0xffffffffu, hit_low != 0)) {
+#pragma unroll
+      for (int i = 0; i < SA_PX; i++) {
+        const int slot = warp_append((hit_low >> i) & 1u, &ctr->n_low);
+        if (low && slot >= 0 && slot < low_cap) {
+          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = y; r.value = c[i]; r.reserved0 = 0;
+          low[slot] = r;
+        }
+      }
+    }
+  }
+}
+
+void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
+                     double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
+                     int low_cap, Counters *ctr)
+{
+  ScanAllArgs A;
+  A.n_oct = n_oct; A.spo = spo; A.count_low = count_low; A.pix_threshold = pix_threshold;
+  int total = 0;
+  for (int o = 0; o < n_oct; o++) {
+    A.tile_start[o] = total;
+    A.tiles_x[o] = (h_octs[o].w + SA_TW - 1) / SA_TW;
+    total += A.tiles_x[o] * ((h_octs[o].h + SA_TH - 1) / SA_TH);
+  }
+  A.tile_start[n_oct] = total;
+  if (total == 0) return;
+  dim3 block(32, SA_TH);
+  scan_all_kernel<<<total, block, 0, st>>>(d_octs, A, cand, cand_cap, low, low_cap, ctr);
+}
+
 // ---- step function: SIFT_findExtremas on three Matrix2D (fp64) images ----------
 __global__ void __launch_bounds__(SC_BX *SC_BY)
 scan_f64_kernel(const double *__restrict__ d0, const double *__restrict__ d1, const double *__restrict__ d2,
