@@ -247,41 +247,86 @@ __device__ __forceinline__ void vblur_window(const VBlurArgs &A, const double *_
 }
 
 // Level-sequential: one thread = one column x 8 rows x all levels, previous level kept in registers.
-__global__ void __launch_bounds__(VB_COLS *VS_RG)
-vblur_seq_kernel(const double *__restrict__ weights, VBlurArgs A, int wtotal)
+// The T rows a CTA needs for a level ((64 + 2R + 1) x 32 columns) are brought into shared memory with
+// cp.async (LDGSTS) one level ahead of the arithmetic, so the sliding windows never wait on global memory.
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 {
-  extern __shared__ double wsm[];
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define VS_THREADS (VB_COLS * VS_RG)
+
+__device__ __forceinline__ void vseq_issue_tile(const VBlurArgs &A, int li, double *__restrict__ tile, int x0, int ybase,
+                                                int tid)
+{
+  const int w = A.oct.w, h = A.oct.h, R = A.L.radius[li];
+  const int rows = VS_RG * NOUT + 2 * R + 1;
+  const double *__restrict__ T = A.L.T[li];
+  const int c = tid & (VB_COLS - 1);
+  if (x0 + c < w) {
+    for (int i = tid / VB_COLS; i < rows; i += VS_THREADS / VB_COLS) {
+      int yy = min(max(ybase - R + i, 0), h - 1);                              // sift.js:118-119 clamp
+      if (A.ups) yy >>= 1;                                                     // rows 2b and 2b+1 are equal
+      cp_async8(tile + i * VB_COLS + c, T + (size_t)yy * w + x0 + c);
+    }
+  }
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(VS_THREADS, 3)
+vblur_seq_kernel(const double *__restrict__ weights, VBlurArgs A, int wtotal, int tile_elems)
+{
+  extern __shared__ double smem[];
+  double *wsm = smem;
+  double *tile0 = smem + ((wtotal + 1) & ~1);
+  double *tile1 = tile0 + tile_elems;
   const int tid = threadIdx.y * VB_COLS + threadIdx.x;
+  const int w = A.oct.w, h = A.oct.h;
+  const int x0 = blockIdx.x * VB_COLS, ybase = blockIdx.y * VS_RG * NOUT;
+  vseq_issue_tile(A, 0, tile0, x0, ybase, tid);
   {
     int wo = 0;
     for (int i = 0; i < A.L.nlev; i++) {
       const int n_i = 2 * A.L.radius[i] + 1;
-      for (int e = tid; e < n_i; e += VB_COLS * VS_RG) wsm[wo + e] = __ldg(weights + A.L.woff[i] + e);
+      for (int e = tid; e < n_i; e += VS_THREADS) wsm[wo + e] = __ldg(weights + A.L.woff[i] + e);
       wo += n_i;
     }
   }
-  __syncthreads();
-  const int w = A.oct.w, h = A.oct.h;
-  const int x = blockIdx.x * VB_COLS + threadIdx.x;
-  const int y0 = (blockIdx.y * VS_RG + threadIdx.y) * NOUT;
-  if (x >= w || y0 >= h) return;
+  const int x = x0 + threadIdx.x;
+  const int y0 = ybase + threadIdx.y * NOUT;
+  const bool active = x < w && y0 < h;
   double prev[NOUT];
 #pragma unroll
   for (int k = 0; k < NOUT; k++) prev[k] = 0.0;
-  if (A.seed_is_level0) {                               // octaves >= 1: level 0 is the unblurred seed
+  if (A.seed_is_level0 && active) {                     // octaves >= 1: level 0 is the unblurred seed
 #pragma unroll
     for (int k = 0; k < NOUT; k++) prev[k] = A.oct.seed64[(size_t)min(y0 + k, h - 1) * w + x];
   }
   int wo = 0;
   for (int li = 0; li < A.L.nlev; li++) {
-    double acc[NOUT];
-    vblur_window(A, wsm + wo, li, x, y0, acc);
-    wo += 2 * A.L.radius[li] + 1;
-    vblur_store(A, A.L.level[li], x, y0, acc, prev);
+    double *cur = (li & 1) ? tile1 : tile0;
+    if (li + 1 < A.L.nlev) {
+      vseq_issue_tile(A, li + 1, (li & 1) ? tile0 : tile1, x0, ybase, tid);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                    // tile li (and, first time, the taps) visible to the CTA
+    const int n = 2 * A.L.radius[li] + 1;
+    if (active) {
+      double acc[NOUT];
+      const double *base = cur + (threadIdx.y * NOUT) * VB_COLS + threadIdx.x;
+      window8(wsm + wo, n, [&](int p) { return base[p * VB_COLS]; }, acc);
+      vblur_store(A, A.L.level[li], x, y0, acc, prev);
 #pragma unroll
-    for (int k = 0; k < NOUT; k++) prev[k] = acc[k];
+      for (int k = 0; k < NOUT; k++) prev[k] = acc[k];
+    }
+    wo += n;
+    __syncthreads();                                    // cur is overwritten by the copy issued next iteration
   }
-  (void)wtotal;
 }
 
 // Level-parallel (small octaves): levels across threadIdx.z, unrounded values exchanged through shared memory.
@@ -346,9 +391,10 @@ void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const dou
   if (warps >= SIFT_BIG_OCTAVE_WARPS) {
     dim3 block(VB_COLS, VS_RG);
     dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VS_RG * NOUT - 1) / (VS_RG * NOUT));
-    const size_t smem = (size_t)(wtotal + 1) * sizeof(double);
+    const int tile_elems = (VS_RG * NOUT + 2 * rmax + 1 + 1) * VB_COLS;    // +1 row: window prefetch slack
+    const size_t smem = ((size_t)((wtotal + 2) & ~1) + 2 * (size_t)tile_elems) * sizeof(double);
     cudaFuncSetAttribute(vblur_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vblur_seq_kernel<<<grid, block, smem, st>>>(d_weights, A, wtotal);
+    vblur_seq_kernel<<<grid, block, smem, st>>>(d_weights, A, wtotal, tile_elems);
   } else {
     dim3 block(VB_COLS, VB_RG, A.L.nlev);
     dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VB_RG * NOUT - 1) / (VB_RG * NOUT));

@@ -155,10 +155,13 @@ __global__ void __launch_bounds__(32 * SA_TH)
 scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidate *__restrict__ cand, int cand_cap,
                 sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
 {
-  int o = 0;
-  while (o + 1 < A.n_oct && (int)blockIdx.x >= A.tile_start[o + 1]) o++;
-  const int t = blockIdx.x - A.tile_start[o];
-  const int ty = t / A.tiles_x[o], tx = t - ty * A.tiles_x[o];
+  // static indices only: a dynamically indexed kernel-parameter array is copied to local memory
+  int o = 0, t0 = 0, ntx = A.tiles_x[0];
+#pragma unroll
+  for (int i = 1; i < SIFT_MAX_OCTAVES; i++)
+    if (i < A.n_oct && (int)blockIdx.x >= A.tile_start[i]) { o = i; t0 = A.tile_start[i]; ntx = A.tiles_x[i]; }
+  const int t = blockIdx.x - t0;
+  const int ty = t / ntx, tx = t - ty * ntx;
   const OctaveDev &oc = octs[o];
   const int w = oc.w, h = oc.h;
   const size_t pitch = oc.pitch;
