@@ -185,12 +185,13 @@ void launch_hblur(cudaStream_t st, const void *src, int dtype, size_t src_pitch_
   BlurLevels L = make_levels(plans, first_level, nlev, T, &rmax);
   dim3 block(32, HB_WARPS);
   dim3 grid((w + HB_TW - 1) / HB_TW, (hrows + HB_WARPS - 1) / HB_WARPS, 1);
-  const bool all_levels = (size_t)grid.x * grid.y * HB_WARPS >= SIFT_BIG_OCTAVE_WARPS;
   int wtotal = 0;
   for (int i = 0; i < L.nlev; i++) wtotal += 2 * L.radius[i] + 1;
-  if (!all_levels) { grid.z = L.nlev; }
   const int span = HB_TW + 2 * rmax + NOUT;
   const size_t smem = ((size_t)((wtotal + 2) & ~1) + (size_t)HB_WARPS * ((span + (span >> 3)) + 1)) * sizeof(double);
+  // rows are staged once and every level is computed from them, unless that no longer fits shared memory
+  const bool all_levels = smem <= 160 * 1024;
+  if (!all_levels) { grid.z = L.nlev; }
   cudaFuncSetAttribute(hblur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   hblur_kernel<<<grid, block, smem, st>>>(src, src_pitch_bytes, src_w, dtype, upsample, w, hrows, rmax,
                                           all_levels ? wtotal : 2 * rmax + 1, d_weights, L);
@@ -387,12 +388,12 @@ void launch_vblur(cudaStream_t st, int upsample, const OctaveDev &oct, const dou
   A.L = make_levels(plans, first_level, oct.nlev, T, &rmax);
   int wtotal = 0;
   for (int i = 0; i < A.L.nlev; i++) wtotal += 2 * A.L.radius[i] + 1;
-  const size_t warps = ((size_t)(oct.w + 31) / 32) * ((oct.h + NOUT - 1) / NOUT);
-  if (warps >= SIFT_BIG_OCTAVE_WARPS) {
+  const int tile_elems = (VS_RG * NOUT + 2 * rmax + 1 + 1) * VB_COLS;      // +1 row: window prefetch slack
+  const size_t smem_seq = ((size_t)((wtotal + 2) & ~1) + 2 * (size_t)tile_elems) * sizeof(double);
+  if (smem_seq <= 200 * 1024) {
     dim3 block(VB_COLS, VS_RG);
     dim3 grid((oct.w + VB_COLS - 1) / VB_COLS, (oct.h + VS_RG * NOUT - 1) / (VS_RG * NOUT));
-    const int tile_elems = (VS_RG * NOUT + 2 * rmax + 1 + 1) * VB_COLS;    // +1 row: window prefetch slack
-    const size_t smem = ((size_t)((wtotal + 2) & ~1) + 2 * (size_t)tile_elems) * sizeof(double);
+    const size_t smem = smem_seq;
     cudaFuncSetAttribute(vblur_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     vblur_seq_kernel<<<grid, block, smem, st>>>(d_weights, A, wtotal, tile_elems);
   } else {

@@ -53,10 +53,15 @@ struct sift_ctx {
   OctaveDev *d_octs = nullptr;
 
   // ---- device arenas (grow only)
-  Scratch planes, seeds, tbuf, image, cand, low, outbuf, misc[6];
+  // image / outbuf / h_out exist twice: slot 1 is only used by the pipelined batch path
+  Scratch planes, seeds, tbuf, image_s[2], cand, low, outbuf_s[2], misc[6];
   int cand_cap = 0, low_cap = 0, kp_cap = 0;
-  void *h_out = nullptr;      // pinned mirror of outbuf
-  size_t h_out_cap = 0;
+  int slot = 0;               // which image / outbuf / h_out the stage helpers address
+  void *h_out_s[2] = { nullptr, nullptr };   // pinned mirrors of outbuf
+  size_t h_out_cap_s[2] = { 0, 0 };
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_d2h[2] = { nullptr, nullptr };
+  std::vector<uint64_t> sort_a, sort_b;
   void *h_cand = nullptr;     // pinned candidate staging
   size_t h_cand_cap = 0;
 
@@ -261,7 +266,7 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
     ctx->cand_cap = want;
   }
   if (want > ctx->kp_cap) {
-    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
     ctx->kp_cap = want;
   }
   ctx->prm = *p; ctx->in_w = w; ctx->in_h = h; ctx->n_oct = n_oct; ctx->nlev = nlev;
@@ -269,8 +274,8 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
   return SIFT_OK;
 }
 
-static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->outbuf.p; }
-static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->outbuf.p + sizeof(Counters)); }
+static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->outbuf_s[ctx->slot].p; }
+static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->outbuf_s[ctx->slot].p + sizeof(Counters)); }
 
 // Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
 static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
@@ -385,6 +390,41 @@ static inline uint64_t cand_key(int o, int s, int y, int x)
 }
 
 // Reference output order = candidate order: octave, scale, row, column (background.js:468-471, sift.js:221-222).
+// LSD radix sort of (key, index) and a gather into `dst` (may alias nothing in `src`).
+static void sort_keypoints_into(sift_ctx *ctx, const sift_keypoint *src, int n, sift_keypoint *dst, int dst_cap)
+{
+  if (n <= 0) return;
+  std::vector<uint64_t> &a = ctx->sort_a, &b = ctx->sort_b;
+  a.resize((size_t)n); b.resize((size_t)n);
+  uint64_t ormask = 0;
+  for (int i = 0; i < n; i++) {
+    const uint64_t k = cand_key(src[i].octave, src[i].candScale, src[i].candY, src[i].candX);
+    ormask |= k;
+    a[i] = k;   // index carried separately below
+  }
+  // keys are < 2^62; pack index (n < 2^26) is not possible in 64 bits for large images, so sort index pairs
+  std::vector<uint32_t> ia((size_t)n), ib((size_t)n);
+  for (int i = 0; i < n; i++) ia[i] = (uint32_t)i;
+  const int DIG = 11, NB = 1 << DIG;
+  std::vector<uint32_t> hist((size_t)NB);
+  for (int shift = 0; shift < 64; shift += DIG) {
+    if (((ormask >> shift) & (NB - 1)) == 0 && (ormask >> shift) != 0 && false) continue;
+    if ((ormask >> shift) == 0) break;
+    if (((ormask >> shift) & (uint64_t)(NB - 1)) == 0) continue;   // digit is zero in every key
+    std::fill(hist.begin(), hist.end(), 0u);
+    for (int i = 0; i < n; i++) hist[(a[i] >> shift) & (NB - 1)]++;
+    uint32_t sum = 0;
+    for (int d = 0; d < NB; d++) { const uint32_t c = hist[d]; hist[d] = sum; sum += c; }
+    for (int i = 0; i < n; i++) {
+      const uint32_t pos = hist[(a[i] >> shift) & (NB - 1)]++;
+      b[pos] = a[i]; ib[pos] = ia[i];
+    }
+    a.swap(b); ia.swap(ib);
+  }
+  const int m = std::min(n, dst_cap);
+  for (int i = 0; i < m; i++) dst[i] = src[ia[i]];
+}
+
 static void sort_keypoints(sift_keypoint *k, int n)
 {
   std::sort(k, k + n, [](const sift_keypoint &a, const sift_keypoint &b) {
@@ -409,9 +449,9 @@ static int upload_image(sift_ctx *ctx, const void *image, int dtype, int w, int 
   if (pitch_bytes == 0) pitch_bytes = row;
   if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
   int rc;
-  if ((rc = grow(ctx, ctx->image, row * h))) return rc;
-  if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->image.p, image, row * h, cudaMemcpyHostToDevice, ctx->stream));
-  else CK(cudaMemcpy2DAsync(ctx->image.p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = grow(ctx, ctx->image_s[ctx->slot], row * h))) return rc;
+  if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->image_s[ctx->slot].p, image, row * h, cudaMemcpyHostToDevice, ctx->stream));
+  else CK(cudaMemcpy2DAsync(ctx->image_s[ctx->slot].p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->stream));
   *dev_pitch = row;
   return SIFT_OK;
 }
@@ -422,18 +462,18 @@ static int download_keypoints(sift_ctx *ctx, Counters *c, sift_keypoint **kps)
 {
   int rc;
   const size_t first = sizeof(Counters) + (size_t)std::min(ctx->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
-  if ((rc = grow_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
+  if ((rc = grow_pinned(ctx, &ctx->h_out_s[ctx->slot], &ctx->h_out_cap_s[ctx->slot], sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
     return rc;
-  CK(cudaMemcpyAsync(ctx->h_out, ctx->outbuf.p, first, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_out_s[ctx->slot], ctx->outbuf_s[ctx->slot].p, first, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  *c = *(Counters *)ctx->h_out;
+  *c = *(Counters *)ctx->h_out_s[ctx->slot];
   const int n = std::min(c->n_kp, ctx->kp_cap);
   if (n > FIRST_CHUNK) {
-    CK(cudaMemcpyAsync((char *)ctx->h_out + first, (char *)ctx->outbuf.p + first,
+    CK(cudaMemcpyAsync((char *)ctx->h_out_s[ctx->slot] + first, (char *)ctx->outbuf_s[ctx->slot].p + first,
                        (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  *kps = (sift_keypoint *)((char *)ctx->h_out + sizeof(Counters));
+  *kps = (sift_keypoint *)((char *)ctx->h_out_s[ctx->slot] + sizeof(Counters));
   return SIFT_OK;
 }
 
@@ -446,14 +486,11 @@ static int scan_refine_download(sift_ctx *ctx, Counters *c, sift_keypoint **kps,
     if ((rc = run_scan(ctx, count_low))) return rc;
     if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->kp_cap))) return rc;
     if ((rc = download_keypoints(ctx, c, kps))) return rc;
-    if (c->n_cand <= ctx->cand_cap && c->n_kp <= ctx->kp_cap) {
-      sort_keypoints(*kps, c->n_kp);
-      return SIFT_OK;
-    }
+    if (c->n_cand <= ctx->cand_cap && c->n_kp <= ctx->kp_cap) return SIFT_OK;   // unordered: callers sort-gather
     const int want = std::max(c->n_cand, c->n_kp) + 1024;
     if ((rc = grow(ctx, ctx->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
     ctx->cand_cap = want;
-    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
     ctx->kp_cap = want;
   }
   return fail(ctx, SIFT_ERR_CAPACITY, "candidate buffer kept overflowing");
@@ -514,12 +551,19 @@ SIFT_API void sift_destroy(sift_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  Scratch *all[] = { &c->planes, &c->seeds, &c->tbuf, &c->image, &c->cand, &c->low, &c->outbuf,
+  Scratch *all[] = { &c->planes, &c->seeds, &c->tbuf, &c->image_s[0], &c->image_s[1], &c->cand, &c->low, &c->outbuf_s[0], &c->outbuf_s[1],
                      &c->misc[0], &c->misc[1], &c->misc[2], &c->misc[3], &c->misc[4], &c->misc[5] };
   for (Scratch *s : all) if (s->p) cudaFree(s->p);
   if (c->d_weights) cudaFree(c->d_weights);
   if (c->d_octs) cudaFree(c->d_octs);
-  if (c->h_out) cudaFreeHost(c->h_out);
+  for (int i = 0; i < 2; i++) {
+    if (c->h_out_s[i]) cudaFreeHost(c->h_out_s[i]);
+    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+  }
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->h_cand) cudaFreeHost(c->h_cand);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   cudaEventDestroy(c->ev0);
@@ -577,7 +621,7 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
   size_t dpitch;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
-  if ((rc = run_pyramid(ctx, ctx->image.p, dtype, dpitch))) return rc;
+  if ((rc = run_pyramid(ctx, ctx->image_s[ctx->slot].p, dtype, dpitch))) return rc;
   Counters c;
   sift_keypoint *kps;
   if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
@@ -588,11 +632,8 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
   ctx->last = c;
   fill_stats(stats, c, 0, ms, (int)(ctx->launches - l0));
   *n_out = c.n_kp;
-  if (c.n_kp > cap) {
-    if (cap > 0) memcpy(out, kps, (size_t)cap * sizeof(sift_keypoint));
-    return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
-  }
-  if (c.n_kp) memcpy(out, kps, (size_t)c.n_kp * sizeof(sift_keypoint));
+  sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
+  if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
   return SIFT_OK;
 }
 
@@ -665,7 +706,7 @@ SIFT_API int sift_build_scale_space(sift_ctx *ctx, const void *image, int dtype,
   if ((rc = ensure_plan(ctx, width, height, params))) return rc;
   size_t dpitch;
   if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
-  if ((rc = run_pyramid(ctx, ctx->image.p, dtype, dpitch))) return rc;
+  if ((rc = run_pyramid(ctx, ctx->image_s[ctx->slot].p, dtype, dpitch))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   return SIFT_OK;
 }
@@ -752,7 +793,7 @@ SIFT_API int sift_refine(sift_ctx *ctx, const sift_params *params, const sift_ca
     ctx->cand_cap = n_cands;
   }
   if (n_cands > ctx->kp_cap) {
-    if ((rc = grow(ctx, ctx->outbuf, sizeof(Counters) + (size_t)n_cands * sizeof(sift_keypoint)))) return rc;
+    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)n_cands * sizeof(sift_keypoint)))) return rc;
     ctx->kp_cap = n_cands;
   }
   CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
