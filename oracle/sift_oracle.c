@@ -9,11 +9,14 @@
  *
  * PARITY PINNING: the reference ships no tests, golden vectors or fixtures
  *  and no JavaScript engine exists in the build container,
- * so the pin is tests/golden/jsref_*.json: outputs of the UNMODIFIED reference
- * sources executed by oracle/jsmini.py (a small ECMAScript-subset interpreter,
- * see that file) on tiny inputs.  tests/test_oracle_pin.py compares this file
- * against those vectors.  Where that is not enough the header of DESIGN.md says
- * so.
+ * so the pin is tests/golden/ref_*.npz: outputs of the UNMODIFIED reference
+ * sources (read from /root/reference, never copied) executed by oracle/jsmini.py,
+ * a small ECMAScript-subset interpreter, driven like main.js drives the worker
+ * (oracle/make_golden.py is the committed generator).  tests/test_golden_reference.py
+ * requires this file to reproduce every Gaussian level, DoG level, candidate and
+ * refined keypoint of those runs BIT FOR BIT (absoluteSigma to 2 ulp: pow).  The
+ * inputs are tiny (the interpreter manages ~60k kernel taps per second); larger
+ * sizes rest on this restatement plus the analytic KATs in tests/test_oracle_kat.py.
  *
  * Every function cites the reference file:line it restates.  All arithmetic is
  * IEEE binary64 like JS Number; loop orders and operation orders follow the

@@ -425,13 +425,6 @@ static void sort_keypoints_into(sift_ctx *ctx, const sift_keypoint *src, int n, 
   for (int i = 0; i < m; i++) dst[i] = src[ia[i]];
 }
 
-static void sort_keypoints(sift_keypoint *k, int n)
-{
-  std::sort(k, k + n, [](const sift_keypoint &a, const sift_keypoint &b) {
-    return cand_key(a.octave, a.candScale, a.candY, a.candX) < cand_key(b.octave, b.candScale, b.candY, b.candX);
-  });
-}
-
 static void sort_candidates(sift_candidate *c, int n)
 {
   std::sort(c, c + n, [](const sift_candidate &a, const sift_candidate &b) {
@@ -662,6 +655,41 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
   return SIFT_OK;
 }
 
+// Batch pipeline state: make both slots (image, outbuf, pinned mirror) and the side streams exist.
+static int ensure_batch_resources(sift_ctx *ctx, size_t image_bytes)
+{
+  int rc;
+  if (!ctx->h2d_stream) CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->ev_h2d[i]) CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    if (!ctx->ev_done[i]) CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    if (!ctx->ev_d2h[i]) CK(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+  }
+  CK(cudaStreamSynchronize(ctx->h2d_stream));
+  CK(cudaStreamSynchronize(ctx->d2h_stream));
+  for (int i = 0; i < 2; i++) {
+    if ((rc = grow(ctx, ctx->image_s[i], image_bytes))) return rc;
+    if ((rc = grow(ctx, ctx->outbuf_s[i], sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint)))) return rc;
+    if ((rc = grow_pinned(ctx, &ctx->h_out_s[i], &ctx->h_out_cap_s[i],
+                          sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
+      return rc;
+  }
+  return SIFT_OK;
+}
+
+static void add_stats(sift_stats &t, const sift_stats &s)
+{
+  t.candidates += s.candidates; t.keypoints += s.keypoints;
+  t.rejLowContrast += s.rejLowContrast; t.rejEdge += s.rejEdge;
+  t.rejLeftScale += s.rejLeftScale; t.rejLeftRows += s.rejLeftRows; t.rejLeftCols += s.rejLeftCols;
+  t.rejNoConvergence += s.rejNoConvergence; t.rejSingular += s.rejSingular;
+  t.msDevice += s.msDevice; t.kernelLaunches += s.kernelLaunches;
+}
+
+// Images are independent: frame i+1 is uploaded and frame i-1 is downloaded / ordered on the
+// host while frame i is computed.  Two slots of {device image, device keypoints, pinned mirror}; the pyramid
+// itself is shared because the compute stream processes one frame at a time.
 SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int width, int height,
                                size_t pitch_bytes, size_t image_stride_bytes, int n_images,
                                const sift_params *params, sift_keypoint *out, int cap, int *offsets,
@@ -669,27 +697,107 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;
   if (!images || !offsets || n_images < 0) return fail(ctx, SIFT_ERR_BAD_ARGS, "images / offsets NULL or n_images < 0");
+  if (cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "out is NULL with cap %d", cap);
+  const size_t es = dtype_size(dtype);
+  if (!es) return fail(ctx, SIFT_ERR_BAD_ARGS, "unknown dtype %d", dtype);
   sift_stats total;
   memset(&total, 0, sizeof total);
   total.lowContrastExtrema = -1;
-  int n = 0, rc = SIFT_OK, overflow = 0;
   offsets[0] = 0;
-  for (int i = 0; i < n_images; i++) {
-    int ni = 0;
+  if (n_images == 0) { if (stats) *stats = total; return SIFT_OK; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  ctx->slot = 0;
+  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  const size_t row = (size_t)width * es;
+  if (pitch_bytes == 0) pitch_bytes = row;
+  if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
+  if ((rc = ensure_batch_resources(ctx, row * height))) return rc;
+  const size_t first = sizeof(Counters) + (size_t)std::min(ctx->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+  const int64_t l0 = ctx->launches;
+  int n = 0, overflow = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+
+  int done = 0, issued = 0;     // frames consumed by the host / frames whose device work has been issued
+  auto take = [&](int j, int ni, const sift_stats &si) { n += ni; offsets[j + 1] = n; add_stats(total, si); };
+  // consume frame `done` (its D2H was issued): order its keypoints into `out`
+  auto consume = [&]() -> int {
+    const int j = done, sl = j & 1;
+    CK(cudaEventSynchronize(ctx->ev_d2h[sl]));
+    Counters c = *(Counters *)ctx->h_out_s[sl];
     sift_stats si;
-    const void *img = (const char *)images + (size_t)i * image_stride_bytes;
+    memset(&si, 0, sizeof si);
+    if (c.n_cand > ctx->cand_cap || c.n_kp > ctx->kp_cap) {
+      // rare: device buffers too small -- drain the pipeline and redo every issued frame on the growing
+      // single-frame path (the buffers, pinned mirrors included, are reallocated by it)
+      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaStreamSynchronize(ctx->h2d_stream));
+      CK(cudaStreamSynchronize(ctx->d2h_stream));
+      ctx->slot = 0;
+      for (int q = j; q < issued; q++) {
+        int ni = 0;
+        const int room = overflow ? 0 : std::max(0, cap - n);
+        const void *img = (const char *)images + (size_t)q * image_stride_bytes;
+        const int r2 = sift_detect(ctx, img, dtype, width, height, pitch_bytes, params, room ? out + n : nullptr, room, &ni, &si);
+        if (r2 == SIFT_ERR_CAPACITY) overflow = 1;
+        else if (r2 != SIFT_OK) return r2;
+        take(q, ni, si);
+      }
+      done = issued;
+      return ensure_batch_resources(ctx, row * height);
+    }
+    if (c.n_kp > FIRST_CHUNK) {
+      CK(cudaMemcpyAsync((char *)ctx->h_out_s[sl] + first, (char *)ctx->outbuf_s[sl].p + first,
+                         (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CK(cudaStreamSynchronize(ctx->d2h_stream));
+    }
+    const sift_keypoint *kps = (const sift_keypoint *)((char *)ctx->h_out_s[sl] + sizeof(Counters));
     const int room = overflow ? 0 : std::max(0, cap - n);
-    rc = sift_detect(ctx, img, dtype, width, height, pitch_bytes, params, room ? out + n : nullptr, room, &ni, &si);
-    if (rc == SIFT_ERR_CAPACITY) overflow = 1;
-    else if (rc != SIFT_OK) return rc;
-    n += ni;
-    offsets[i + 1] = n;
-    total.candidates += si.candidates; total.keypoints += si.keypoints;
-    total.rejLowContrast += si.rejLowContrast; total.rejEdge += si.rejEdge;
-    total.rejLeftScale += si.rejLeftScale; total.rejLeftRows += si.rejLeftRows; total.rejLeftCols += si.rejLeftCols;
-    total.rejNoConvergence += si.rejNoConvergence; total.rejSingular += si.rejSingular;
-    total.msDevice += si.msDevice; total.kernelLaunches += si.kernelLaunches;
+    sort_keypoints_into(ctx, kps, c.n_kp, room ? out + n : nullptr, room);
+    if (c.n_kp > room) overflow = 1;
+    fill_stats(&si, c, 0, 0.f, 0);
+    ctx->last = c;
+    take(j, c.n_kp, si);
+    done = j + 1;
+    return SIFT_OK;
+  };
+
+  for (int i = 0; i < n_images; i++) {
+    const int sl = i & 1;
+    const void *img = (const char *)images + (size_t)i * image_stride_bytes;
+    // upload i: the slot's previous frame (i-2) must have been read by the compute stream
+    if (i >= 2) CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[sl], 0));
+    else CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev0, 0));
+    if (pitch_bytes == row)
+      CK(cudaMemcpyAsync(ctx->image_s[sl].p, img, row * height, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    else
+      CK(cudaMemcpy2DAsync(ctx->image_s[sl].p, row, img, pitch_bytes, row, height, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CK(cudaEventRecord(ctx->ev_h2d[sl], ctx->h2d_stream));
+    // compute i: needs the upload, and the slot's previous keypoints (frame i-2) must be on the host already
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[sl], 0));
+    if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[sl], 0));
+    ctx->slot = sl;
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+    if ((rc = run_pyramid(ctx, ctx->image_s[sl].p, dtype, row))) return rc;
+    if ((rc = run_scan(ctx, 0))) return rc;
+    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->kp_cap))) return rc;
+    CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+    // download i
+    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_done[sl], 0));
+    CK(cudaMemcpyAsync(ctx->h_out_s[sl], ctx->outbuf_s[sl].p, first, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CK(cudaEventRecord(ctx->ev_d2h[sl], ctx->d2h_stream));
+    issued = i + 1;
+    // meanwhile the host orders frame i-1
+    while (done < i) if ((rc = consume())) return rc;
   }
+  while (done < n_images) if ((rc = consume())) return rc;
+  ctx->slot = 0;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  total.msDevice = ms;
+  total.kernelLaunches = (int)(ctx->launches - l0);
   if (stats) *stats = total;
   if (overflow) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints in the batch, capacity %d", n, cap);
   return SIFT_OK;

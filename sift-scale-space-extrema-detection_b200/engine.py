@@ -125,6 +125,14 @@ class Engine:
         self._check(self._lib.sift_detect_device(self._h, d_image, dtype, w, h, pitch, C.byref(prm), d_out, cap,
                                                  d_count, 1 if ordered else 0))
 
+    def detect_batch_raw(self, ptr: int, dtype: int, w: int, h: int, pitch: int, stride: int, n_images: int,
+                         prm: L.Params, out_ptr: int, cap: int, offsets_ptr: int):
+        """sift_detect_batch on raw host pointers (pinned buffers owned by the caller). Returns Stats."""
+        st = L.Stats()
+        self._check(self._lib.sift_detect_batch(self._h, ptr, dtype, w, h, pitch, stride, n_images, C.byref(prm),
+                                                out_ptr, cap, C.cast(offsets_ptr, C.POINTER(C.c_int)), C.byref(st)))
+        return st
+
     def detect_batch(self, images, params: L.Params | None = None, capacity: int | None = None, **overrides):
         """images: ndarray [n, h, w] (u8 / f32 / f64). Returns (keypoints, offsets[n+1], stats)."""
         a = np.ascontiguousarray(images)

@@ -33,13 +33,15 @@ def _uniform(u64: np.ndarray) -> np.ndarray:
     return (u64 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
-def synthetic_u8(width: int, height: int, seed: int = 1234, blobs: int | None = None) -> np.ndarray:
-    """Return the (height, width) uint8 synthetic frame for ``seed`` (frame i of a batch: 1234+i)."""
+def synthetic_u8(width: int, height: int, seed: int = 1234, blobs: int | None = None,
+                 sigma_lo: float = 1.5, sigma_hi: float = 12.0) -> np.ndarray:
+    """Return the (height, width) uint8 synthetic frame for ``seed`` (frame i of a batch: 1234+i).
+    ``sigma_lo/hi`` narrow the blob sizes for the tiny golden-vector inputs (tests/golden)."""
     nb = blobs if blobs is not None else max(8, (width * height) // 4096)
     r = _uniform(_splitmix_stream(seed, 4 * nb))
     cx = r[0::4] * width
     cy = r[1::4] * height
-    sg = 1.5 + r[2::4] * 10.5
+    sg = sigma_lo + r[2::4] * (sigma_hi - sigma_lo)
     am = -0.35 + r[3::4] * 0.7
     yy, xx = np.mgrid[0:height, 0:width]
     img = 0.5 + 0.15 * ((((xx // 24) + (yy // 24)) & 1).astype(np.float64) * 2.0 - 1.0)
