@@ -36,6 +36,7 @@ METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200
 W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
 FRAMES = 8                     # frames per GPU per step (distinct seeds)
+LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
 CPU_TILE = 128                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
 
@@ -195,6 +196,7 @@ def workload_config(n_gpus: int) -> dict:
                         f"(6 blur levels), sigma0={MIN_BLUR}, assumed blur {ASSUMED}, contrast 0.015 "
                         f"(reference constant), edge r=10, 2x-upsampled base octave",
             "frames_per_gpu_per_step": FRAMES, "sharding": f"images split by rank x{n_gpus}, no collective",
+            "frames_in_flight_per_gpu": LANES,
             "l2": "no flush: one frame's pyramid (735 MB algorithmic) exceeds the 126 MB L2 and frames rotate"}
 
 
@@ -255,6 +257,7 @@ def run_own(args):
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    eng.flush()                      # the public stream waits for every frame in flight (host not blocked)
     e1.record(stream)
     barrier()
     launches = eng.kernel_launches - l0
@@ -282,6 +285,7 @@ def run_own(args):
     d2h_per_frame = 64 + min(cap, 8192) * L.KEYPOINT_DTYPE.itemsize
 
     # ---- per-kernel-class timing (separate instrumented pass, CUDA events on the engine's stream)
+    eng.set_lanes(1)                 # one frame at a time: per-kernel times without cross-frame overlap
     eng.set_profiling(True)
     prof_steps = 2
     for _ in range(prof_steps):

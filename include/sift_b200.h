@@ -146,8 +146,14 @@ SIFT_API const char *sift_last_error(const sift_ctx *ctx);   /* ctx may be NULL:
 SIFT_API const char *sift_version(void);
 SIFT_API void sift_default_params(sift_params *p);           /* worker.js:33-37 defaults */
 SIFT_API int sift_synchronize(sift_ctx *ctx);
-/* The CUDA stream (cudaStream_t) all work of the context is issued on. */
+/* The public CUDA stream (cudaStream_t) of the context.  Device-resident calls fork from it (they see
+ * everything queued on it before the call) and run on internal lanes -- one stream + pyramid per frame in
+ * flight -- so consecutive frames overlap.  sift_flush() makes the public stream wait for all lanes
+ * (without blocking the host): queue it before consuming device results or recording an event there. */
 SIFT_API void *sift_stream(sift_ctx *ctx);
+SIFT_API int sift_flush(sift_ctx *ctx);
+/* Frames in flight for sift_detect_device / sift_detect_batch (1..4, default 3, env SIFT_B200_LANES). */
+SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes);
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for the context */
 
 /* Per-kernel-class device timing (CUDA events around each launch group on sift_stream).
@@ -174,7 +180,8 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
 
 /* Same, image already in device memory; keypoints stay in device memory
  * (d_out, unordered unless `ordered` != 0) and *d_count (device int) receives
- * the count.  Asynchronous on sift_stream(ctx). */
+ * the count.  Asynchronous: ordered after what is already queued on sift_stream(ctx);
+ * sift_flush() / sift_synchronize() order the results before later work on that stream. */
 SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
                                 size_t pitch_bytes, const sift_params *params,
                                 sift_keypoint *d_out, int cap, int *d_count, int ordered);

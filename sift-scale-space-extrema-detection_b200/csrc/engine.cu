@@ -23,12 +23,35 @@ struct Scratch {
   size_t cap = 0;
 };
 
+// One lane = one stream plus everything a frame in flight owns: its pyramid, candidate list, keypoint
+// buffer (device + pinned mirror) and input image.  Images are independent, so frames of a
+// batch are dealt round-robin to lanes and their kernels overlap: the small, latency-bound launches of
+// the high octaves of one frame run next to the octave-0 launch of another, and uploads / downloads of
+// one lane overlap the kernels of the others.  The stage API and single-image calls use lane 0.
+#define SIFT_MAX_LANES 4
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
+  Scratch planes, seeds, tbuf, image, cand, outbuf;
+  int cand_cap = 0, kp_cap = 0;
+  void *h_out = nullptr;       // pinned mirror of outbuf
+  size_t h_out_cap = 0;
+  OctaveDev octs[SIFT_MAX_OCTAVES];
+  OctaveDev *d_octs = nullptr;
+  uint64_t plan_id = 0;        // plan the buffers above are laid out for
+  bool busy = false;           // device work issued since the last join with the public stream
+};
+
 struct sift_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t main_stream = nullptr;   // the public stream (sift_stream): lanes fork from / join into it
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
+
+  Lane lanes[SIFT_MAX_LANES];
+  Lane *L = nullptr;                    // lane the stage helpers address
+  int n_lanes = 3, next_lane = 0;
 
   // ---- optional per-kernel-class CUDA-event profiling (sift_set_profiling)
   bool profiling = false;
@@ -38,9 +61,11 @@ struct sift_ctx {
 
   // ---- plan (depends on params + input size)
   bool plan_valid = false;
+  uint64_t plan_id = 0;
   sift_params prm;
   int in_w = 0, in_h = 0;
   int n_oct = 0, nlev = 0;
+  int ow[SIFT_MAX_OCTAVES], oh[SIFT_MAX_OCTAVES];
   LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   double dog_blur[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   std::vector<double> h_weights;   // [0,256): u8 -> v/255.0 table, then per-level taps
@@ -49,18 +74,10 @@ struct sift_ctx {
   bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
   double *d_weights = nullptr;
   size_t d_weights_cap = 0;
-  OctaveDev octs[SIFT_MAX_OCTAVES];
-  OctaveDev *d_octs = nullptr;
 
-  // ---- device arenas (grow only)
-  // image / outbuf / h_out exist twice: slot 1 is only used by the pipelined batch path
-  Scratch planes, seeds, tbuf, image_s[2], cand, low, outbuf_s[2], misc[6];
-  int cand_cap = 0, low_cap = 0, kp_cap = 0;
-  int slot = 0;               // which image / outbuf / h_out the stage helpers address
-  void *h_out_s[2] = { nullptr, nullptr };   // pinned mirrors of outbuf
-  size_t h_out_cap_s[2] = { 0, 0 };
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_d2h[2] = { nullptr, nullptr };
+  // ---- lane-0-only arenas of the stage / step API (grow only)
+  Scratch low, misc[6];
+  int low_cap = 0;
   std::vector<uint64_t> sort_a, sort_b;
   void *h_cand = nullptr;     // pinned candidate staging
   size_t h_cand_cap = 0;
@@ -92,7 +109,7 @@ static int fail(sift_ctx *c, int code, const char *fmt, ...)
 static int grow(sift_ctx *ctx, Scratch &s, size_t bytes)
 {
   if (bytes <= s.cap) return SIFT_OK;
-  if (s.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
+  if (s.p) { CK(cudaStreamSynchronize(ctx->L->stream)); CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
   bytes = (bytes + 255) & ~(size_t)255;
   CK(cudaMalloc(&s.p, bytes));
   s.cap = bytes;
@@ -102,7 +119,7 @@ static int grow(sift_ctx *ctx, Scratch &s, size_t bytes)
 static int grow_pinned(sift_ctx *ctx, void **p, size_t *cap, size_t bytes)
 {
   if (bytes <= *cap) return SIFT_OK;
-  if (*p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
+  if (*p) { CK(cudaStreamSynchronize(ctx->L->stream)); CK(cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
   CK(cudaMallocHost(p, bytes));
   *cap = bytes;
   return SIFT_OK;
@@ -118,12 +135,12 @@ static void prof_begin(sift_ctx *ctx, int kind)
     ctx->spans.push_back(sp);
   }
   ctx->spans[ctx->spans_used].kind = kind;
-  cudaEventRecord(ctx->spans[ctx->spans_used].a, ctx->stream);
+  cudaEventRecord(ctx->spans[ctx->spans_used].a, ctx->L->stream);
 }
 static void prof_end(sift_ctx *ctx)
 {
   if (!ctx->profiling) return;
-  cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->stream);
+  cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->L->stream);
   ctx->spans_used++;
 }
 
@@ -222,7 +239,30 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
     }
   }
 
-  // ---- device memory
+  for (int o = 0; o < n_oct; o++) { ctx->ow[o] = ow[o]; ctx->oh[o] = oh[o]; }
+  // ---- weights (shared by all lanes)
+  const size_t wbytes = ctx->h_weights.size() * sizeof(double);
+  CK(cudaDeviceSynchronize());          // a plan change is rare; no lane may still read the old tables
+  if (wbytes > ctx->d_weights_cap) {
+    if (ctx->d_weights) CK(cudaFree(ctx->d_weights));
+    CK(cudaMalloc((void **)&ctx->d_weights, wbytes));
+    ctx->d_weights_cap = wbytes;
+  }
+  CK(cudaMemcpy(ctx->d_weights, ctx->h_weights.data(), wbytes, cudaMemcpyHostToDevice));
+  ctx->prm = *p; ctx->in_w = w; ctx->in_h = h; ctx->n_oct = n_oct; ctx->nlev = nlev;
+  ctx->plan_id++;
+  ctx->plan_valid = true;
+  return SIFT_OK;
+}
+
+// Device memory of one lane for the current plan (lazy: lanes other than 0 are only touched by batches).
+static int ensure_lane(sift_ctx *ctx, Lane *ln)
+{
+  if (ln->plan_id == ctx->plan_id) return SIFT_OK;
+  Lane *saved = ctx->L;
+  ctx->L = ln;                          // grow() synchronises ctx->L->stream before freeing
+  const int n_oct = ctx->n_oct, nlev = ctx->nlev, w = ctx->in_w, h = ctx->in_h;
+  const int *ow = ctx->ow, *oh = ctx->oh;
   size_t plane_elems = 0, seed_elems = 0, t_bytes = 0;
   for (int o = 0; o < n_oct; o++) {
     const int pitch = (ow[o] + 31) & ~31;
@@ -230,64 +270,72 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
     if (o > 0) seed_elems += (size_t)ow[o] * oh[o];
     const size_t trows = (o == 0) ? (size_t)h : (size_t)oh[o];
     const size_t tl = (o == 0) ? nlev : nlev - 1;
-    t_bytes = std::max(t_bytes, tl * trows * ow[o] * sizeof(double));
+    if (o > 0 || !ctx->fused0) t_bytes = std::max(t_bytes, tl * trows * ow[o] * sizeof(double));
   }
-  int rc;
-  if ((rc = grow(ctx, ctx->planes, plane_elems * sizeof(float)))) return rc;
-  if ((rc = grow(ctx, ctx->seeds, std::max<size_t>(seed_elems, 1) * sizeof(double)))) return rc;
-  if ((rc = grow(ctx, ctx->tbuf, t_bytes))) return rc;
-  const size_t wbytes = ctx->h_weights.size() * sizeof(double);
-  if (wbytes > ctx->d_weights_cap) {
-    if (ctx->d_weights) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->d_weights)); }
-    CK(cudaMalloc((void **)&ctx->d_weights, wbytes));
-    ctx->d_weights_cap = wbytes;
-  }
-  CK(cudaMemcpyAsync(ctx->d_weights, ctx->h_weights.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
-
-  float *pp = (float *)ctx->planes.p;
-  double *sp = (double *)ctx->seeds.p;
-  for (int o = 0; o < n_oct; o++) {
-    OctaveDev &od = ctx->octs[o];
-    memset(&od, 0, sizeof od);
-    od.w = ow[o]; od.h = oh[o]; od.pitch = (ow[o] + 31) & ~31; od.nlev = nlev;
-    const size_t pe = (size_t)od.h * od.pitch;
-    for (int s = 0; s < nlev; s++) { od.gauss[s] = pp; pp += pe; }
-    for (int s = 0; s < nlev - 1; s++) { od.dog[s] = pp; pp += pe; }
-    if (o > 0) { od.seed64 = sp; sp += (size_t)od.w * od.h; }
-  }
-  if (!ctx->d_octs) CK(cudaMalloc((void **)&ctx->d_octs, sizeof(OctaveDev) * SIFT_MAX_OCTAVES));
-  CK(cudaMemcpyAsync(ctx->d_octs, ctx->octs, sizeof(OctaveDev) * n_oct, cudaMemcpyHostToDevice, ctx->stream));
-  // cudaMemcpyAsync from pageable memory is staged before returning, so h_weights / octs may change afterwards.
-
-  // candidate / keypoint capacity: extrema are ~3e-4 of the voxels on the synthetic frames
-  const int want = (int)std::min<int64_t>(std::max<int64_t>(16384, ((int64_t)w * h) / 8), 1 << 26);
-  if (want > ctx->cand_cap) {
-    if ((rc = grow(ctx, ctx->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
-    ctx->cand_cap = want;
-  }
-  if (want > ctx->kp_cap) {
-    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
-    ctx->kp_cap = want;
-  }
-  ctx->prm = *p; ctx->in_w = w; ctx->in_h = h; ctx->n_oct = n_oct; ctx->nlev = nlev;
-  ctx->plan_valid = true;
-  return SIFT_OK;
+  int rc = SIFT_OK;
+  do {
+    if ((rc = grow(ctx, ln->planes, plane_elems * sizeof(float)))) break;
+    if ((rc = grow(ctx, ln->seeds, std::max<size_t>(seed_elems, 1) * sizeof(double)))) break;
+    if ((rc = grow(ctx, ln->tbuf, std::max<size_t>(t_bytes, 8)))) break;
+    float *pp = (float *)ln->planes.p;
+    double *sp = (double *)ln->seeds.p;
+    for (int o = 0; o < n_oct; o++) {
+      OctaveDev &od = ln->octs[o];
+      memset(&od, 0, sizeof od);
+      od.w = ow[o]; od.h = oh[o]; od.pitch = (ow[o] + 31) & ~31; od.nlev = nlev;
+      const size_t pe = (size_t)od.h * od.pitch;
+      for (int s = 0; s < nlev; s++) { od.gauss[s] = pp; pp += pe; }
+      for (int s = 0; s < nlev - 1; s++) { od.dog[s] = pp; pp += pe; }
+      if (o > 0) { od.seed64 = sp; sp += (size_t)od.w * od.h; }
+    }
+    if (!ln->d_octs && cudaMalloc((void **)&ln->d_octs, sizeof(OctaveDev) * SIFT_MAX_OCTAVES) != cudaSuccess) {
+      rc = fail(ctx, SIFT_ERR_CUDA, "cudaMalloc(d_octs) failed");
+      break;
+    }
+    // pageable source: staged before the call returns, so octs may change afterwards
+    if (cudaMemcpyAsync(ln->d_octs, ln->octs, sizeof(OctaveDev) * n_oct, cudaMemcpyHostToDevice, ln->stream) != cudaSuccess) {
+      rc = fail(ctx, SIFT_ERR_CUDA, "upload of the octave table failed");
+      break;
+    }
+    // candidate / keypoint capacity: extrema are ~3e-4 of the voxels on the synthetic frames
+    const int want = (int)std::min<int64_t>(std::max<int64_t>(16384, ((int64_t)w * h) / 8), 1 << 26);
+    if (want > ln->cand_cap) {
+      if ((rc = grow(ctx, ln->cand, (size_t)want * sizeof(sift_candidate)))) break;
+      ln->cand_cap = want;
+    }
+    if (want > ln->kp_cap) {
+      if ((rc = grow(ctx, ln->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) break;
+      ln->kp_cap = want;
+    }
+    ln->plan_id = ctx->plan_id;
+  } while (0);
+  ctx->L = saved;
+  return rc;
 }
 
-static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->outbuf_s[ctx->slot].p; }
-static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->outbuf_s[ctx->slot].p + sizeof(Counters)); }
+// plan + lane 0 (what every single-image / stage entry point needs)
+static int ensure_plan0(sift_ctx *ctx, int w, int h, const sift_params *p)
+{
+  int rc;
+  ctx->L = &ctx->lanes[0];
+  if ((rc = ensure_plan(ctx, w, h, p))) return rc;
+  return ensure_lane(ctx, ctx->L);
+}
+
+static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->L->outbuf.p; }
+static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->L->outbuf.p + sizeof(Counters)); }
 
 // Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
 static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
 {
   const int spo = ctx->prm.scalesPerOctave;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->L->stream;
   for (int o = 0; o < ctx->n_oct; o++) {
-    const OctaveDev &od = ctx->octs[o];
+    const OctaveDev &od = ctx->L->octs[o];
     if (o == 0 && ctx->fused0) {
       prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
       launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od,
-                           (ctx->n_oct > 1) ? &ctx->octs[1] : nullptr, ctx->d_weights, ctx->plans[0],
+                           (ctx->n_oct > 1) ? &ctx->L->octs[1] : nullptr, ctx->d_weights, ctx->plans[0],
                            ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
       ctx->launches += 1;
       prof_end(ctx);
@@ -296,7 +344,7 @@ static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pit
     const int first = (o == 0) ? 0 : 1;
     const int hrows = (o == 0) ? ctx->in_h : od.h;
     double *T[SIFT_MAX_LEVELS];
-    for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->tbuf.p + (size_t)i * hrows * od.w;
+    for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->L->tbuf.p + (size_t)i * hrows * od.w;
     prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
     if (o == 0)
       launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
@@ -305,7 +353,7 @@ static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pit
       launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
                    ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
     launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T,
-                 (o + 1 < ctx->n_oct) ? &ctx->octs[o + 1] : nullptr, spo, ctx->keep_gauss);
+                 (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr, spo, ctx->keep_gauss);
     ctx->launches += 2;
     prof_end(ctx);
   }
@@ -326,8 +374,8 @@ static int run_scan(sift_ctx *ctx, int count_low, const sift_params *thr = nullp
   if (thr) { tp.contrastThreshold = thr->contrastThreshold; tp.preFilterFactor = thr->preFilterFactor; }
   const double pix_thr = contrast_threshold(tp) * tp.preFilterFactor;               // sift.js:293
   prof_begin(ctx, SIFT_PROF_SCAN);
-  launch_scan_all(ctx->stream, ctx->octs, ctx->d_octs, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
-                  (sift_candidate *)ctx->cand.p, ctx->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
+  launch_scan_all(ctx->L->stream, ctx->L->octs, ctx->L->d_octs, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
+                  (sift_candidate *)ctx->L->cand.p, ctx->L->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
                   dev_counters(ctx));
   ctx->launches += 1;
   prof_end(ctx);
@@ -358,8 +406,8 @@ static RefineParams refine_params(const sift_ctx *ctx, const sift_params *over)
 static int run_refine(sift_ctx *ctx, int n_cand_host, sift_keypoint *d_out, int cap, const sift_params *over = nullptr)
 {
   prof_begin(ctx, SIFT_PROF_REFINE);
-  launch_refine(ctx->stream, ctx->d_octs, ctx->n_oct, (const sift_candidate *)ctx->cand.p,
-                &dev_counters(ctx)->n_cand, n_cand_host, ctx->cand_cap, refine_params(ctx, over), d_out, cap,
+  launch_refine(ctx->L->stream, ctx->L->d_octs, ctx->n_oct, (const sift_candidate *)ctx->L->cand.p,
+                &dev_counters(ctx)->n_cand, n_cand_host, ctx->L->cand_cap, refine_params(ctx, over), d_out, cap,
                 dev_counters(ctx));
   prof_end(ctx);
   ctx->launches += 1;
@@ -442,9 +490,9 @@ static int upload_image(sift_ctx *ctx, const void *image, int dtype, int w, int 
   if (pitch_bytes == 0) pitch_bytes = row;
   if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
   int rc;
-  if ((rc = grow(ctx, ctx->image_s[ctx->slot], row * h))) return rc;
-  if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->image_s[ctx->slot].p, image, row * h, cudaMemcpyHostToDevice, ctx->stream));
-  else CK(cudaMemcpy2DAsync(ctx->image_s[ctx->slot].p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = grow(ctx, ctx->L->image, row * h))) return rc;
+  if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->L->image.p, image, row * h, cudaMemcpyHostToDevice, ctx->L->stream));
+  else CK(cudaMemcpy2DAsync(ctx->L->image.p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->L->stream));
   *dev_pitch = row;
   return SIFT_OK;
 }
@@ -454,19 +502,19 @@ static int upload_image(sift_ctx *ctx, const void *image, int dtype, int w, int 
 static int download_keypoints(sift_ctx *ctx, Counters *c, sift_keypoint **kps)
 {
   int rc;
-  const size_t first = sizeof(Counters) + (size_t)std::min(ctx->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
-  if ((rc = grow_pinned(ctx, &ctx->h_out_s[ctx->slot], &ctx->h_out_cap_s[ctx->slot], sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
+  const size_t first = sizeof(Counters) + (size_t)std::min(ctx->L->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+  if ((rc = grow_pinned(ctx, &ctx->L->h_out, &ctx->L->h_out_cap, sizeof(Counters) + (size_t)ctx->L->kp_cap * sizeof(sift_keypoint))))
     return rc;
-  CK(cudaMemcpyAsync(ctx->h_out_s[ctx->slot], ctx->outbuf_s[ctx->slot].p, first, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  *c = *(Counters *)ctx->h_out_s[ctx->slot];
-  const int n = std::min(c->n_kp, ctx->kp_cap);
+  CK(cudaMemcpyAsync(ctx->L->h_out, ctx->L->outbuf.p, first, cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
+  *c = *(Counters *)ctx->L->h_out;
+  const int n = std::min(c->n_kp, ctx->L->kp_cap);
   if (n > FIRST_CHUNK) {
-    CK(cudaMemcpyAsync((char *)ctx->h_out_s[ctx->slot] + first, (char *)ctx->outbuf_s[ctx->slot].p + first,
-                       (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync((char *)ctx->L->h_out + first, (char *)ctx->L->outbuf.p + first,
+                       (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->L->stream));
+    CK(cudaStreamSynchronize(ctx->L->stream));
   }
-  *kps = (sift_keypoint *)((char *)ctx->h_out_s[ctx->slot] + sizeof(Counters));
+  *kps = (sift_keypoint *)((char *)ctx->L->h_out + sizeof(Counters));
   return SIFT_OK;
 }
 
@@ -475,16 +523,16 @@ static int scan_refine_download(sift_ctx *ctx, Counters *c, sift_keypoint **kps,
 {
   int rc;
   for (int attempt = 0; attempt < 3; attempt++) {
-    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
     if ((rc = run_scan(ctx, count_low))) return rc;
-    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->kp_cap))) return rc;
+    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->L->kp_cap))) return rc;
     if ((rc = download_keypoints(ctx, c, kps))) return rc;
-    if (c->n_cand <= ctx->cand_cap && c->n_kp <= ctx->kp_cap) return SIFT_OK;   // unordered: callers sort-gather
+    if (c->n_cand <= ctx->L->cand_cap && c->n_kp <= ctx->L->kp_cap) return SIFT_OK;   // unordered: callers sort-gather
     const int want = std::max(c->n_cand, c->n_kp) + 1024;
-    if ((rc = grow(ctx, ctx->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
-    ctx->cand_cap = want;
-    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
-    ctx->kp_cap = want;
+    if ((rc = grow(ctx, ctx->L->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
+    ctx->L->cand_cap = want;
+    if ((rc = grow(ctx, ctx->L->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    ctx->L->kp_cap = want;
   }
   return fail(ctx, SIFT_ERR_CAPACITY, "candidate buffer kept overflowing");
 }
@@ -510,6 +558,7 @@ SIFT_API void sift_default_params(sift_params *p)
   p->minInterpixelDistance = 0.5;  // background.js:461
 }
 
+SIFT_API void sift_destroy(sift_ctx *c);
 SIFT_API int sift_create(int device, sift_ctx **out)
 {
   if (!out) return fail(nullptr, SIFT_ERR_BAD_ARGS, "out is NULL");
@@ -527,14 +576,23 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SIFT_ERR_CUDA, "cudaSetDevice failed");
   sift_ctx *c = new sift_ctx();
   c->device = device;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
-    delete c;
-    return fail(nullptr, SIFT_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  bool ok = cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  for (int i = 0; ok && i < SIFT_MAX_LANES; i++)
+    ok = cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->lanes[i].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->lanes[i].ev_done, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    const char *why = cudaGetErrorString(cudaGetLastError());
+    sift_destroy(c);
+    return fail(nullptr, SIFT_ERR_CUDA, "stream/event creation failed: %s", why);
   }
+  c->L = &c->lanes[0];
   sift_default_params(&c->prm);
   const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
+  const char *nl = getenv("SIFT_B200_LANES");
+  if (nl && nl[0] >= '1' && nl[0] <= '0' + SIFT_MAX_LANES) c->n_lanes = nl[0] - '0';
   *out = c;
   return SIFT_OK;
 }
@@ -543,44 +601,77 @@ SIFT_API void sift_destroy(sift_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  Scratch *all[] = { &c->planes, &c->seeds, &c->tbuf, &c->image_s[0], &c->image_s[1], &c->cand, &c->low, &c->outbuf_s[0], &c->outbuf_s[1],
-                     &c->misc[0], &c->misc[1], &c->misc[2], &c->misc[3], &c->misc[4], &c->misc[5] };
+  cudaDeviceSynchronize();
+  for (Lane &ln : c->lanes) {
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf };
+    for (Scratch *s : all) if (s->p) cudaFree(s->p);
+    if (ln.d_octs) cudaFree(ln.d_octs);
+    if (ln.h_out) cudaFreeHost(ln.h_out);
+    if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+    if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+  }
+  Scratch *all[] = { &c->low, &c->misc[0], &c->misc[1], &c->misc[2], &c->misc[3], &c->misc[4], &c->misc[5] };
   for (Scratch *s : all) if (s->p) cudaFree(s->p);
   if (c->d_weights) cudaFree(c->d_weights);
-  if (c->d_octs) cudaFree(c->d_octs);
-  for (int i = 0; i < 2; i++) {
-    if (c->h_out_s[i]) cudaFreeHost(c->h_out_s[i]);
-    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
-    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
-    if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
-  }
-  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->h_cand) cudaFreeHost(c->h_cand);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
-  cudaEventDestroy(c->ev0);
-  cudaEventDestroy(c->ev1);
-  cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->main_stream) cudaStreamDestroy(c->main_stream);
   delete c;
 }
 
 SIFT_API const char *sift_last_error(const sift_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-SIFT_API int sift_synchronize(sift_ctx *ctx)
+// Make the public stream wait for every lane that has work in flight (non-blocking for the host).
+static int join_lanes(sift_ctx *ctx)
 {
-  if (!ctx) return SIFT_ERR_BAD_ARGS;
-  CK(cudaStreamSynchronize(ctx->stream));
+  for (Lane &ln : ctx->lanes) {
+    if (!ln.busy) continue;
+    CK(cudaEventRecord(ln.ev_done, ln.stream));
+    CK(cudaStreamWaitEvent(ctx->main_stream, ln.ev_done, 0));
+    ln.busy = false;
+  }
   return SIFT_OK;
 }
 
-SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+SIFT_API int sift_flush(sift_ctx *ctx)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  CK(cudaSetDevice(ctx->device));
+  return join_lanes(ctx);
+}
+
+SIFT_API int sift_synchronize(sift_ctx *ctx)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = join_lanes(ctx))) return rc;
+  CK(cudaStreamSynchronize(ctx->main_stream));
+  for (Lane &ln : ctx->lanes) CK(cudaStreamSynchronize(ln.stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (n_lanes < 1 || n_lanes > SIFT_MAX_LANES) return fail(ctx, SIFT_ERR_BAD_ARGS, "lanes %d outside 1..%d", n_lanes, SIFT_MAX_LANES);
+  int rc;
+  if ((rc = sift_synchronize(ctx))) return rc;
+  ctx->n_lanes = n_lanes;
+  ctx->next_lane = 0;
+  return SIFT_OK;
+}
+
+SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->main_stream : nullptr; }
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled)
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   ctx->profiling = enabled != 0;
   ctx->spans_used = 0;
   return SIFT_OK;
@@ -589,7 +680,7 @@ SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled)
 SIFT_API int sift_get_profile(sift_ctx *ctx, float *ms_by_kind, int *launch_groups_by_kind, int n_kinds)
 {
   if (!ctx || !ms_by_kind || n_kinds < SIFT_PROF_NKINDS) return SIFT_ERR_BAD_ARGS;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   for (int i = 0; i < n_kinds; i++) { ms_by_kind[i] = 0.f; if (launch_groups_by_kind) launch_groups_by_kind[i] = 0; }
   for (size_t i = 0; i < ctx->spans_used; i++) {
     float ms = 0.f;
@@ -609,16 +700,16 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
   if (cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "out is NULL with cap %d", cap);
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  if ((rc = ensure_plan0(ctx, width, height, params))) return rc;
   const int64_t l0 = ctx->launches;
   size_t dpitch;
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->L->stream));
   if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
-  if ((rc = run_pyramid(ctx, ctx->image_s[ctx->slot].p, dtype, dpitch))) return rc;
+  if ((rc = run_pyramid(ctx, ctx->L->image.p, dtype, dpitch))) return rc;
   Counters c;
   sift_keypoint *kps;
   if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
-  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->L->stream));
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -644,38 +735,27 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
   CK(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  Lane *ln = &ctx->lanes[ctx->next_lane];
+  ctx->next_lane = (ctx->next_lane + 1) % ctx->n_lanes;
+  if ((rc = ensure_lane(ctx, ln))) return rc;
+  ctx->L = ln;
   if (pitch_bytes == 0) pitch_bytes = (size_t)width * es;
-  if ((rc = run_pyramid(ctx, d_image, dtype, pitch_bytes))) return rc;
-  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
-  if ((rc = run_scan(ctx, 0))) return rc;
-  if ((rc = run_refine(ctx, -1, d_out, cap))) return rc;
-  copy_count_kernel<<<1, 1, 0, ctx->stream>>>(dev_counters(ctx), d_count);
-  ctx->launches += 1;
-  CK(cudaGetLastError());
-  return SIFT_OK;
-}
-
-// Batch pipeline state: make both slots (image, outbuf, pinned mirror) and the side streams exist.
-static int ensure_batch_resources(sift_ctx *ctx, size_t image_bytes)
-{
-  int rc;
-  if (!ctx->h2d_stream) CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
-  if (!ctx->d2h_stream) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
-    if (!ctx->ev_h2d[i]) CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-    if (!ctx->ev_done[i]) CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-    if (!ctx->ev_d2h[i]) CK(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+  // fork: everything the caller queued on the public stream so far (e.g. the producer of d_image) is visible
+  CK(cudaEventRecord(ln->ev_fork, ctx->main_stream));
+  CK(cudaStreamWaitEvent(ln->stream, ln->ev_fork, 0));
+  rc = run_pyramid(ctx, d_image, dtype, pitch_bytes);
+  if (!rc) rc = cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream) == cudaSuccess ? SIFT_OK : fail(ctx, SIFT_ERR_CUDA, "memset failed");
+  if (!rc) rc = run_scan(ctx, 0);
+  if (!rc) rc = run_refine(ctx, -1, d_out, cap);
+  if (!rc) {
+    copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), d_count);
+    ctx->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "copy_count launch failed");
   }
-  CK(cudaStreamSynchronize(ctx->h2d_stream));
-  CK(cudaStreamSynchronize(ctx->d2h_stream));
-  for (int i = 0; i < 2; i++) {
-    if ((rc = grow(ctx, ctx->image_s[i], image_bytes))) return rc;
-    if ((rc = grow(ctx, ctx->outbuf_s[i], sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint)))) return rc;
-    if ((rc = grow_pinned(ctx, &ctx->h_out_s[i], &ctx->h_out_cap_s[i],
-                          sizeof(Counters) + (size_t)ctx->kp_cap * sizeof(sift_keypoint))))
-      return rc;
-  }
-  return SIFT_OK;
+  ln->busy = true;
+  ctx->pyramid_built = false;          // the stage API reads lane 0, which this call may not have used
+  ctx->L = &ctx->lanes[0];
+  return rc;
 }
 
 static void add_stats(sift_stats &t, const sift_stats &s)
@@ -687,9 +767,9 @@ static void add_stats(sift_stats &t, const sift_stats &s)
   t.msDevice += s.msDevice; t.kernelLaunches += s.kernelLaunches;
 }
 
-// Images are independent: frame i+1 is uploaded and frame i-1 is downloaded / ordered on the
-// host while frame i is computed.  Two slots of {device image, device keypoints, pinned mirror}; the pyramid
-// itself is shared because the compute stream processes one frame at a time.
+// Images are independent: frame i runs on lane i % n_lanes -- upload, kernels and download
+// queued on that lane's stream -- so the copies of one frame overlap the kernels of the others and the
+// host orders frame i - n_lanes + 1 while the device works.
 SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int width, int height,
                                size_t pitch_bytes, size_t image_stride_bytes, int n_images,
                                const sift_params *params, sift_keypoint *out, int cap, int *offsets,
@@ -707,33 +787,62 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
   if (n_images == 0) { if (stats) *stats = total; return SIFT_OK; }
   CK(cudaSetDevice(ctx->device));
   int rc;
-  ctx->slot = 0;
+  if ((rc = sift_synchronize(ctx))) return rc;            // lanes may hold device-resident work of earlier calls
   if ((rc = ensure_plan(ctx, width, height, params))) return rc;
   const size_t row = (size_t)width * es;
   if (pitch_bytes == 0) pitch_bytes = row;
   if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
-  if ((rc = ensure_batch_resources(ctx, row * height))) return rc;
-  const size_t first = sizeof(Counters) + (size_t)std::min(ctx->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+  const int NL = std::min(ctx->n_lanes, n_images);
+  auto prepare_lanes = [&]() -> int {
+    for (int l = 0; l < NL; l++) {
+      Lane *ln = &ctx->lanes[l];
+      ctx->L = ln;
+      int r;
+      if ((r = ensure_lane(ctx, ln))) return r;
+      if ((r = grow(ctx, ln->image, row * height))) return r;
+      if ((r = grow_pinned(ctx, &ln->h_out, &ln->h_out_cap, sizeof(Counters) + (size_t)ln->kp_cap * sizeof(sift_keypoint))))
+        return r;
+    }
+    return SIFT_OK;
+  };
+  if ((rc = prepare_lanes())) { ctx->L = &ctx->lanes[0]; return rc; }
   const int64_t l0 = ctx->launches;
   int n = 0, overflow = 0;
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
-
   int done = 0, issued = 0;     // frames consumed by the host / frames whose device work has been issued
+  CK(cudaEventRecord(ctx->ev0, ctx->lanes[0].stream));
   auto take = [&](int j, int ni, const sift_stats &si) { n += ni; offsets[j + 1] = n; add_stats(total, si); };
-  // consume frame `done` (its D2H was issued): order its keypoints into `out`
+
+  auto issue = [&](int i) -> int {
+    Lane *ln = &ctx->lanes[i % NL];
+    ctx->L = ln;
+    const void *img = (const char *)images + (size_t)i * image_stride_bytes;
+    if (pitch_bytes == row) CK(cudaMemcpyAsync(ln->image.p, img, row * height, cudaMemcpyHostToDevice, ln->stream));
+    else CK(cudaMemcpy2DAsync(ln->image.p, row, img, pitch_bytes, row, height, cudaMemcpyHostToDevice, ln->stream));
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream));
+    int r;
+    if ((r = run_pyramid(ctx, ln->image.p, dtype, row))) return r;
+    if ((r = run_scan(ctx, 0))) return r;
+    if ((r = run_refine(ctx, -1, dev_keypoints(ctx), ln->kp_cap))) return r;
+    const size_t first = sizeof(Counters) + (size_t)std::min(ln->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+    CK(cudaMemcpyAsync(ln->h_out, ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
+    CK(cudaEventRecord(ln->ev_done, ln->stream));
+    issued = i + 1;
+    return SIFT_OK;
+  };
+
+  // consume frame `done`: order its keypoints into `out`
   auto consume = [&]() -> int {
-    const int j = done, sl = j & 1;
-    CK(cudaEventSynchronize(ctx->ev_d2h[sl]));
-    Counters c = *(Counters *)ctx->h_out_s[sl];
+    const int j = done;
+    Lane *ln = &ctx->lanes[j % NL];
+    ctx->L = ln;
+    CK(cudaEventSynchronize(ln->ev_done));
+    Counters c = *(Counters *)ln->h_out;
     sift_stats si;
     memset(&si, 0, sizeof si);
-    if (c.n_cand > ctx->cand_cap || c.n_kp > ctx->kp_cap) {
-      // rare: device buffers too small -- drain the pipeline and redo every issued frame on the growing
-      // single-frame path (the buffers, pinned mirrors included, are reallocated by it)
-      CK(cudaStreamSynchronize(ctx->stream));
-      CK(cudaStreamSynchronize(ctx->h2d_stream));
-      CK(cudaStreamSynchronize(ctx->d2h_stream));
-      ctx->slot = 0;
+    if (c.n_cand > ln->cand_cap || c.n_kp > ln->kp_cap) {
+      // rare: device buffers too small -- drain every lane and redo the issued frames on the growing
+      // single-frame path (lane 0), then size the other lanes like it
+      for (int l = 0; l < NL; l++) CK(cudaStreamSynchronize(ctx->lanes[l].stream));
       for (int q = j; q < issued; q++) {
         int ni = 0;
         const int room = overflow ? 0 : std::max(0, cap - n);
@@ -744,14 +853,23 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
         take(q, ni, si);
       }
       done = issued;
-      return ensure_batch_resources(ctx, row * height);
+      Lane *l0p = &ctx->lanes[0];
+      for (int l = 1; l < NL; l++) {
+        Lane *o = &ctx->lanes[l];
+        ctx->L = o;
+        int r;
+        if (l0p->cand_cap > o->cand_cap) { if ((r = grow(ctx, o->cand, (size_t)l0p->cand_cap * sizeof(sift_candidate)))) return r; o->cand_cap = l0p->cand_cap; }
+        if (l0p->kp_cap > o->kp_cap) { if ((r = grow(ctx, o->outbuf, sizeof(Counters) + (size_t)l0p->kp_cap * sizeof(sift_keypoint)))) return r; o->kp_cap = l0p->kp_cap; }
+      }
+      return prepare_lanes();
     }
     if (c.n_kp > FIRST_CHUNK) {
-      CK(cudaMemcpyAsync((char *)ctx->h_out_s[sl] + first, (char *)ctx->outbuf_s[sl].p + first,
-                         (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-      CK(cudaStreamSynchronize(ctx->d2h_stream));
+      const size_t first = sizeof(Counters) + (size_t)FIRST_CHUNK * sizeof(sift_keypoint);
+      CK(cudaMemcpyAsync((char *)ln->h_out + first, (char *)ln->outbuf.p + first,
+                         (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ln->stream));
+      CK(cudaStreamSynchronize(ln->stream));
     }
-    const sift_keypoint *kps = (const sift_keypoint *)((char *)ctx->h_out_s[sl] + sizeof(Counters));
+    const sift_keypoint *kps = (const sift_keypoint *)((char *)ln->h_out + sizeof(Counters));
     const int room = overflow ? 0 : std::max(0, cap - n);
     sort_keypoints_into(ctx, kps, c.n_kp, room ? out + n : nullptr, room);
     if (c.n_kp > room) overflow = 1;
@@ -762,37 +880,20 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     return SIFT_OK;
   };
 
-  for (int i = 0; i < n_images; i++) {
-    const int sl = i & 1;
-    const void *img = (const char *)images + (size_t)i * image_stride_bytes;
-    // upload i: the slot's previous frame (i-2) must have been read by the compute stream
-    if (i >= 2) CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[sl], 0));
-    else CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev0, 0));
-    if (pitch_bytes == row)
-      CK(cudaMemcpyAsync(ctx->image_s[sl].p, img, row * height, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    else
-      CK(cudaMemcpy2DAsync(ctx->image_s[sl].p, row, img, pitch_bytes, row, height, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    CK(cudaEventRecord(ctx->ev_h2d[sl], ctx->h2d_stream));
-    // compute i: needs the upload, and the slot's previous keypoints (frame i-2) must be on the host already
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[sl], 0));
-    if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[sl], 0));
-    ctx->slot = sl;
-    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
-    if ((rc = run_pyramid(ctx, ctx->image_s[sl].p, dtype, row))) return rc;
-    if ((rc = run_scan(ctx, 0))) return rc;
-    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->kp_cap))) return rc;
-    CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
-    // download i
-    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_done[sl], 0));
-    CK(cudaMemcpyAsync(ctx->h_out_s[sl], ctx->outbuf_s[sl].p, first, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    CK(cudaEventRecord(ctx->ev_d2h[sl], ctx->d2h_stream));
-    issued = i + 1;
-    // meanwhile the host orders frame i-1
-    while (done < i) if ((rc = consume())) return rc;
+  rc = SIFT_OK;
+  for (int i = 0; i < n_images && !rc; i++) {
+    while (!rc && i - done >= NL) rc = consume();          // the lane's previous frame must be off its buffers
+    if (!rc && issued <= i) rc = issue(i);                  // (an overflow fallback may already have covered frame i)
   }
-  while (done < n_images) if ((rc = consume())) return rc;
-  ctx->slot = 0;
-  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  while (!rc && done < n_images) {
+    if (issued <= done) rc = issue(done);
+    if (!rc) rc = consume();
+  }
+  ctx->L = &ctx->lanes[0];
+  ctx->pyramid_built = false;
+  if (rc) return rc;
+  for (int l = 0; l < NL; l++) CK(cudaStreamSynchronize(ctx->lanes[l].stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->lanes[0].stream));
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -811,11 +912,11 @@ SIFT_API int sift_build_scale_space(sift_ctx *ctx, const void *image, int dtype,
   if (!image) return fail(ctx, SIFT_ERR_BAD_ARGS, "image is NULL");
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  if ((rc = ensure_plan0(ctx, width, height, params))) return rc;
   size_t dpitch;
   if ((rc = upload_image(ctx, image, dtype, width, height, pitch_bytes, &dpitch))) return rc;
-  if ((rc = run_pyramid(ctx, ctx->image_s[ctx->slot].p, dtype, dpitch))) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
+  if ((rc = run_pyramid(ctx, ctx->L->image.p, dtype, dpitch))) return rc;
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -842,29 +943,29 @@ SIFT_API int sift_find_candidates(sift_ctx *ctx, const sift_params *params, sift
     ctx->low_cap = low_cap;
   }
   for (int attempt = 0;; attempt++) {
-    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
     const int saved_low_cap = ctx->low_cap;
     if (!low) ctx->low_cap = 0;                      // count only
     rc = run_scan(ctx, count_low, params);
     ctx->low_cap = saved_low_cap;
     if (rc) return rc;
-    CK(cudaMemcpyAsync(&c, dev_counters(ctx), sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (c.n_cand <= ctx->cand_cap || attempt >= 2) break;
-    if ((rc = grow(ctx, ctx->cand, (size_t)(c.n_cand + 1024) * sizeof(sift_candidate)))) return rc;
-    ctx->cand_cap = c.n_cand + 1024;
+    CK(cudaMemcpyAsync(&c, dev_counters(ctx), sizeof c, cudaMemcpyDeviceToHost, ctx->L->stream));
+    CK(cudaStreamSynchronize(ctx->L->stream));
+    if (c.n_cand <= ctx->L->cand_cap || attempt >= 2) break;
+    if ((rc = grow(ctx, ctx->L->cand, (size_t)(c.n_cand + 1024) * sizeof(sift_candidate)))) return rc;
+    ctx->L->cand_cap = c.n_cand + 1024;
   }
   ctx->last = c;
   *n_out = c.n_cand;
   if (n_low) *n_low = c.n_low;
   int status = SIFT_OK;
-  const int nc = std::min(std::min(c.n_cand, ctx->cand_cap), cap);
+  const int nc = std::min(std::min(c.n_cand, ctx->L->cand_cap), cap);
   if (nc > 0 && out) {
     // sort needs the whole list: stage through pinned memory
-    const int all = std::min(c.n_cand, ctx->cand_cap);
+    const int all = std::min(c.n_cand, ctx->L->cand_cap);
     if ((rc = grow_pinned(ctx, &ctx->h_cand, &ctx->h_cand_cap, (size_t)all * sizeof(sift_candidate)))) return rc;
-    CK(cudaMemcpyAsync(ctx->h_cand, ctx->cand.p, (size_t)all * sizeof(sift_candidate), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_cand, ctx->L->cand.p, (size_t)all * sizeof(sift_candidate), cudaMemcpyDeviceToHost, ctx->L->stream));
+    CK(cudaStreamSynchronize(ctx->L->stream));
     sort_candidates((sift_candidate *)ctx->h_cand, all);
     memcpy(out, ctx->h_cand, (size_t)nc * sizeof(sift_candidate));
   }
@@ -892,24 +993,24 @@ SIFT_API int sift_refine(sift_ctx *ctx, const sift_params *params, const sift_ca
   for (int i = 0; i < n_cands; i++) {
     const sift_candidate &c = cands[i];
     if (c.octave < 0 || c.octave >= ctx->n_oct || c.scaleLevel < 1 || c.scaleLevel > ndog - 2 || c.x < 1 ||
-        c.y < 1 || c.x > ctx->octs[c.octave].w - 2 || c.y > ctx->octs[c.octave].h - 2)
+        c.y < 1 || c.x > ctx->L->octs[c.octave].w - 2 || c.y > ctx->L->octs[c.octave].h - 2)
       return fail(ctx, SIFT_ERR_BAD_ARGS, "candidate %d (o%d s%d x%d y%d) outside the DoG interior", i, c.octave,
                   c.scaleLevel, c.x, c.y);
   }
-  if (n_cands > ctx->cand_cap) {
-    if ((rc = grow(ctx, ctx->cand, (size_t)n_cands * sizeof(sift_candidate)))) return rc;
-    ctx->cand_cap = n_cands;
+  if (n_cands > ctx->L->cand_cap) {
+    if ((rc = grow(ctx, ctx->L->cand, (size_t)n_cands * sizeof(sift_candidate)))) return rc;
+    ctx->L->cand_cap = n_cands;
   }
-  if (n_cands > ctx->kp_cap) {
-    if ((rc = grow(ctx, ctx->outbuf_s[ctx->slot], sizeof(Counters) + (size_t)n_cands * sizeof(sift_keypoint)))) return rc;
-    ctx->kp_cap = n_cands;
+  if (n_cands > ctx->L->kp_cap) {
+    if ((rc = grow(ctx, ctx->L->outbuf, sizeof(Counters) + (size_t)n_cands * sizeof(sift_keypoint)))) return rc;
+    ctx->L->kp_cap = n_cands;
   }
-  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->stream));
+  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
   Counters c;
   sift_keypoint *kps = nullptr;
   if (n_cands > 0) {
-    CK(cudaMemcpyAsync(ctx->cand.p, cands, (size_t)n_cands * sizeof(sift_candidate), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = run_refine(ctx, n_cands, dev_keypoints(ctx), ctx->kp_cap, params))) return rc;
+    CK(cudaMemcpyAsync(ctx->L->cand.p, cands, (size_t)n_cands * sizeof(sift_candidate), cudaMemcpyHostToDevice, ctx->L->stream));
+    if ((rc = run_refine(ctx, n_cands, dev_keypoints(ctx), ctx->L->kp_cap, params))) return rc;
   }
   if ((rc = download_keypoints(ctx, &c, &kps))) return rc;
   c.n_cand = n_cands;
@@ -943,8 +1044,8 @@ SIFT_API int sift_get_pyramid_info(const sift_ctx *ctx, int *octaves, int *level
 SIFT_API int sift_get_octave_size(const sift_ctx *ctx, int octave, int *width, int *height)
 {
   if (!ctx || !ctx->plan_valid || octave < 0 || octave >= ctx->n_oct) return SIFT_ERR_BAD_ARGS;
-  if (width) *width = ctx->octs[octave].w;
-  if (height) *height = ctx->octs[octave].h;
+  if (width) *width = ctx->L->octs[octave].w;
+  if (height) *height = ctx->L->octs[octave].h;
   return SIFT_OK;
 }
 
@@ -962,7 +1063,7 @@ static float *plane_ptr(sift_ctx *ctx, int kind, int octave, int level)
   if (!ctx->plan_valid || octave < 0 || octave >= ctx->n_oct) return nullptr;
   const int nl = (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->nlev : ctx->nlev - 1;
   if (level < 0 || level >= nl) return nullptr;
-  return (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->octs[octave].gauss[level] : ctx->octs[octave].dog[level];
+  return (kind == SIFT_LEVEL_GAUSSIAN) ? ctx->L->octs[octave].gauss[level] : ctx->L->octs[octave].dog[level];
 }
 
 SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, float *dst)
@@ -973,10 +1074,10 @@ SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, floa
   float *p = plane_ptr(ctx, kind, octave, level);
   if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "no level kind %d octave %d level %d", kind, octave, level);
   CK(cudaSetDevice(ctx->device));
-  const OctaveDev &od = ctx->octs[octave];
+  const OctaveDev &od = ctx->L->octs[octave];
   CK(cudaMemcpy2DAsync(dst, (size_t)od.w * 4, p, (size_t)od.pitch * 4, (size_t)od.w * 4, od.h,
-                       cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                       cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -988,7 +1089,7 @@ SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, cons
     return fail(ctx, SIFT_ERR_BAD_ARGS, "octave-0 size %dx%d must be even (2x upsampled)", width0, height0);
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure_plan(ctx, width0 / 2, height0 / 2, params))) return rc;
+  if ((rc = ensure_plan0(ctx, width0 / 2, height0 / 2, params))) return rc;
   ctx->pyramid_built = true;
   return SIFT_OK;
 }
@@ -1000,10 +1101,10 @@ SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, cons
   float *p = plane_ptr(ctx, kind, octave, level);
   if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "no level kind %d octave %d level %d", kind, octave, level);
   CK(cudaSetDevice(ctx->device));
-  const OctaveDev &od = ctx->octs[octave];
+  const OctaveDev &od = ctx->L->octs[octave];
   CK(cudaMemcpy2DAsync(p, (size_t)od.pitch * 4, src, (size_t)od.w * 4, (size_t)od.w * 4, od.h,
-                       cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                       cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -1025,18 +1126,18 @@ SIFT_API int sift_blur_chunk(sift_ctx *ctx, const double *input, int rows, int c
   if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n)) ||
       (rc = grow(ctx, ctx->misc[3], w.size() * sizeof(double))))
     return rc;
-  CK(cudaMemcpyAsync(ctx->misc[0].p, input, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->misc[3].p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));                        // w is a local
-  launch_blur_plane_f64(ctx->stream, (const double *)ctx->misc[0].p, rows, cols, (double *)ctx->misc[1].p,
+  CK(cudaMemcpyAsync(ctx->misc[0].p, input, n, cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaMemcpyAsync(ctx->misc[3].p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));                        // w is a local
+  launch_blur_plane_f64(ctx->L->stream, (const double *)ctx->misc[0].p, rows, cols, (double *)ctx->misc[1].p,
                         (double *)ctx->misc[2].p, (const double *)ctx->misc[3].p, R, x1, y1, x2, y2);
   ctx->launches += 2;
   CK(cudaGetLastError());
   const size_t rowb = (size_t)(x2 - x1) * sizeof(double);
   CK(cudaMemcpy2DAsync(output + (size_t)y1 * cols + x1, (size_t)cols * 8,
                        (const double *)ctx->misc[2].p + (size_t)y1 * cols + x1, (size_t)cols * 8, rowb, y2 - y1,
-                       cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                       cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -1051,17 +1152,17 @@ SIFT_API int sift_subtract_chunk(sift_ctx *ctx, const double *a, const double *b
   const size_t n = (size_t)rows * cols * sizeof(double);
   int rc;
   if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n))) return rc;
-  CK(cudaMemcpyAsync(ctx->misc[0].p, a, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->misc[1].p, b, n, cudaMemcpyHostToDevice, ctx->stream));
-  launch_subtract_f64(ctx->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
+  CK(cudaMemcpyAsync(ctx->misc[0].p, a, n, cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaMemcpyAsync(ctx->misc[1].p, b, n, cudaMemcpyHostToDevice, ctx->L->stream));
+  launch_subtract_f64(ctx->L->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
                       (double *)ctx->misc[2].p, cols, x1, y1, x2, y2);
   ctx->launches += 1;
   CK(cudaGetLastError());
   const size_t rowb = (size_t)(x2 - x1) * sizeof(double);
   CK(cudaMemcpy2DAsync(output + (size_t)y1 * cols + x1, (size_t)cols * 8,
                        (const double *)ctx->misc[2].p + (size_t)y1 * cols + x1, (size_t)cols * 8, rowb, y2 - y1,
-                       cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+                       cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -1084,28 +1185,28 @@ SIFT_API int sift_find_extremas(sift_ctx *ctx, const double *d0, const double *d
   if ((rc = grow(ctx, ctx->misc[0], n)) || (rc = grow(ctx, ctx->misc[1], n)) || (rc = grow(ctx, ctx->misc[2], n)) ||
       (rc = grow(ctx, ctx->misc[3], 256 + 2 * list_bytes)))
     return rc;
-  CK(cudaMemcpyAsync(ctx->misc[0].p, d0, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->misc[1].p, d1, n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->misc[2].p, d2, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc[0].p, d0, n, cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaMemcpyAsync(ctx->misc[1].p, d1, n, cudaMemcpyHostToDevice, ctx->L->stream));
+  CK(cudaMemcpyAsync(ctx->misc[2].p, d2, n, cudaMemcpyHostToDevice, ctx->L->stream));
   char *base = (char *)ctx->misc[3].p;
   int *counts = (int *)base;
   double *cv = (double *)(base + 256);
   double *lv = cv + npx;
   int32_t *cxy = (int32_t *)(lv + npx);
   int32_t *lxy = cxy + 2 * npx;
-  CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->L->stream));
   sift_params tmp;
   sift_default_params(&tmp);
   tmp.scalesPerOctave = scales_per_octave;
   tmp.contrastThreshold = contrast_threshold_c;
   const double pix_thr = contrast_threshold(tmp) * prefilter_factor;              // sift.js:285-293
-  launch_scan_f64(ctx->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
+  launch_scan_f64(ctx->L->stream, (const double *)ctx->misc[0].p, (const double *)ctx->misc[1].p,
                   (const double *)ctx->misc[2].p, rows, cols, pix_thr, cxy, cv, (int)npx, lxy, lv, (int)npx, counts);
   ctx->launches += 1;
   CK(cudaGetLastError());
   int hc[2];
-  CK(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   *n_cand = hc[0];
   *n_low = hc[1];
   auto fetch = [&](int cnt, const int32_t *dxy, const double *dv, int32_t *oxy, double *ov, int ocap) -> int {
@@ -1146,13 +1247,13 @@ SIFT_API int sift_gradient_hessian(sift_ctx *ctx, const double *dm, const double
   int rc;
   if ((rc = grow(ctx, ctx->misc[4], sizeof win + 12 * sizeof(double)))) return rc;
   double *dwin = (double *)ctx->misc[4].p;
-  CK(cudaMemcpyAsync(dwin, win, sizeof win, cudaMemcpyHostToDevice, ctx->stream));
-  launch_grad_hess_f64(ctx->stream, dwin, dwin + 9, dwin + 18, 3, 1, 1, dwin + 27);
+  CK(cudaMemcpyAsync(dwin, win, sizeof win, cudaMemcpyHostToDevice, ctx->L->stream));
+  launch_grad_hess_f64(ctx->L->stream, dwin, dwin + 9, dwin + 18, 3, 1, 1, dwin + 27);
   ctx->launches += 1;
   CK(cudaGetLastError());
   double out12[12];
-  CK(cudaMemcpyAsync(out12, dwin + 27, sizeof out12, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(out12, dwin + 27, sizeof out12, cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   for (int i = 0; i < 3; i++) g[i] = out12[i];
   for (int i = 0; i < 9; i++) h[i] = out12[3 + i];
   return SIFT_OK;
@@ -1181,12 +1282,12 @@ SIFT_API int sift_linear_resize(sift_ctx *ctx, const double *input, int rows, in
   int rc;
   const size_t nin = (size_t)rows * cols * 8, nout = (size_t)orows * ocols * 8;
   if ((rc = grow(ctx, ctx->misc[0], nin)) || (rc = grow(ctx, ctx->misc[1], nout))) return rc;
-  CK(cudaMemcpyAsync(ctx->misc[0].p, input, nin, cudaMemcpyHostToDevice, ctx->stream));
-  launch_resize_f64(ctx->stream, (const double *)ctx->misc[0].p, rows, cols, rate, (double *)ctx->misc[1].p, orows, ocols);
+  CK(cudaMemcpyAsync(ctx->misc[0].p, input, nin, cudaMemcpyHostToDevice, ctx->L->stream));
+  launch_resize_f64(ctx->L->stream, (const double *)ctx->misc[0].p, rows, cols, rate, (double *)ctx->misc[1].p, orows, ocols);
   ctx->launches += 1;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(output, ctx->misc[1].p, nout, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(output, ctx->misc[1].p, nout, cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 

@@ -81,6 +81,14 @@ class Engine:
     def synchronize(self):
         self._check(self._lib.sift_synchronize(self._h))
 
+    def flush(self):
+        """Order every device-resident detection issued so far before later work on `stream` (non-blocking)."""
+        self._check(self._lib.sift_flush(self._h))
+
+    def set_lanes(self, n: int):
+        """Frames in flight for detect_device / detect_batch (1..4)."""
+        self._check(self._lib.sift_set_lanes(self._h, int(n)))
+
     def set_profiling(self, enabled: bool):
         self._check(self._lib.sift_set_profiling(self._h, 1 if enabled else 0))
 

@@ -157,3 +157,41 @@ def test_full_hd_properties(engine):
     kb = {(int(k["scaleLevel"]), int(k["localX"]), 2160 - 1 - int(k["localY"])) for k in b if k["octave"] == 0}
     assert len(ka) > 500
     assert len(ka & kb) >= 0.995 * max(len(ka), len(kb))
+
+
+def test_device_resident_frames_in_flight_equal_single(engine):
+    """sift_detect_device deals frames to lanes (frames in flight); results must equal the host call, per frame."""
+    import torch
+    n, w, h = 7, 200, 144
+    frames = np.stack([fixtures.synthetic_u8(w, h, 50 + i) for i in range(n)])
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    d = torch.from_numpy(frames).cuda()
+    cap = 4096
+    out = torch.zeros(n, cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for lanes in (3, 1, 4):
+        engine.set_lanes(lanes)
+        out.zero_(); cnt.zero_()
+        torch.cuda.synchronize()
+        for i in range(n):
+            engine.detect_device(d[i].data_ptr(), L.SIFT_U8, w, h, 0, prm, out[i].data_ptr(), cap, cnt[i].data_ptr())
+        engine.synchronize()
+        for i in range(n):
+            k = int(cnt[i].item())
+            got = np.frombuffer(out[i].cpu().numpy().tobytes(), dtype=L.KEYPOINT_DTYPE)[:k]
+            want, _ = engine.detect(frames[i], prm)
+            key = lambda a: np.lexsort((a["candX"], a["candY"], a["candScale"], a["octave"]))
+            assert k == len(want) and k > 5
+            assert got[key(got)].tobytes() == want.tobytes()
+    engine.set_lanes(3)
+
+
+def test_batch_overflow_falls_back_and_stays_correct(engine):
+    """More keypoints than the device buffers were sized for: the batch path regrows and still matches."""
+    frames = np.stack([fixtures.synthetic_u8(96, 96, 300 + i, blobs=400, sigma_lo=0.7, sigma_hi=2.0) for i in range(5)])
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=0.8)
+    kps, offs, st = engine.detect_batch(frames, prm)
+    assert st["keypoints"] == len(kps) == offs[-1]
+    for i in range(5):
+        single, _ = engine.detect(frames[i], prm)
+        assert kps[offs[i]:offs[i + 1]].tobytes() == single.tobytes()
