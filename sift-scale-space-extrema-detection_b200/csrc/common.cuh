@@ -64,6 +64,16 @@ void launch_resize_f64(cudaStream_t st, const double *in, int rows, int cols, do
                        int orows, int ocols);
 void launch_seed_to_f32(cudaStream_t st, const double *seed, int w, int h, float *dst, int pitch);
 
+// blur_sep.cu: pass A (along x) -> fp64 T^T planes -> pass B (along y), all levels of an octave per launch
+bool sep_supported(const LevelPlan *plans, int first_level, int nlev, int w, int h);
+size_t sep_t_elems(int w, int trows, int n_levels);
+void launch_sep_pass_a(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int upsample,
+                       int w, int hrows, int h, const double *d_weights, const LevelPlan *plans, int first_level,
+                       int nlev, double *tbase);
+void launch_sep_pass_b(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
+                       const LevelPlan *plans, int first_level, double *tbase, int hrows, const OctaveDev *next,
+                       int spo, int keep_gauss);
+
 // blur_fused.cu
 void fused0_merge_taps(const double *w, int R, double *out /* fused0_taps_per_level() doubles */);
 int fused0_taps_per_level(void);
@@ -78,6 +88,13 @@ void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int s
                         int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,
                         Counters *ctr);
 void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
+                     double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
+                     int low_cap, Counters *ctr);
+// TMA-tiled scan (one tensor map per octave and DoG level, built per lane when its pyramid is laid out)
+size_t scan_tma_map_bytes(int n_oct, int ndog);
+bool scan_tma_supported(int ndog);
+int scan_tma_build_maps(const OctaveDev *octs, int n_oct, int ndog, void *h_maps);
+void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_maps, int n_oct, int spo,
                      double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
                      int low_cap, Counters *ctr);
 void launch_scan_f64(cudaStream_t st, const double *d0, const double *d1, const double *d2, int rows, int cols,

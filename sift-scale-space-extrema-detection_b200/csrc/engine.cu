@@ -32,7 +32,8 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps;
+  bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
   int cand_cap = 0, kp_cap = 0;
   void *h_out = nullptr;       // pinned mirror of outbuf
   size_t h_out_cap = 0;
@@ -72,6 +73,8 @@ struct sift_ctx {
   int poly_woff = 0;               // octave 0: merged polyphase tap table (blur_fused.cu)
   bool fused0 = false;             // octave 0 runs the fused polyphase kernel
   bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
+  bool no_tma = false;             // SIFT_B200_NO_TMA=1: the pointer-chasing scan instead of the TMA-tiled one
+  bool force_old = false;          // SIFT_B200_FORCE_OLD=1: the row-major-T fallback kernels (blur_generic.cu) everywhere
   double *d_weights = nullptr;
   size_t d_weights_cap = 0;
 
@@ -270,7 +273,8 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
     if (o > 0) seed_elems += (size_t)ow[o] * oh[o];
     const size_t trows = (o == 0) ? (size_t)h : (size_t)oh[o];
     const size_t tl = (o == 0) ? nlev : nlev - 1;
-    if (o > 0 || !ctx->fused0) t_bytes = std::max(t_bytes, tl * trows * ow[o] * sizeof(double));
+    if (o > 0 || !ctx->fused0)
+      t_bytes = std::max(t_bytes, std::max(tl * trows * ow[o], sep_t_elems(ow[o], (int)trows, (int)tl)) * sizeof(double));
   }
   int rc = SIFT_OK;
   do {
@@ -296,6 +300,20 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
     if (cudaMemcpyAsync(ln->d_octs, ln->octs, sizeof(OctaveDev) * n_oct, cudaMemcpyHostToDevice, ln->stream) != cudaSuccess) {
       rc = fail(ctx, SIFT_ERR_CUDA, "upload of the octave table failed");
       break;
+    }
+    // TMA descriptors of the DoG planes for the tiled scan
+    ln->tma_scan = false;
+    if (!ctx->no_tma && scan_tma_supported(nlev - 1)) {
+      std::vector<char> hm(scan_tma_map_bytes(n_oct, nlev - 1));
+      if (scan_tma_build_maps(ln->octs, n_oct, nlev - 1, hm.data())) {
+        if ((rc = grow(ctx, ln->tmaps, hm.size()))) break;
+        if (cudaMemcpyAsync(ln->tmaps.p, hm.data(), hm.size(), cudaMemcpyHostToDevice, ln->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ln->stream) != cudaSuccess) {
+          rc = fail(ctx, SIFT_ERR_CUDA, "upload of the TMA descriptors failed");
+          break;
+        }
+        ln->tma_scan = true;
+      }
     }
     // candidate / keypoint capacity: extrema are ~3e-4 of the voxels on the synthetic frames
     const int want = (int)std::min<int64_t>(std::max<int64_t>(16384, ((int64_t)w * h) / 8), 1 << 26);
@@ -343,17 +361,29 @@ static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pit
     }
     const int first = (o == 0) ? 0 : 1;
     const int hrows = (o == 0) ? ctx->in_h : od.h;
-    double *T[SIFT_MAX_LEVELS];
-    for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->L->tbuf.p + (size_t)i * hrows * od.w;
     prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
-    if (o == 0)
-      launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
-                   ctx->plans[o], first, ctx->nlev, T, nullptr);
-    else
-      launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
-                   ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
-    launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T,
-                 (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr, spo, ctx->keep_gauss);
+    const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
+    if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
+      double *tb = (double *)ctx->L->tbuf.p;
+      if (o == 0)
+        launch_sep_pass_a(st, d_image, dtype, pitch_bytes, ctx->in_w, 1, od.w, hrows, od.h, ctx->d_weights,
+                          ctx->plans[o], first, ctx->nlev, tb);
+      else
+        launch_sep_pass_a(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, 0, od.w, hrows, od.h,
+                          ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb);
+      launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss);
+    } else {
+      // radii too large for the staged tiles (octaves >= 4): row-major T, level-parallel kernels
+      double *T[SIFT_MAX_LEVELS];
+      for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->L->tbuf.p + (size_t)i * hrows * od.w;
+      if (o == 0)
+        launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
+                     ctx->plans[o], first, ctx->nlev, T, nullptr);
+      else
+        launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
+                     ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
+      launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T, next, spo, ctx->keep_gauss);
+    }
     ctx->launches += 2;
     prof_end(ctx);
   }
@@ -374,9 +404,14 @@ static int run_scan(sift_ctx *ctx, int count_low, const sift_params *thr = nullp
   if (thr) { tp.contrastThreshold = thr->contrastThreshold; tp.preFilterFactor = thr->preFilterFactor; }
   const double pix_thr = contrast_threshold(tp) * tp.preFilterFactor;               // sift.js:293
   prof_begin(ctx, SIFT_PROF_SCAN);
-  launch_scan_all(ctx->L->stream, ctx->L->octs, ctx->L->d_octs, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
-                  (sift_candidate *)ctx->L->cand.p, ctx->L->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
-                  dev_counters(ctx));
+  if (ctx->L->tma_scan)
+    launch_scan_tma(ctx->L->stream, ctx->L->octs, ctx->L->tmaps.p, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
+                    (sift_candidate *)ctx->L->cand.p, ctx->L->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
+                    dev_counters(ctx));
+  else
+    launch_scan_all(ctx->L->stream, ctx->L->octs, ctx->L->d_octs, ctx->n_oct, ctx->prm.scalesPerOctave, pix_thr, count_low,
+                    (sift_candidate *)ctx->L->cand.p, ctx->L->cand_cap, (sift_candidate *)ctx->low.p, ctx->low_cap,
+                    dev_counters(ctx));
   ctx->launches += 1;
   prof_end(ctx);
   CK(cudaGetLastError());
@@ -591,6 +626,10 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   sift_default_params(&c->prm);
   const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
+  const char *fo = getenv("SIFT_B200_FORCE_OLD");
+  c->force_old = fo && fo[0] == '1';
+  const char *nt = getenv("SIFT_B200_NO_TMA");
+  c->no_tma = nt && nt[0] == '1';
   const char *nl = getenv("SIFT_B200_LANES");
   if (nl && nl[0] >= '1' && nl[0] <= '0' + SIFT_MAX_LANES) c->n_lanes = nl[0] - '0';
   *out = c;
@@ -603,7 +642,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);

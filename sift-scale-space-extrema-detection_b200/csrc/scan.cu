@@ -8,6 +8,8 @@
 // (sift.js:285-294) sends it to the candidate list, otherwise to the low-contrast
 // list (only materialised / counted on request: it feeds red UI markers only,
 // background.js:408-413).
+#include <cmath>
+#include <cstring>
 #include "common.cuh"
 
 #define SC_BX 32
@@ -227,6 +229,264 @@ void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *
   if (total == 0) return;
   dim3 block(32, SA_TH);
   scan_all_kernel<<<total, block, 0, st>>>(d_octs, A, cand, cand_cap, low, low_cap, ctr);
+}
+
+// ---- whole pyramid in one launch, TMA-tiled -------------------------------------------------------
+// One CTA = one 128 x 32 pixel tile of one octave.  An elected thread issues one TMA 2D tile load
+// (cp.async.bulk.tensor) per DoG level -- box 136 x 34 floats: the tile plus the one-pixel ring the
+// 26-neighbour test needs, widened to keep 16-byte alignment -- and the CTA waits on an mbarrier; out-of-
+// range rows / columns are zero-filled by the TMA unit and never tested (sift.js:221-222 scans the
+// interior only).  Every DoG value is read from HBM once per tile (+ halo) and all tests run from shared
+// memory, branch-free: a thread owns 2 neighbouring pixels and marches down 8 rows keeping, per level, the
+// horizontal 3-max / 3-min of the two previous rows in registers; a pixel is a strict maximum iff it is
+// greater than max(3x3 block above, 3x3 block below, its 8 in-plane neighbours) (sift.js:261,266: ties
+// are never extrema).  Hits are compacted with ballot / popc and one atomic per warp.
+#include <cuda.h>
+
+#define ST_TW 128
+#define ST_TH 16
+#define ST_BW (ST_TW + 8)      // box: 4 columns left (alignment) + tile + 4 right
+#define ST_BH (ST_TH + 2)
+#define ST_PLANE ((ST_BH * ST_BW + 31) & ~31)   // floats per staged level: TMA destinations are 128-byte aligned
+#define ST_ROWS 8              // rows marched by one thread
+#define ST_THREADS ((ST_TW / 2) * (ST_TH / ST_ROWS))   // 128
+#ifndef ST_STAGES
+#define ST_STAGES 1            // 1: one tile per CTA, four CTAs per SM hide the load; 2: persistent CTAs, double buffer
+#endif
+
+struct ScanTmaArgs {
+  int n_oct, spo, ndog, count_low, total_tiles;
+  int tile_start[SIFT_MAX_OCTAVES + 1];
+  int tiles_x[SIFT_MAX_OCTAVES];
+  int w[SIFT_MAX_OCTAVES], h[SIFT_MAX_OCTAVES];
+  float thr_f;                   // smallest float >= the double threshold (see launch_scan_tma)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct ScanTile { int o, x_tile, y_tile, w, h; };
+
+__device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t)
+{
+  // static indices only: a dynamically indexed kernel-parameter array is copied to local memory
+  ScanTile T;
+  int o = 0, t0 = 0, ntx = A.tiles_x[0], w = A.w[0], h = A.h[0];
+#pragma unroll
+  for (int i = 1; i < SIFT_MAX_OCTAVES; i++)
+    if (i < A.n_oct && t >= A.tile_start[i]) { o = i; t0 = A.tile_start[i]; ntx = A.tiles_x[i]; w = A.w[i]; h = A.h[i]; }
+  const int tt = t - t0;
+  const int ty = tt / ntx, tx = tt - ty * ntx;
+  T.o = o; T.x_tile = tx * ST_TW; T.y_tile = ty * ST_TH; T.w = w; T.h = h;
+  return T;
+}
+
+// Persistent CTAs, two tile buffers: while the CTA tests tile k out of one buffer the TMA unit fills the
+// other with tile k + 1, so the HBM latency of a tile is hidden behind the arithmetic of the previous one.
+template <int ND>   // DoG levels per octave (spo + 2)
+__global__ void __launch_bounds__(ST_THREADS, ST_STAGES == 1 ? 4 : 2)
+scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_candidate *__restrict__ cand,
+                int cand_cap, sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
+{
+  extern __shared__ __align__(128) float tiles[];       // [ST_STAGES][ND][ST_PLANE], each level [ST_BH][ST_BW]
+  __shared__ __align__(8) unsigned long long bar[ST_STAGES];
+  const int tid = threadIdx.x;
+
+  auto issue = [&](int t, int stage) {                  // one thread: arm the barrier, one TMA tile load per level
+    const ScanTile T = scan_decode_tile(A, t);
+    const unsigned bytes = ND * ST_BH * ST_BW * sizeof(float);
+    const unsigned b = smem_u32(&bar[stage]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+#pragma unroll
+    for (int p = 0; p < ND; p++) {
+      const CUtensorMap *m = maps + T.o * ND + p;
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+          ::"r"(smem_u32(tiles + (stage * ND + p) * ST_PLANE)), "l"(m), "r"(b), "r"(T.x_tile - 4), "r"(T.y_tile - 1)
+          : "memory");
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < ST_STAGES; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < A.total_tiles) issue(blockIdx.x, 0);
+
+  // thread -> 2 pixels (columns 2*cx, 2*cx+1 of the tile) x rows [8*ry, 8*ry + 8)
+  const int cx = tid & (ST_TW / 2 - 1), ry = tid / (ST_TW / 2);
+  const int xl = 2 * cx;                                  // tile-local column of pixel 0
+  const int row_first = ry * ST_ROWS;                     // tile-local row of the first output row
+
+  int k = 0;
+  for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, k++) {
+    const int stage = ST_STAGES > 1 ? (k & 1) : 0;
+    if (ST_STAGES > 1 && tid == 0 && t + (int)gridDim.x < A.total_tiles) issue(t + gridDim.x, stage ^ 1);   // that buffer was released by the
+                                                                                             // __syncthreads of iteration k-1
+    {
+      const unsigned parity = ST_STAGES > 1 ? ((k >> 1) & 1) : (k & 1);
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(&bar[stage])), "r"(parity) : "memory");
+      }
+    }
+    const ScanTile T = scan_decode_tile(A, t);
+    const float *tile = tiles + stage * ND * ST_PLANE;
+    const int x0 = T.x_tile + xl;
+    const bool col_ok[2] = { x0 >= 1 && x0 < T.w - 1, x0 + 1 >= 1 && x0 + 1 < T.w - 1 };      // sift.js:222
+    // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3): horizontal
+    // 3-max / 3-min, and for the centre levels the row's own values and its left/right-only max / min
+    float hmax[3][ND][2], hmin[3][ND][2], cen[3][ND][2], lrmax[3][ND][2], lrmin[3][ND][2];
+#pragma unroll 1
+    for (int r3 = 0; r3 < ST_ROWS + 2; r3 += 3) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int r = r3 + j;
+        if (r >= ST_ROWS + 2) break;
+        constexpr int dummy = 0; (void)dummy;
+        const int cs = j, bs = (j + 2) % 3, as = (j + 1) % 3;          // slots of rows r, r-1, r-2
+        // box row of tile-local row (row_first - 1 + r) is (row_first + r): the box starts one row above the tile
+#pragma unroll
+        for (int p = 0; p < ND; p++) {
+          const float *rowp = tile + p * ST_PLANE + (row_first + r) * ST_BW + 4 + xl;
+          const float2 v = *reinterpret_cast<const float2 *>(rowp);
+          const float L = rowp[-1], Rr = rowp[2];
+          const float mx = fmaxf(v.x, v.y), mn = fminf(v.x, v.y);
+          hmax[cs][p][0] = fmaxf(L, mx); hmax[cs][p][1] = fmaxf(mx, Rr);
+          hmin[cs][p][0] = fminf(L, mn); hmin[cs][p][1] = fminf(mn, Rr);
+          if (p >= 1 && p < ND - 1) {
+            cen[cs][p][0] = v.x; cen[cs][p][1] = v.y;
+            lrmax[cs][p][0] = fmaxf(L, v.y); lrmax[cs][p][1] = fmaxf(v.x, Rr);
+            lrmin[cs][p][0] = fminf(L, v.y); lrmin[cs][p][1] = fminf(v.x, Rr);
+          }
+        }
+        if (r >= 2) {
+          const int y = T.y_tile + row_first + r - 2;        // the middle row (slots as, bs, cs = rows y-1, y, y+1)
+          const bool row_ok = y >= 1 && y < T.h - 1;         // sift.js:221
+          float m9[ND][2], n9[ND][2];                        // 3x3 max / min per level (centre included)
+#pragma unroll
+          for (int p = 0; p < ND; p++)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              m9[p][i] = fmaxf(fmaxf(hmax[as][p][i], hmax[bs][p][i]), hmax[cs][p][i]);
+              n9[p][i] = fminf(fminf(hmin[as][p][i], hmin[bs][p][i]), hmin[cs][p][i]);
+            }
+          unsigned hits = 0;                                 // bit (s-1)*2 + i: candidate; bit 16 + ...: low contrast
+#pragma unroll
+          for (int s = 1; s < ND - 1; s++) {                 // background.js:377
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const float c = cen[bs][s][i];
+              const float ring_max = fmaxf(fmaxf(hmax[as][s][i], hmax[cs][s][i]), lrmax[bs][s][i]);
+              const float ring_min = fminf(fminf(hmin[as][s][i], hmin[cs][s][i]), lrmin[bs][s][i]);
+              const float nmax = fmaxf(fmaxf(m9[s - 1][i], m9[s + 1][i]), ring_max);
+              const float nmin = fminf(fminf(n9[s - 1][i], n9[s + 1][i]), ring_min);
+              const bool ext = (c > nmax || c < nmin) && row_ok && col_ok[i];           // sift.js:261, 266
+              const bool strong = fabsf(c) >= A.thr_f;                                  // sift.js:294 (see launch_scan_tma)
+              hits |= (ext && strong) ? 1u << ((s - 1) * 2 + i) : 0u;
+              hits |= (ext && !strong) ? 1u << (16 + (s - 1) * 2 + i) : 0u;
+            }
+          }
+          if (!A.count_low) hits &= 0xffffu;
+          if (__any_sync(0xffffffffu, hits != 0)) {          // rare: ~3e-4 of the voxels
+            for (int s = 1; s < ND - 1; s++)
+              for (int i = 0; i < 2; i++) {
+                float c = 0.f;
+#pragma unroll
+                for (int ss = 1; ss < ND - 1; ss++)
+#pragma unroll
+                  for (int ii = 0; ii < 2; ii++) if (ss == s && ii == i) c = cen[bs][ss][ii];
+                sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = y; rec.value = c; rec.reserved0 = 0;
+                int slot = warp_append((hits >> ((s - 1) * 2 + i)) & 1u, &ctr->n_cand);
+                if (slot >= 0 && slot < cand_cap) cand[slot] = rec;
+                if (A.count_low) {
+                  slot = warp_append((hits >> (16 + (s - 1) * 2 + i)) & 1u, &ctr->n_low);
+                  if (low && slot >= 0 && slot < low_cap) low[slot] = rec;
+                }
+              }
+          }
+        }
+      }
+    }
+    __syncthreads();                                        // every thread is done with this buffer: it may be refilled
+    if (ST_STAGES == 1 && tid == 0 && t + (int)gridDim.x < A.total_tiles) issue(t + gridDim.x, 0);
+  }
+}
+
+// Host: one CUtensorMap per (octave, DoG level).  The driver entry point is fetched through the runtime
+// (no link-time dependency on libcuda).  Returns 0 when TMA descriptors cannot be built.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+size_t scan_tma_map_bytes(int n_oct, int ndog) { return (size_t)n_oct * ndog * sizeof(CUtensorMap); }
+
+bool scan_tma_supported(int ndog) { return ndog >= 3 && ndog <= 6; }
+
+int scan_tma_build_maps(const OctaveDev *octs, int n_oct, int ndog, void *h_maps)
+{
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+      return 0;
+    encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap *maps = (CUtensorMap *)h_maps;
+  for (int o = 0; o < n_oct; o++)
+    for (int p = 0; p < ndog; p++) {
+      const cuuint64_t gdim[2] = { (cuuint64_t)octs[o].w, (cuuint64_t)octs[o].h };
+      const cuuint64_t gstride[1] = { (cuuint64_t)octs[o].pitch * sizeof(float) };
+      const cuuint32_t box[2] = { ST_BW, ST_BH };
+      const cuuint32_t estride[2] = { 1, 1 };
+      if (encode(&maps[o * ndog + p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)octs[o].dog[p], gdim, gstride, box, estride,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    }
+  return 1;
+}
+
+void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_maps, int n_oct, int spo,
+                     double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
+                     int low_cap, Counters *ctr)
+{
+  ScanTmaArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_oct = n_oct; A.spo = spo; A.ndog = spo + 2; A.count_low = count_low;
+  // sift.js:294 compares abs(value) >= threshold in double.  The DoG values are floats, and for a float a,
+  // (double)a >= T  <=>  a >= (the smallest float that is >= T): one float compare, exactly equivalent.
+  float tf = (float)pix_threshold;
+  if ((double)tf < pix_threshold) tf = nextafterf(tf, INFINITY);
+  A.thr_f = tf;
+  int total = 0;
+  for (int o = 0; o < n_oct; o++) {
+    A.tile_start[o] = total;
+    A.tiles_x[o] = (h_octs[o].w + ST_TW - 1) / ST_TW;
+    A.w[o] = h_octs[o].w; A.h[o] = h_octs[o].h;
+    if (h_octs[o].w >= 3 && h_octs[o].h >= 3) total += A.tiles_x[o] * ((h_octs[o].h + ST_TH - 1) / ST_TH);
+  }
+  A.tile_start[n_oct] = total;
+  A.total_tiles = total;
+  if (total == 0) return;
+  const int nd = spo + 2;
+  const size_t smem = (size_t)ST_STAGES * nd * ST_PLANE * sizeof(float);
+  const int grid = (ST_STAGES == 1 || total < 148 * 2) ? total : 148 * 2;      // persistent: two CTAs per SM
+  const CUtensorMap *maps = (const CUtensorMap *)d_maps;
+#define LAUNCH_ND(N)                                                                                         \
+  case N:                                                                                                    \
+    cudaFuncSetAttribute(scan_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    scan_tma_kernel<N><<<grid, ST_THREADS, smem, st>>>(maps, A, cand, cand_cap, low, low_cap, ctr);         \
+    break;
+  switch (nd) { LAUNCH_ND(3) LAUNCH_ND(4) LAUNCH_ND(5) LAUNCH_ND(6) }
+#undef LAUNCH_ND
 }
 
 // ---- step function: SIFT_findExtremas on three Matrix2D (fp64) images ----------
