@@ -1,0 +1,83 @@
+//@ts-nocheck
+'use strict';
+// Drop-in for the four stage functions behind the reference's worker message switch (background.js:14-50),
+// as plain exported functions with the request field names of src/worker.js:40-98 and the reply schemas
+// of background.js:233-236, 350-353, 446-449, 681-684 -- plus one fused detect() that keeps the pyramid
+// on the GPU.  The postMessage transport is gone; addon/worker-adapter.js puts it back for callers that
+// still speak WorkerMessageTypes.
+import { native, context, toPixels, toMatrix2D, decodeKeypoints, decodeCandidates, encodeCandidates, LEVEL } from './native.js';
+
+const paramsOf = (o = {}) => ({
+  numberOfOctaves: o.numberOfOctaves ?? 5, scalesPerOctave: o.scalesPerOctave ?? 3,         // worker.js:33-34
+  minBlurLevel: o.minBlurLevel ?? 0.8, assumedBlur: o.assumedBlur ?? 0.5,                   // worker.js:35-36
+  contrastThreshold: o.contrastThreshold ?? 0.015, preFilterFactor: o.preFilterFactor ?? 0.8,
+  edgeRatio: o.edgeRatio ?? 10, maxIterations: o.maxIterations ?? 5, offsetBound: o.offsetBound ?? 0.6,
+  minInterpixelDistance: o.minInterpixelDistance ?? 0.5,
+});
+
+function readLevels(kind, matrices) {
+  const info = native.pyramidInfo(context());
+  const out = [];
+  for (let o = 0; o < info.octaves; o++) {
+    const levels = [];
+    for (let s = 0; s < info.levels - (kind === LEVEL.DOG ? 1 : 0); s++) {
+      const l = native.getLevel(context(), kind, o, s);
+      levels.push({ blurLevel: l.blurLevel,
+                    image: matrices ? toMatrix2D(l.data, l.height, l.width) : { data: l.data, width: l.width, height: l.height } });
+    }
+    out.push(levels);
+  }
+  return out;
+}
+
+/** background.js:71 -- request {inputImage, numberOfOctaves, scalesPerOctave, minBlurLevel, assumedBlur, chunkSize}. */
+export function computeGaussianScaleSpace(request, { matrices = Array.isArray(request.inputImage) } = {}) {
+  const px = toPixels(request.inputImage);
+  native.buildScaleSpace(context(), px.data, px.width, px.height, px.dtype, paramsOf(request));
+  return readLevels(LEVEL.GAUSSIAN, matrices);
+}
+
+/** background.js:258 -- the DoG of the pyramid the context holds (formed by the blur kernels). */
+export function computeDifferenceOfGaussians(_scaleSpace, { matrices = true } = {}) {
+  return readLevels(LEVEL.DOG, matrices);
+}
+
+/** background.js:359 -- request {differenceOfGaussians, octaveBaseImages (unused), scalesPerOctave}. */
+export function findCandidateKeypoints(request) {
+  const r = native.findCandidates(context(), null, false);
+  const info = native.pyramidInfo(context());
+  const reply = [];
+  for (let o = 0; o < info.octaves; o++) {
+    reply.push([]);
+    for (let s = 1; s < info.levels - 2; s++) reply[o].push({ scaleLevel: s, localExtremas: [] });
+  }
+  for (const c of decodeCandidates(r.records, r.count)) reply[c.octave][c.scaleLevel - 1].localExtremas.push({ x: c.x, y: c.y, value: c.value });
+  return reply;
+}
+
+/** background.js:455 -- request {differenceOfGaussians, scalesPerOctave, numberOfOctaves, candidateKeypoints,
+ *  minBlurLevel, minInterpixelDistance}. */
+export function refineCandidateKeypoints(request) {
+  const flat = [];
+  for (let octave = 0; octave < request.numberOfOctaves; octave++)                     // background.js:468-471
+    for (let scale_i = 0; scale_i < request.scalesPerOctave; scale_i++) {
+      const entry = request.candidateKeypoints[octave][scale_i];
+      for (const e of entry.localExtremas) flat.push({ octave, scaleLevel: entry.scaleLevel, x: e.x, y: e.y, value: e.value });
+    }
+  const r = native.refine(context(), paramsOf(request), encodeCandidates(flat), flat.length);
+  return decodeKeypoints(r.records, r.count);
+}
+
+/** The whole chain main.js:111 -> 239 -> 274 -> 325 in one device-resident call. */
+export function detect(image, options = {}) {
+  const px = toPixels(image);
+  const r = native.detect(context(), px.data, px.width, px.height, px.dtype, paramsOf(options));
+  return { keypoints: decodeKeypoints(r.records, r.count), stats: r.stats };
+}
+
+/** n equally sized frames packed back to back in one typed array; frames overlap on the GPU. */
+export function detectBatch(frames, width, height, nImages, dtype, options = {}, capacity = nImages * 32768) {
+  const r = native.detectBatch(context(), frames, width, height, nImages, dtype, paramsOf(options), capacity);
+  const all = decodeKeypoints(r.records, r.offsets[nImages]);
+  return { keypoints: Array.from({ length: nImages }, (_, i) => all.slice(r.offsets[i], r.offsets[i + 1])), stats: r.stats };
+}

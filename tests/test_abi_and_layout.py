@@ -104,3 +104,36 @@ def test_fixture_generator_is_reproducible():
     assert a.dtype == np.uint8 and a.shape == (48, 64)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     assert int(a.astype(np.int64).sum()) == int(np.frombuffer(a.tobytes(), np.uint8).astype(np.int64).sum())
+
+
+def test_napi_addon_builds_and_binds_only_the_c_abi():
+    """addon/sift_b200.node: exports the N-API registration symbol, imports only napi_* (resolved from the node
+    executable at load time) and sift_* symbols that include/sift_b200.h declares."""
+    import subprocess
+    addon = os.path.join(ROOT, "addon")
+    subprocess.check_call(["make", "-C", addon], stdout=subprocess.DEVNULL)
+    out = subprocess.run(["nm", "-D", os.path.join(addon, "sift_b200.node")], capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    undefined = {ln.split()[-1] for ln in out.splitlines() if " U " in ln}
+    assert "napi_register_module_v1" in defined
+    used = {s for s in undefined if s.startswith("sift_")}
+    assert used and used <= set(_declared_symbols())
+    assert len({s for s in undefined if s.startswith("napi_")}) >= 15
+    foreign = {s.split("@")[0] for s in undefined if not s.startswith(("sift_", "napi_", "_"))}
+    assert foreign <= {"memset", "memcpy", "free", "malloc", "strlen", "snprintf"}, foreign
+
+
+def test_js_drop_in_modules_keep_the_reference_export_names():
+    """addon/sift.js and addon/background.js export the names src/sift.js and background.js define."""
+    sift_js = open(os.path.join(ROOT, "addon", "sift.js")).read()
+    for name in ("SIFT_blurMatrix2DChunk", "SIFT_subtractMatrix2DChunk", "SIFT_findExtremas",
+                 "SIFT_generateGradientVector", "SIFT_generateHessianMatrix"):
+        assert re.search(rf"export function {name}\(", sift_js), name
+    bg_js = open(os.path.join(ROOT, "addon", "background.js")).read()
+    for name in ("computeGaussianScaleSpace", "computeDifferenceOfGaussians", "findCandidateKeypoints",
+                 "refineCandidateKeypoints", "detect"):
+        assert re.search(rf"export function {name}\(", bg_js), name
+    # the JS glue parses under the test interpreter's tokenizer (syntax smoke; it cannot run without Node)
+    from oracle import jsmini
+    for f in ("sift.js", "background.js", "native.js"):
+        assert len(jsmini.tokenize(open(os.path.join(ROOT, "addon", f)).read())) > 100
