@@ -129,6 +129,7 @@ static napi_value stats_object(napi_env env, const sift_stats *s)
   set_num(env, o, "rejLeftRows", s->rejLeftRows); set_num(env, o, "rejLeftCols", s->rejLeftCols);
   set_num(env, o, "rejNoConvergence", s->rejNoConvergence); set_num(env, o, "rejSingular", s->rejSingular);
   set_num(env, o, "msDevice", s->msDevice); set_num(env, o, "kernelLaunches", s->kernelLaunches);
+  set_num(env, o, "leftStrip", s->leftStrip);
   return o;
 }
 

@@ -135,6 +135,8 @@ typedef struct sift_stats {
   int32_t rejSingular;      /* abs(det) < Number.EPSILON (matrix2d.js:482): the reference throws, we discard */
   float msDevice;           /* CUDA-event time of the device work of this call */
   int32_t kernelLaunches;   /* kernels launched by this call */
+  int32_t leftStrip;        /* mosaic strips only: walks (counted in rejLeftRows) that left the strip's halo, not the
+                             * image -- 0 means the strip result equals the whole-image result */
 } sift_stats;
 
 typedef struct sift_ctx sift_ctx;
@@ -221,6 +223,38 @@ SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, floa
  * when refineCandidateKeypoints / findCandidateKeypoints receive foreign matrices). */
 SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, const sift_params *params);
 SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, const float *src);
+
+/* ---------------------------------------------------------- mosaic strips */
+/* A mosaic too large for one GPU is cut into horizontal strips of the octave-0 grid, one per GPU
+ * (SURVEY.md 8e).  Every level of an octave is blurred from that octave's base image only
+ * (background.js:185-190), so the only cross-strip dependency is the base (seed) image's halo: per octave a
+ * strip needs `halo` = max kernel radius + margin rows of its neighbours' seed.  The engine computes one
+ * octave at a time; between octaves the caller exchanges seed rows (NCCL / P2P) directly in device memory.
+ * All row numbers below are rows of the GLOBAL octave grids. */
+typedef struct sift_strip_layout {
+  int32_t octaves;
+  int32_t width[12], height[12];   /* global octave sizes */
+  int32_t own0[12], own1[12];      /* rows this strip owns (its keypoints come from these) */
+  int32_t top[12], bottom[12];     /* rows this strip holds: owned rows + halos, clipped to the image */
+  int32_t halo[12];                /* rows needed beyond the owned range: max radius + margin, even */
+} sift_strip_layout;
+/* Host-only arithmetic (no device needed).  row0/row1: owned octave-0 rows, multiples of 2^(octaves-1)
+ * (row1 may also be the image bottom, 2 * full_height).  margin: rows kept beyond the blur halo for the
+ * scan and for refinement walks. */
+SIFT_API int sift_strip_layout_compute(const sift_params *params, int full_width, int full_height, int row0,
+                                       int row1, int margin, sift_strip_layout *out);
+/* Lay the strip's pyramid out on the device (lane 0) and upload the source rows
+ * [top[0]/2, (bottom[0]+1)/2) of the full image (`rows` points at the first of them). */
+SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const sift_strip_layout *layout,
+                              const void *rows, int dtype, size_t pitch_bytes);
+/* Device pointer to the strip's fp64 seed image of octave >= 1: dense, width[octave] doubles per row, first row
+ * = global row top[octave].  After sift_strip_octave(octave - 1) the OWNED rows are final; the caller fills
+ * the halo rows from the neighbouring strips, then calls sift_strip_octave(octave). */
+SIFT_API int sift_strip_seed(sift_ctx *ctx, int octave, double **d_seed);
+/* Blur + DoG of one octave (0, 1, 2 ... in order) and the owned rows of the next octave's seed.  Synchronous. */
+SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave);
+/* Scan + refine over all octaves: keypoints of the owned rows, global coordinates, reference order. */
+SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *n_out, sift_stats *stats);
 
 /* ----------------------------------------------------- fine step functions */
 /* src/sift.js:72  float64 in / out like Matrix2D; half-open chunk; writes only the chunk of output. */

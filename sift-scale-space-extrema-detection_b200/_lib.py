@@ -50,11 +50,19 @@ class Keypoint(C.Structure):
                 ("candScale", C.c_int32), ("candX", C.c_int32), ("candY", C.c_int32), ("iterations", C.c_int32)]
 
 
+class StripLayout(C.Structure):
+    """sift_strip_layout: rows of the global octave grids a mosaic strip owns / holds (include/sift_b200.h)."""
+    _fields_ = [("octaves", C.c_int32), ("width", C.c_int32 * 12), ("height", C.c_int32 * 12),
+                ("own0", C.c_int32 * 12), ("own1", C.c_int32 * 12), ("top", C.c_int32 * 12),
+                ("bottom", C.c_int32 * 12), ("halo", C.c_int32 * 12)]
+
+
 class Stats(C.Structure):
     _fields_ = [("candidates", C.c_int32), ("lowContrastExtrema", C.c_int32), ("keypoints", C.c_int32),
                 ("rejLowContrast", C.c_int32), ("rejEdge", C.c_int32), ("rejLeftScale", C.c_int32),
                 ("rejLeftRows", C.c_int32), ("rejLeftCols", C.c_int32), ("rejNoConvergence", C.c_int32),
-                ("rejSingular", C.c_int32), ("msDevice", C.c_float), ("kernelLaunches", C.c_int32)]
+                ("rejSingular", C.c_int32), ("msDevice", C.c_float), ("kernelLaunches", C.c_int32),
+                ("leftStrip", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -91,6 +99,12 @@ PROTOTYPES = {
                                      C.c_int, _VP, C.c_int]),
     "sift_detect_batch": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int,
                                     C.POINTER(Params), _VP, C.c_int, _IP, C.POINTER(Stats)]),
+    "sift_strip_layout_compute": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(StripLayout)]),
+    "sift_strip_begin": (C.c_int, [_VP, C.POINTER(Params), C.POINTER(StripLayout), _VP, C.c_int, C.c_size_t]),
+    "sift_strip_seed": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
+    "sift_strip_octave": (C.c_int, [_VP, C.c_int]),
+    "sift_strip_finish": (C.c_int, [_VP, _VP, C.c_int, _IP, C.POINTER(Stats)]),
     "sift_build_scale_space": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Params)]),
     "sift_build_dog": (C.c_int, [_VP]),
     "sift_find_candidates": (C.c_int, [_VP, C.POINTER(Params), _VP, C.c_int, _IP, _VP, C.c_int, _IP]),

@@ -164,8 +164,6 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
   const bool col_ok = x < w;
   const bool rows_full = y_first + 16 <= h;
   const bool seed_lane = A.has_next && (X & 1) == 0 && col_ok;
-  const size_t seed_first = (size_t)(b_tile + 8 * rg) * A.next.w + (x >> 1);
-  const size_t g0_first = (size_t)(b_tile + 8 * rg) * A.next.pitch + (x >> 1);
 
   double prev[16];
 #pragma unroll
@@ -224,9 +222,10 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
       if (s == A.spo && seed_lane) {                 // in[2a][2b] (matrix2d.js:129): even rows (phase 0), even columns
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          if (y_first + 2 * k < h) {
-            A.next.seed64[seed_first + (size_t)k * A.next.w] = a0[k];
-            A.next.gauss[0][g0_first + (size_t)k * A.next.pitch] = (float)a0[k];
+          const int nr = b_tile + 8 * rg + k + A.oct.seed_off;      // row of the next octave (strip-local)
+          if (y_first + 2 * k < h && nr >= 0 && nr < A.next.h) {
+            A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = a0[k];
+            A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)a0[k];
           }
         }
       }

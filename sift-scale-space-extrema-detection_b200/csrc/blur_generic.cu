@@ -221,9 +221,10 @@ __device__ __forceinline__ void vblur_store(const VBlurArgs &A, int s, int x, in
     const size_t o = (size_t)y * pitch + x;
     if (A.keep_gauss) A.oct.gauss[s][o] = (float)acc[k];
     if (s > 0) A.oct.dog[s - 1][o] = (float)(prev[k] - acc[k]);
-    if (A.has_next && s == A.spo && ((y | x) & 1) == 0) {                      // matrix2d.js:129 in[2a][2b]
-      A.next.seed64[(size_t)(y >> 1) * A.next.w + (x >> 1)] = acc[k];
-      A.next.gauss[0][(size_t)(y >> 1) * A.next.pitch + (x >> 1)] = (float)acc[k];
+    const int nr = (y >> 1) + A.oct.seed_off;                                  // row of the next octave (strip-local)
+    if (A.has_next && s == A.spo && ((y | x) & 1) == 0 && nr >= 0 && nr < A.next.h) {   // matrix2d.js:129 in[2a][2b]
+      A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = acc[k];
+      A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)acc[k];
     }
   }
 }

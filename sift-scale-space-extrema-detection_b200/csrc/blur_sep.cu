@@ -244,13 +244,12 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
           }
         }
         if (A.has_next && s == A.spo && (a & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
-          double *sp = A.next.seed64 + (size_t)(b0 >> 1) * A.next.w + (a >> 1);
-          float *g0 = A.next.gauss[0] + (size_t)(b0 >> 1) * A.next.pitch + (a >> 1);
 #pragma unroll
           for (int k = 0; k < NO; k += 2) {
-            if (b0 + k < A.nb) {
-              sp[(k >> 1) * A.next.w] = acc[k];
-              g0[(k >> 1) * A.next.pitch] = (float)acc[k];
+            const int nr = ((b0 + k) >> 1) + A.oct.seed_off;     // row of the next octave (strip-local)
+            if (b0 + k < A.nb && nr >= 0 && nr < A.next.h) {
+              A.next.seed64[(size_t)nr * A.next.w + (a >> 1)] = acc[k];
+              A.next.gauss[0][(size_t)nr * A.next.pitch + (a >> 1)] = (float)acc[k];
             }
           }
         }

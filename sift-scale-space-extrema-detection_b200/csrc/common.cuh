@@ -20,6 +20,11 @@ struct OctaveDev {
   float *gauss[SIFT_MAX_LEVELS];
   float *dog[SIFT_MAX_LEVELS];
   double *seed64;      // h * w dense, octaves >= 1 (nullptr for octave 0)
+  // ---- mosaic strips: this octave image is rows [y_top, y_top + h) of a taller global
+  // octave of gh rows; rows [own0, own1) (local) are owned by this strip, the rest is halo.  A whole image
+  // is the strip y_top = 0, gh = h, own = [0, h), seed_off = 0.
+  int y_top, gh, own0, own1;
+  int seed_off;        // local row (y >> 1) + seed_off of the next octave receives this octave's even row y
 };
 
 // Per-level blur description (host computed, background.js:156-177 + sift.js:38).
@@ -36,7 +41,8 @@ struct Counters {
   int n_low;           // low-contrast extrema (when counted)
   int n_kp;            // keypoints appended
   int outcomes[8];     // refine outcomes, index = REFINE_* below
-  int pad[5];
+  int n_left_strip;    // refinement walks that left the strip's halo (not the image): resolved by a wider margin
+  int pad[4];
 };
 
 enum {

@@ -67,6 +67,11 @@ struct sift_ctx {
   int in_w = 0, in_h = 0;
   int n_oct = 0, nlev = 0;
   int ow[SIFT_MAX_OCTAVES], oh[SIFT_MAX_OCTAVES];
+  bool is_strip = false;                // the octave images are row strips of a mosaic (sift_strip_*)
+  sift_strip_layout strip;
+  int strip_next_octave = 0;            // octave sift_strip_octave expects next
+  int strip_dtype = 0;
+  size_t strip_pitch = 0;
   LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   double dog_blur[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   std::vector<double> h_weights;   // [0,256): u8 -> v/255.0 table, then per-level taps
@@ -179,8 +184,84 @@ static bool same_params(const sift_params &a, const sift_params &b)
          a.minBlurLevel == b.minBlurLevel && a.assumedBlur == b.assumedBlur;
 }
 
+// background.js:89-177: blur levels, offset sigmas and radii of every level (host only, no device needed).
+// Returns 0 or the (octave * 100 + level) of the level whose offset sigma is not realisable.
+static int level_schedule(const sift_params *p, LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS])
+{
+  const int spo = p->scalesPerOctave, nlev = spo + 3, n_oct = p->numberOfOctaves;
+  const double k = std::pow(2.0, 1.0 / spo);                                   // background.js:100
+  double base_blur = p->minBlurLevel;                                          // background.js:89
+  for (int o = 0; o < n_oct; o++)
+    for (int s = 0; s < nlev; s++) {
+      LevelPlan &lp = plans[o][s];
+      lp.woff = -1;
+      if (o > 0 && s == 0) {
+        base_blur = plans[o - 1][spo].blurLevel;                               // background.js:122
+        lp.blurLevel = base_blur; lp.offsetSigma = 0; lp.radius = 0;
+        continue;
+      }
+      const double current_k = std::pow(k, (double)s);                         // :157
+      const double target = base_blur * current_k;                             // :173
+      const double base_sigma = (o == 0) ? p->assumedBlur : base_blur;         // :174-176
+      const double off = std::sqrt((target * target) - (base_sigma * base_sigma));   // :177
+      lp.blurLevel = target; lp.offsetSigma = off;
+      if (!(off > 0) || !std::isfinite(off)) return o * 100 + s + 1;
+      lp.radius = (int)js_round(3 * off);                                      // sift.js:38
+    }
+  return 0;
+}
+
+static int check_params(sift_ctx *ctx, const sift_params *p)
+{
+  if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "params is NULL");
+  if (p->numberOfOctaves < 1 || p->numberOfOctaves > SIFT_MAX_OCTAVES)
+    return fail(ctx, SIFT_ERR_UNSUPPORTED, "numberOfOctaves %d outside 1..%d", p->numberOfOctaves, SIFT_MAX_OCTAVES);
+  if (p->scalesPerOctave < 1 || p->scalesPerOctave + 3 > SIFT_MAX_LEVELS)
+    return fail(ctx, SIFT_ERR_UNSUPPORTED, "scalesPerOctave %d outside 1..%d", p->scalesPerOctave, SIFT_MAX_LEVELS - 3);
+  return SIFT_OK;
+}
+
+// Row strips of a mosaic.  All rows are rows of the GLOBAL octave grids.
+static int strip_layout(sift_ctx *ctx, const sift_params *p, int full_w, int full_h, int row0, int row1, int margin,
+                        sift_strip_layout *out)
+{
+  int rc;
+  if ((rc = check_params(ctx, p))) return rc;
+  if (!out || full_w < 1 || full_h < 1 || margin < 1) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad mosaic size / margin");
+  const int n_oct = p->numberOfOctaves, nlev = p->scalesPerOctave + 3;
+  const int H0 = 2 * full_h, align = 1 << (n_oct - 1);
+  if (row0 < 0 || row1 <= row0 || row1 > H0 || (row0 % align) != 0 || (row1 != H0 && (row1 % align) != 0))
+    return fail(ctx, SIFT_ERR_BAD_ARGS, "strip rows [%d, %d) must lie in [0, %d) on multiples of %d (2^(octaves-1))",
+                row0, row1, H0, align);
+  LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
+  const int bad = level_schedule(p, plans);
+  if (bad) return fail(ctx, SIFT_ERR_BAD_ARGS, "sigma schedule not realisable at octave %d level %d", (bad - 1) / 100, (bad - 1) % 100);
+  memset(out, 0, sizeof *out);
+  out->octaves = n_oct;
+  int W = 2 * full_w, H = H0;
+  for (int o = 0; o < n_oct; o++) {
+    int rmax = 0;
+    for (int s = 0; s < nlev; s++) rmax = std::max(rmax, plans[o][s].radius);
+    const int halo = (rmax + margin + 1) & ~1;
+    const int own0 = row0 >> o, own1 = (row1 == H0) ? H : (row1 >> o);
+    out->width[o] = W; out->height[o] = H;
+    out->own0[o] = own0; out->own1[o] = own1;
+    out->top[o] = std::max(0, own0 - halo) & ~1;
+    out->bottom[o] = std::min(H, own1 + halo);
+    out->halo[o] = halo;
+    if (own1 <= own0) return fail(ctx, SIFT_ERR_UNSUPPORTED, "strip owns no row of octave %d", o);
+    // the halo comes from the direct neighbours only: a strip must be at least one halo tall in every octave
+    if ((row0 > 0 || row1 < H0) && own1 - own0 < halo)
+      return fail(ctx, SIFT_ERR_UNSUPPORTED, "strip is %d rows tall in octave %d but the halo is %d: gather this octave instead",
+                  own1 - own0, o, halo);
+    W = (W + 1) / 2; H = (H + 1) / 2;
+  }
+  return SIFT_OK;
+}
+
 // background.js:84-177: sizes, blur levels, offset sigmas, radii; allocates the pyramid.
-static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
+// background.js:84-177: sizes, blur levels, offset sigmas, radii; allocates the pyramid.
+static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p, const sift_strip_layout *strip = nullptr)
 {
   if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "params is NULL");
   if (w < 1 || h < 1) return fail(ctx, SIFT_ERR_BAD_ARGS, "image size %dx%d", w, h);
@@ -190,44 +271,38 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
     return fail(ctx, SIFT_ERR_UNSUPPORTED, "scalesPerOctave %d outside 1..%d", p->scalesPerOctave, SIFT_MAX_LEVELS - 3);
   if ((int64_t)w * 2 > (1 << 30) || (int64_t)h * 2 > (1 << 30))
     return fail(ctx, SIFT_ERR_UNSUPPORTED, "image too large");
-  if (ctx->plan_valid && ctx->in_w == w && ctx->in_h == h && same_params(ctx->prm, *p)) {
+  const bool same_strip = (!strip && !ctx->is_strip) || (strip && ctx->is_strip && memcmp(strip, &ctx->strip, sizeof *strip) == 0);
+  if (ctx->plan_valid && ctx->in_w == w && ctx->in_h == h && same_params(ctx->prm, *p) && same_strip) {
     ctx->prm = *p;   // thresholds may differ; they do not affect the plan
     return SIFT_OK;
   }
   ctx->plan_valid = false;
   ctx->pyramid_built = false;
   const int spo = p->scalesPerOctave, nlev = spo + 3, n_oct = p->numberOfOctaves;
-  const double k = std::pow(2.0, 1.0 / spo);                                   // background.js:100
+  (void)spo;
 
   // sizes: octave 0 is the 2x nearest-neighbour upsample (background.js:84), then ceil halves (matrix2d.js:119)
   int ow[SIFT_MAX_OCTAVES], oh[SIFT_MAX_OCTAVES];
   ow[0] = 2 * w; oh[0] = 2 * h;
   for (int o = 1; o < n_oct; o++) { ow[o] = (ow[o - 1] + 1) / 2; oh[o] = (oh[o - 1] + 1) / 2; }
 
+  if (strip) {                          // octave images are the strip's rows [top, bottom) of the global octaves
+    for (int o = 0; o < n_oct; o++) { ow[o] = strip->width[o]; oh[o] = strip->bottom[o] - strip->top[o]; }
+  }
+  const int bad = level_schedule(p, ctx->plans);
+  if (bad)
+    return fail(ctx, SIFT_ERR_BAD_ARGS, "sigma schedule not realisable at octave %d level %d (target %g)", (bad - 1) / 100,
+                (bad - 1) % 100, ctx->plans[(bad - 1) / 100][(bad - 1) % 100].blurLevel);
   ctx->h_weights.clear();
   for (int v = 0; v < 256; v++) ctx->h_weights.push_back((double)v / 255.0);   // image-utils.js:114
-  double base_blur = p->minBlurLevel;                                          // background.js:89
   for (int o = 0; o < n_oct; o++) {
     for (int s = 0; s < nlev; s++) {
       LevelPlan &lp = ctx->plans[o][s];
-      if (o > 0 && s == 0) {
-        base_blur = ctx->plans[o - 1][spo].blurLevel;                          // background.js:122
-        lp.blurLevel = base_blur; lp.offsetSigma = 0; lp.radius = 0; lp.woff = -1;
-        continue;
-      }
-      const double current_k = std::pow(k, (double)s);                         // :157
-      const double target = base_blur * current_k;                             // :173
-      const double base_sigma = (o == 0) ? p->assumedBlur : base_blur;         // :174-176
-      const double off = std::sqrt((target * target) - (base_sigma * base_sigma));   // :177
-      if (!(off > 0) || !std::isfinite(off))
-        return fail(ctx, SIFT_ERR_BAD_ARGS,
-                    "sigma schedule not realisable at octave %d level %d (target %g, base %g)", o, s, target, base_sigma);
-      lp.blurLevel = target; lp.offsetSigma = off;
-      lp.radius = (int)js_round(3 * off);                                      // sift.js:38
+      if (o > 0 && s == 0) continue;
       if (lp.radius > 4096) return fail(ctx, SIFT_ERR_UNSUPPORTED, "kernel radius %d too large", lp.radius);
       lp.woff = (int)ctx->h_weights.size();
       ctx->h_weights.resize(ctx->h_weights.size() + 2 * lp.radius + 1 + SIFT_WPAD, 0.0);
-      gaussian_taps(off, lp.radius, ctx->h_weights.data() + lp.woff);
+      gaussian_taps(lp.offsetSigma, lp.radius, ctx->h_weights.data() + lp.woff);
     }
     for (int s = 1; s < nlev; s++) ctx->dog_blur[o][s - 1] = ctx->plans[o][s - 1].blurLevel;   // background.js:327
   }
@@ -253,6 +328,8 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p)
   }
   CK(cudaMemcpy(ctx->d_weights, ctx->h_weights.data(), wbytes, cudaMemcpyHostToDevice));
   ctx->prm = *p; ctx->in_w = w; ctx->in_h = h; ctx->n_oct = n_oct; ctx->nlev = nlev;
+  ctx->is_strip = strip != nullptr;
+  if (strip) ctx->strip = *strip;
   ctx->plan_id++;
   ctx->plan_valid = true;
   return SIFT_OK;
@@ -287,6 +364,12 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
       OctaveDev &od = ln->octs[o];
       memset(&od, 0, sizeof od);
       od.w = ow[o]; od.h = oh[o]; od.pitch = (ow[o] + 31) & ~31; od.nlev = nlev;
+      od.y_top = 0; od.gh = oh[o]; od.own0 = 0; od.own1 = oh[o]; od.seed_off = 0;
+      if (ctx->is_strip) {
+        const sift_strip_layout &sl = ctx->strip;
+        od.y_top = sl.top[o]; od.gh = sl.height[o]; od.own0 = sl.own0[o] - sl.top[o]; od.own1 = sl.own1[o] - sl.top[o];
+        od.seed_off = (o + 1 < n_oct) ? sl.top[o] / 2 - sl.top[o + 1] : 0;
+      }
       const size_t pe = (size_t)od.h * od.pitch;
       for (int s = 0; s < nlev; s++) { od.gauss[s] = pp; pp += pe; }
       for (int s = 0; s < nlev - 1; s++) { od.dog[s] = pp; pp += pe; }
@@ -343,50 +426,54 @@ static int ensure_plan0(sift_ctx *ctx, int w, int h, const sift_params *p)
 static Counters *dev_counters(sift_ctx *ctx) { return (Counters *)ctx->L->outbuf.p; }
 static sift_keypoint *dev_keypoints(sift_ctx *ctx) { return (sift_keypoint *)((char *)ctx->L->outbuf.p + sizeof(Counters)); }
 
-// Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
-static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
+// Blur + DoG of one octave and the seed of the next, from an image already on the device (octave 0) or from
+// the octave's seed (octaves >= 1).
+static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, size_t pitch_bytes)
 {
   const int spo = ctx->prm.scalesPerOctave;
   cudaStream_t st = ctx->L->stream;
-  for (int o = 0; o < ctx->n_oct; o++) {
-    const OctaveDev &od = ctx->L->octs[o];
-    if (o == 0 && ctx->fused0) {
-      prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
-      launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od,
-                           (ctx->n_oct > 1) ? &ctx->L->octs[1] : nullptr, ctx->d_weights, ctx->plans[0],
-                           ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
-      ctx->launches += 1;
-      prof_end(ctx);
-      continue;
-    }
-    const int first = (o == 0) ? 0 : 1;
-    const int hrows = (o == 0) ? ctx->in_h : od.h;
-    prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
-    const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
-    if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
-      double *tb = (double *)ctx->L->tbuf.p;
-      if (o == 0)
-        launch_sep_pass_a(st, d_image, dtype, pitch_bytes, ctx->in_w, 1, od.w, hrows, od.h, ctx->d_weights,
-                          ctx->plans[o], first, ctx->nlev, tb);
-      else
-        launch_sep_pass_a(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, 0, od.w, hrows, od.h,
-                          ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb);
-      launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss);
-    } else {
-      // radii too large for the staged tiles (octaves >= 4): row-major T, level-parallel kernels
-      double *T[SIFT_MAX_LEVELS];
-      for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->L->tbuf.p + (size_t)i * hrows * od.w;
-      if (o == 0)
-        launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
-                     ctx->plans[o], first, ctx->nlev, T, nullptr);
-      else
-        launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
-                     ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
-      launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T, next, spo, ctx->keep_gauss);
-    }
-    ctx->launches += 2;
+  const OctaveDev &od = ctx->L->octs[o];
+  const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
+  if (o == 0 && ctx->fused0) {
+    prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
+    launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
+                         ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
+    ctx->launches += 1;
     prof_end(ctx);
+    return;
   }
+  const int first = (o == 0) ? 0 : 1;
+  const int hrows = (o == 0) ? ctx->in_h : od.h;
+  prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
+  if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
+    double *tb = (double *)ctx->L->tbuf.p;
+    if (o == 0)
+      launch_sep_pass_a(st, d_image, dtype, pitch_bytes, ctx->in_w, 1, od.w, hrows, od.h, ctx->d_weights,
+                        ctx->plans[o], first, ctx->nlev, tb);
+    else
+      launch_sep_pass_a(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, 0, od.w, hrows, od.h,
+                        ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb);
+    launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss);
+  } else {
+    // radii too large for the staged tiles (octaves >= 4): row-major T, level-parallel kernels
+    double *T[SIFT_MAX_LEVELS];
+    for (int i = 0; i < ctx->nlev - first; i++) T[i] = (double *)ctx->L->tbuf.p + (size_t)i * hrows * od.w;
+    if (o == 0)
+      launch_hblur(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, 1, od.w, hrows, ctx->d_weights,
+                   ctx->plans[o], first, ctx->nlev, T, nullptr);
+    else
+      launch_hblur(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, od.h, 0, od.w, hrows,
+                   ctx->d_weights, ctx->plans[o], first, ctx->nlev, T, nullptr);
+    launch_vblur(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, T, next, spo, ctx->keep_gauss);
+  }
+  ctx->launches += 2;
+  prof_end(ctx);
+}
+
+// Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
+static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
+{
+  for (int o = 0; o < ctx->n_oct; o++) run_octave(ctx, o, d_image, dtype, pitch_bytes);
   CK(cudaGetLastError());
   ctx->pyramid_built = true;
   return SIFT_OK;
@@ -465,6 +552,7 @@ static void fill_stats(sift_stats *s, const Counters &c, int count_low, float ms
   s->rejSingular = c.outcomes[REFINE_SINGULAR];
   s->msDevice = ms;
   s->kernelLaunches = launches;
+  s->leftStrip = c.n_left_strip;
 }
 
 static inline uint64_t cand_key(int o, int s, int y, int x)
@@ -803,7 +891,7 @@ static void add_stats(sift_stats &t, const sift_stats &s)
   t.rejLowContrast += s.rejLowContrast; t.rejEdge += s.rejEdge;
   t.rejLeftScale += s.rejLeftScale; t.rejLeftRows += s.rejLeftRows; t.rejLeftCols += s.rejLeftCols;
   t.rejNoConvergence += s.rejNoConvergence; t.rejSingular += s.rejSingular;
-  t.msDevice += s.msDevice; t.kernelLaunches += s.kernelLaunches;
+  t.msDevice += s.msDevice; t.kernelLaunches += s.kernelLaunches; t.leftStrip += s.leftStrip;
 }
 
 // Images are independent: frame i runs on lane i % n_lanes -- upload, kernels and download
@@ -1144,6 +1232,87 @@ SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, cons
   CK(cudaMemcpy2DAsync(p, (size_t)od.pitch * 4, src, (size_t)od.w * 4, (size_t)od.w * 4, od.h,
                        cudaMemcpyHostToDevice, ctx->L->stream));
   CK(cudaStreamSynchronize(ctx->L->stream));
+  return SIFT_OK;
+}
+
+// ---------------------------------------------------------- mosaic strips ----
+SIFT_API int sift_strip_layout_compute(const sift_params *params, int full_width, int full_height, int row0,
+                                       int row1, int margin, sift_strip_layout *out)
+{
+  return strip_layout(nullptr, params, full_width, full_height, row0, row1, margin, out);
+}
+
+SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const sift_strip_layout *layout,
+                              const void *rows, int dtype, size_t pitch_bytes)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!params || !layout || !rows) return fail(ctx, SIFT_ERR_BAD_ARGS, "params / layout / rows is NULL");
+  if (layout->octaves != params->numberOfOctaves) return fail(ctx, SIFT_ERR_BAD_ARGS, "layout was computed for %d octaves", layout->octaves);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = sift_synchronize(ctx))) return rc;
+  const int src_w = layout->width[0] / 2;
+  const int src_h = (layout->bottom[0] + 1) / 2 - layout->top[0] / 2;
+  ctx->L = &ctx->lanes[0];
+  if ((rc = ensure_plan(ctx, src_w, src_h, params, layout))) return rc;
+  if ((rc = ensure_lane(ctx, ctx->L))) return rc;
+  size_t dpitch;
+  if ((rc = upload_image(ctx, rows, dtype, src_w, src_h, pitch_bytes, &dpitch))) return rc;
+  ctx->strip_dtype = dtype; ctx->strip_pitch = dpitch;
+  ctx->strip_next_octave = 0;
+  ctx->pyramid_built = false;
+  CK(cudaStreamSynchronize(ctx->L->stream));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_strip_seed(sift_ctx *ctx, int octave, double **d_seed)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!ctx->plan_valid || !ctx->is_strip) return fail(ctx, SIFT_ERR_STATE, "no strip: call sift_strip_begin first");
+  if (!d_seed || octave < 1 || octave >= ctx->n_oct) return fail(ctx, SIFT_ERR_BAD_ARGS, "octave %d has no seed image", octave);
+  *d_seed = ctx->lanes[0].octs[octave].seed64;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!ctx->plan_valid || !ctx->is_strip) return fail(ctx, SIFT_ERR_STATE, "no strip: call sift_strip_begin first");
+  if (octave != ctx->strip_next_octave || octave >= ctx->n_oct)
+    return fail(ctx, SIFT_ERR_STATE, "octaves run in order: expected %d, got %d", ctx->strip_next_octave, octave);
+  CK(cudaSetDevice(ctx->device));
+  ctx->L = &ctx->lanes[0];
+  if (octave > 0) {
+    // level 0 of this octave = the seed (owned rows computed here, halo rows received): fp32 copy for read-back
+    const OctaveDev &od = ctx->L->octs[octave];
+    launch_seed_to_f32(ctx->L->stream, od.seed64, od.w, od.h, od.gauss[0], od.pitch);
+    ctx->launches += 1;
+  }
+  run_octave(ctx, octave, ctx->L->image.p, ctx->strip_dtype, ctx->strip_pitch);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->L->stream));
+  ctx->strip_next_octave = octave + 1;
+  if (ctx->strip_next_octave == ctx->n_oct) ctx->pyramid_built = true;
+  return SIFT_OK;
+}
+
+SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *n_out, sift_stats *stats)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!n_out || cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad output arguments");
+  if (!ctx->is_strip || !ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "run every octave with sift_strip_octave first");
+  CK(cudaSetDevice(ctx->device));
+  ctx->L = &ctx->lanes[0];
+  const int64_t l0 = ctx->launches;
+  int rc;
+  Counters c;
+  sift_keypoint *kps;
+  if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
+  ctx->last = c;
+  fill_stats(stats, c, 0, 0.f, (int)(ctx->launches - l0));
+  *n_out = c.n_kp;
+  sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
+  if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
   return SIFT_OK;
 }
 

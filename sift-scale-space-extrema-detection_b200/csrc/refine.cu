@@ -92,14 +92,15 @@ refine_kernel(const OctaveDev *__restrict__ octs, const sift_candidate *__restri
 #pragma unroll
     for (int i = 0; i < SIFT_MAX_LEVELS; i++) D.pl[i] = oc.dog[i];
     D.pitch = oc.pitch;
-    const int rows = oc.h, cols = oc.w;
+    const int rows = oc.gh, cols = oc.w, ytop = oc.y_top;    // m is a row of the whole image; the strip holds rows [ytop, ytop + oc.h)
     int s = cd.scaleLevel, m = cd.y, nn = cd.x;
     const double value = (double)cd.value;
     int outcome = REFINE_NO_CONVERGENCE;
+    bool left_strip = false;
     sift_keypoint kp;
     for (int it = 0; it < rp.max_iter; it++) {                                     // background.js:480
       double g[3], h[3][3], inv[3][3];
-      grad_hess(D, s, m, nn, g, h);
+      grad_hess(D, s, m - ytop, nn, g, h);
       if (!inverse3x3(h, inv)) { outcome = REFINE_SINGULAR; break; }               // matrix2d.js:482 (Q7)
       double a[3];
 #pragma unroll
@@ -133,9 +134,11 @@ refine_kernel(const OctaveDev *__restrict__ octs, const sift_candidate *__restri
       nn = (int)js_round(nn + a[2]);
       if (s < 1 || s >= rp.ndog - 1) { outcome = REFINE_LEFT_SCALE; break; }       // :644
       if (m < 1 || m >= rows - 1) { outcome = REFINE_LEFT_ROWS; break; }           // :651
+      if (m - ytop < 1 || m - ytop >= oc.h - 1) { outcome = REFINE_LEFT_ROWS; left_strip = true; break; }   // walked out of the strip's halo
       if (nn < 1 || nn >= cols - 1) { outcome = REFINE_LEFT_COLS; break; }         // :658
     }
     atomicAdd(&ctr->outcomes[outcome], 1);
+    if (left_strip) atomicAdd(&ctr->n_left_strip, 1);
     if (outcome == REFINE_ACCEPTED) {
       const int slot = atomicAdd(&ctr->n_kp, 1);
       if (slot < cap) out[slot] = kp;

@@ -59,7 +59,8 @@ scan_octave_kernel(OctaveDev oct, int octave, int spo, double pix_threshold, int
 {
   const int x = blockIdx.x * SC_BX + threadIdx.x;
   const int y = blockIdx.y * SC_BY + threadIdx.y;
-  const bool inside = (x >= 1 && x < oct.w - 1 && y >= 1 && y < oct.h - 1);          // sift.js:221-222
+  const int yg = y + oct.y_top;                                                       // row of the whole image
+  const bool inside = (x >= 1 && x < oct.w - 1 && yg >= 1 && yg < oct.gh - 1 && y >= oct.own0 && y < oct.own1);   // sift.js:221-222
   const size_t pitch = oct.pitch;
   for (int s = 1; s <= spo; s++) {                                                    // background.js:377
     bool hit = false, hit_low = false;
@@ -75,13 +76,13 @@ scan_octave_kernel(OctaveDev oct, int octave, int spo, double pix_threshold, int
     }
     int slot = warp_append(hit, &ctr->n_cand);
     if (slot >= 0 && slot < cand_cap) {
-      sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = y; r.value = c; r.reserved0 = 0;
+      sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = yg; r.value = c; r.reserved0 = 0;
       cand[slot] = r;
     }
     if (count_low) {
       slot = warp_append(hit_low, &ctr->n_low);
       if (low && slot >= 0 && slot < low_cap) {
-        sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = y; r.value = c; r.reserved0 = 0;
+        sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = yg; r.value = c; r.reserved0 = 0;
         low[slot] = r;
       }
     }
@@ -169,7 +170,8 @@ scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidat
   const size_t pitch = oc.pitch;
   const int x0 = tx * SA_TW + threadIdx.x * SA_PX;
   const int y = ty * SA_TH + threadIdx.y;
-  const bool row_ok = (y >= 1 && y < h - 1) && x0 < w;                                // sift.js:221
+  const int yg = y + oc.y_top;
+  const bool row_ok = (yg >= 1 && yg < oc.gh - 1 && y >= oc.own0 && y < oc.own1) && x0 < w;   // sift.js:221
   for (int s = 1; s <= A.spo; s++) {                                                  // background.js:377
     const float *p1 = oc.dog[s];
     float c[SA_PX] = { 0.f, 0.f, 0.f, 0.f };
@@ -195,7 +197,7 @@ scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidat
       for (int i = 0; i < SA_PX; i++) {
         const int slot = warp_append((hit >> i) & 1u, &ctr->n_cand);
         if (slot >= 0 && slot < cand_cap) {
-          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = y; r.value = c[i]; r.reserved0 = 0;
+          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = yg; r.value = c[i]; r.reserved0 = 0;
           cand[slot] = r;
         }
       }
@@ -205,7 +207,7 @@ scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidat
       for (int i = 0; i < SA_PX; i++) {
         const int slot = warp_append((hit_low >> i) & 1u, &ctr->n_low);
         if (low && slot >= 0 && slot < low_cap) {
-          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = y; r.value = c[i]; r.reserved0 = 0;
+          sift_candidate r; r.octave = o; r.scaleLevel = s; r.x = x0 + i; r.y = yg; r.value = c[i]; r.reserved0 = 0;
           low[slot] = r;
         }
       }
@@ -259,24 +261,30 @@ struct ScanTmaArgs {
   int tile_start[SIFT_MAX_OCTAVES + 1];
   int tiles_x[SIFT_MAX_OCTAVES];
   int w[SIFT_MAX_OCTAVES], h[SIFT_MAX_OCTAVES];
+  int y_top[SIFT_MAX_OCTAVES], gh[SIFT_MAX_OCTAVES], own0[SIFT_MAX_OCTAVES], own1[SIFT_MAX_OCTAVES];   // strips
   float thr_f;                   // smallest float >= the double threshold (see launch_scan_tma)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-struct ScanTile { int o, x_tile, y_tile, w, h; };
+struct ScanTile { int o, x_tile, y_tile, w, h, y_top, gh, own0, own1; };
 
 __device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t)
 {
   // static indices only: a dynamically indexed kernel-parameter array is copied to local memory
   ScanTile T;
   int o = 0, t0 = 0, ntx = A.tiles_x[0], w = A.w[0], h = A.h[0];
+  int y_top = A.y_top[0], gh = A.gh[0], own0 = A.own0[0], own1 = A.own1[0];
 #pragma unroll
   for (int i = 1; i < SIFT_MAX_OCTAVES; i++)
-    if (i < A.n_oct && t >= A.tile_start[i]) { o = i; t0 = A.tile_start[i]; ntx = A.tiles_x[i]; w = A.w[i]; h = A.h[i]; }
+    if (i < A.n_oct && t >= A.tile_start[i]) {
+      o = i; t0 = A.tile_start[i]; ntx = A.tiles_x[i]; w = A.w[i]; h = A.h[i];
+      y_top = A.y_top[i]; gh = A.gh[i]; own0 = A.own0[i]; own1 = A.own1[i];
+    }
   const int tt = t - t0;
   const int ty = tt / ntx, tx = tt - ty * ntx;
   T.o = o; T.x_tile = tx * ST_TW; T.y_tile = ty * ST_TH; T.w = w; T.h = h;
+  T.y_top = y_top; T.gh = gh; T.own0 = own0; T.own1 = own1;
   return T;
 }
 
@@ -367,7 +375,8 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
         }
         if (r >= 2) {
           const int y = T.y_tile + row_first + r - 2;        // the middle row (slots as, bs, cs = rows y-1, y, y+1)
-          const bool row_ok = y >= 1 && y < T.h - 1;         // sift.js:221
+          const int yg = y + T.y_top;                        // row of the whole image (strips)
+          const bool row_ok = yg >= 1 && yg < T.gh - 1 && y >= T.own0 && y < T.own1;   // sift.js:221
           float m9[ND][2], n9[ND][2];                        // 3x3 max / min per level (centre included)
 #pragma unroll
           for (int p = 0; p < ND; p++)
@@ -401,7 +410,7 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
                 for (int ss = 1; ss < ND - 1; ss++)
 #pragma unroll
                   for (int ii = 0; ii < 2; ii++) if (ss == s && ii == i) c = cen[bs][ss][ii];
-                sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = y; rec.value = c; rec.reserved0 = 0;
+                sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = yg; rec.value = c; rec.reserved0 = 0;
                 int slot = warp_append((hits >> ((s - 1) * 2 + i)) & 1u, &ctr->n_cand);
                 if (slot >= 0 && slot < cand_cap) cand[slot] = rec;
                 if (A.count_low) {
@@ -471,6 +480,7 @@ void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_map
     A.tile_start[o] = total;
     A.tiles_x[o] = (h_octs[o].w + ST_TW - 1) / ST_TW;
     A.w[o] = h_octs[o].w; A.h[o] = h_octs[o].h;
+    A.y_top[o] = h_octs[o].y_top; A.gh[o] = h_octs[o].gh; A.own0[o] = h_octs[o].own0; A.own1[o] = h_octs[o].own1;
     if (h_octs[o].w >= 3 && h_octs[o].h >= 3) total += A.tiles_x[o] * ((h_octs[o].h + ST_TH - 1) / ST_TH);
   }
   A.tile_start[n_oct] = total;

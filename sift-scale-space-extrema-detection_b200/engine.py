@@ -157,6 +157,32 @@ class Engine:
                                                 offs.ctypes.data_as(C.POINTER(C.c_int)), C.byref(st)))
         return out[:offs[-1]], offs, st.as_dict()
 
+    # -- mosaic strips (see mosaic.py)
+    def strip_begin(self, params: L.Params, layout: L.StripLayout, rows, rgba: bool = False):
+        a, dt, w, h = _as_image(rows, rgba)
+        self._check(self._lib.sift_strip_begin(self._h, C.byref(params), C.byref(layout), a.ctypes.data, dt, 0))
+
+    def strip_seed(self, octave: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.sift_strip_seed(self._h, octave, C.byref(p)))
+        return int(p.value)
+
+    def strip_octave(self, octave: int):
+        self._check(self._lib.sift_strip_octave(self._h, octave))
+
+    def strip_finish(self, capacity: int = 1 << 16):
+        cap = capacity
+        while True:
+            out = np.zeros(cap, dtype=L.KEYPOINT_DTYPE)
+            n = C.c_int()
+            st = L.Stats()
+            rc = self._lib.sift_strip_finish(self._h, out.ctypes.data, cap, C.byref(n), C.byref(st))
+            if rc == L.SIFT_ERR_CAPACITY:
+                cap = n.value
+                continue
+            self._check(rc)
+            return out[:n.value], st.as_dict()
+
     # -- stages
     def build_scale_space(self, image, params: L.Params, rgba: bool = False):
         a, dt, w, h = _as_image(image, rgba)

@@ -40,7 +40,8 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.Keypoint) == 80 and L.KEYPOINT_DTYPE.itemsize == 80
     assert C.sizeof(L.Candidate) == 24 and L.CANDIDATE_DTYPE.itemsize == 24
     assert C.sizeof(L.Params) == 72
-    assert C.sizeof(L.Stats) == 48
+    assert C.sizeof(L.Stats) == 52
+    assert C.sizeof(L.StripLayout) == 4 + 7 * 12 * 4
     for name, _ in L.Keypoint._fields_:
         assert getattr(L.Keypoint, name).offset == L.KEYPOINT_DTYPE.fields[name][1]
     # the reference's record fields (background.js:619-628) are all present
