@@ -36,8 +36,10 @@ METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200
 W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
 FRAMES = 8                     # frames per GPU per step (distinct seeds)
+# dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0.txt), ncu --set full
+NCU_TRAFFIC_OCT0_BYTES = 332.6e6
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
-CPU_TILE = 128                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
+CPU_TILE = 256                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
 
 def algorithmic_bytes_per_input_px(n_oct: int = N_OCT) -> dict:
@@ -75,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -141,7 +143,7 @@ def cpu_baseline_leg() -> dict:
     """One host core, the float64 port of the reference's dense 2D path, bounded sample."""
     import oracle
     oracle.build()
-    tiles = cpu_tiles(4)
+    tiles = cpu_tiles(8)
     cpu_detect_tile(tiles[0])
     t0 = time.perf_counter()
     for t in tiles:
@@ -246,12 +248,19 @@ def run_own(args):
         return int(h_offs[FRAMES])
 
     # ---- device-resident timing
+    sampler = ClockSampler(local)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        # nvidia-smi needs ~0.3 s to print its first line: keep the GPU on the same load until it does, so
+        # that the samples cover the timed region even when K steps take only a few milliseconds
+        t_spin = time.perf_counter()
+        while not sampler.lines and time.perf_counter() - t_spin < 3.0:
+            step_device()
+            eng.synchronize()
+    barrier()
     l0 = eng.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -262,6 +271,11 @@ def run_own(args):
     barrier()
     launches = eng.kernel_launches - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if rank == 0:                                   # a few more loaded samples, then stop
+        t_spin = time.perf_counter()
+        while len(sampler.lines) < 4 and time.perf_counter() - t_spin < 1.0:
+            step_device()
+            eng.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -320,7 +334,9 @@ def run_own(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "octave-0 upsample+blur+DoG (" + dom + ")",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_OCT0_BYTES, "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of fused_octave0_kernel, "
+                                           "ncu --set full, profiles/r01_ncu_fused_octave0.txt",
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "whole_path": {"algorithmic_bytes_per_input_px": ab["total"],
                                         "achieved": whole_gbs, "frac": whole_gbs / peak},

@@ -77,11 +77,24 @@ __device__ __forceinline__ double src0_at(const Fused0Args &A, const char *p)
 
 // Two-phase sliding window over 8 neighbouring positions:
 //   a0[k] = sum_{j<n} w0[j] v[k+j],  a1[k] = sum_{j<n} w1[j] v[k+j]
-// v[p] = base[p * stride]; positions up to n+7 are read (n+6 used).
+// v[p] = base[p * stride]; positions up to n+7 are read (n+6 used).  `w` holds the two phases interleaved
+// ({w0[j], w1[j]} = one 16-byte load per tap).  The window rotates through 8 registers with compile-time
+// indices: whole groups of 8 taps, then the remainder decomposed as 4 + 2 + 1 with one code block per
+// (size, rotation) pair, so no tap is padded and the accumulators never change registers.
+#define POLY_STEP(U, JJ)                                                                    \
+  {                                                                                         \
+    const double2 c = w2[(JJ)];                                                             \
+    _Pragma("unroll") for (int k = 0; k < 8; k++) {                                         \
+      a0[k] = fma(c.x, vw[(k + (U)) & 7], a0[k]);                                           \
+      a1[k] = fma(c.y, vw[(k + (U)) & 7], a1[k]);                                           \
+    }                                                                                       \
+    vw[(U) & 7] = nxt[(JJ) * stride];                                                       \
+  }
 __device__ __forceinline__ void poly_window(const double *__restrict__ base, const int stride,
-                                            const double *__restrict__ w0, const double *__restrict__ w1,
-                                            const int n, double (&a0)[8], double (&a1)[8])
+                                            const double *__restrict__ w, const int n, double (&a0)[8],
+                                            double (&a1)[8])
 {
+  const double2 *__restrict__ w2 = reinterpret_cast<const double2 *>(w);
   double vw[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) { vw[k] = base[k * stride]; a0[k] = 0.0; a1[k] = 0.0; }
@@ -89,27 +102,40 @@ __device__ __forceinline__ void poly_window(const double *__restrict__ base, con
   int j = 0;
   for (; j + 8 <= n; j += 8) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const double c0 = w0[j + u], c1 = w1[j + u];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        a0[k] = fma(c0, vw[(k + u) & 7], a0[k]);
-        a1[k] = fma(c1, vw[(k + u) & 7], a1[k]);
-      }
-      vw[u] = nxt[(j + u) * stride];
+    for (int u = 0; u < 8; u++) POLY_STEP(u, j + u)
+  }
+  const int rem = n - j;                                     // 0..7, uniform over the CTA
+  if (rem & 4) { POLY_STEP(0, j) POLY_STEP(1, j + 1) POLY_STEP(2, j + 2) POLY_STEP(3, j + 3) }
+  if (rem & 2) {
+    if (rem & 4) { POLY_STEP(4, j + 4) POLY_STEP(5, j + 5) }
+    else { POLY_STEP(0, j) POLY_STEP(1, j + 1) }
+  }
+  if (rem & 1) {
+    switch (rem & 6) {
+      case 0: POLY_STEP(0, j) break;
+      case 2: POLY_STEP(2, j + 2) break;
+      case 4: POLY_STEP(4, j + 4) break;
+      default: POLY_STEP(6, j + 6) break;
     }
   }
+}
+
+// H pass of level s: rows needed by the level's vertical window, 8 source columns x 2 phases per item
+__device__ __forceinline__ void fused0_hpass(const double *__restrict__ S, double *__restrict__ Ts,
+                                             const double *__restrict__ Wt, int s, int R, int tid)
+{
+  const int clo0 = -((R + 1) / 2);
+  const int n = R + 1 + (R & 1);                     // taps per phase incl. the phase-1 shift for odd R
+  const double *w = Wt + s * 2 * F0_WSTRIDE;
+  const int nrows = F0_SH + n - 1;
+  const int row_first = F0_HALO + clo0;
+  for (int i = tid; i < nrows * (F0_SW / 8); i += F0_THREADS) {
+    const int g = i / nrows, rr = row_first + (i - g * nrows);
+    double a0[8], a1[8];
+    poly_window(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, w, n, a0, a1);
+    double *t = Ts + rr * F0_TPITCH + 16 * g;
 #pragma unroll
-  for (int u = 0; u < 7; u++) {
-    if (j + u < n) {
-      const double c0 = w0[j + u], c1 = w1[j + u];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        a0[k] = fma(c0, vw[(k + u) & 7], a0[k]);
-        a1[k] = fma(c1, vw[(k + u) & 7], a1[k]);
-      }
-      vw[u] = nxt[(j + u) * stride];
-    }
+    for (int k = 0; k < 8; k++) { t[2 * k] = a0[k]; t[2 * k + 1] = a1[k]; }
   }
 }
 
@@ -118,8 +144,9 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
 {
   extern __shared__ double smem[];
   double *S = smem;                                   // [48][49] source tile, fp64
-  double *Ts = S + F0_SROWS * F0_SPITCH;              // [49][65] horizontally blurred rows, both phases
-  double *Wt = Ts + F0_TROWS * F0_TPITCH;             // [nlev][2][F0_WSTRIDE] zero-padded merged taps
+  double *Ts0 = S + F0_SROWS * F0_SPITCH;             // 2 x [49][65] horizontally blurred rows, both phases:
+  double *Ts1 = Ts0 + F0_TROWS * F0_TPITCH;           // level s+1 is produced while level s is consumed
+  double *Wt = Ts1 + F0_TROWS * F0_TPITCH;            // [nlev][F0_WSTRIDE]{w0, w1} zero-padded merged taps
   const int tid = threadIdx.x;
   const int a_tile = blockIdx.x * F0_SW, b_tile = blockIdx.y * F0_SH;
 
@@ -150,17 +177,22 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
       for (int i = 0; i < 9; i++) S[so[i]] = src0_at(A, (const char *)A.src + go[i]);
     }
   }
-  for (int e = tid; e < F0_TPITCH; e += F0_THREADS) Ts[(F0_TROWS - 1) * F0_TPITCH + e] = 0.0;   // slack row
+  for (int e = tid; e < F0_TPITCH; e += F0_THREADS) {                                            // slack rows
+    Ts0[(F0_TROWS - 1) * F0_TPITCH + e] = 0.0;
+    Ts1[(F0_TROWS - 1) * F0_TPITCH + e] = 0.0;
+  }
   if (tid < F0_SROWS) S[tid * F0_SPITCH + F0_SCOLS] = 0.0;                                       // pad column
+  __syncthreads();
+  fused0_hpass(S, Ts0, Wt, 0, A.radius[0], tid);
   __syncthreads();
 
   // V-pass ownership: output column X of the tile, source rows 8*rg .. 8*rg+7, both row phases
   const int X = tid & (2 * F0_SW - 1), rg = tid / (2 * F0_SW);
   const int x = 2 * a_tile + X;
   const int w = A.oct.w, h = A.oct.h;
-  const size_t pitch = A.oct.pitch;
+  const int pitch2 = 2 * A.oct.pitch;
   const int y_first = 2 * (b_tile + 8 * rg);
-  const size_t o_first = (size_t)y_first * pitch + x;
+  const size_t o_first = (size_t)y_first * A.oct.pitch + x;
   const bool col_ok = x < w;
   const bool rows_full = y_first + 16 <= h;
   const bool seed_lane = A.has_next && (X & 1) == 0 && col_ok;
@@ -172,38 +204,30 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
   for (int s = 0; s < A.nlev; s++) {                 // octave 0 blurs every level from the base (background.js:110)
     const int R = A.radius[s];
     const int clo0 = -((R + 1) / 2);
-    const int n = R + 1 + (R & 1);                   // taps per phase incl. the phase-1 shift for odd R
-    const double *w0 = Wt + (s * 2) * F0_WSTRIDE, *w1 = w0 + F0_WSTRIDE;
+    const int n = R + 1 + (R & 1);
+    const double *Ts = (s & 1) ? Ts1 : Ts0;
 
-    // ---- H pass: rows needed by this level's vertical window; 8 source columns x 2 phases per item
-    const int nrows = F0_SH + n - 1;                 // = 32 + chi1 - clo0
-    const int row_first = F0_HALO + clo0;
-    for (int i = tid; i < nrows * (F0_SW / 8); i += F0_THREADS) {
-      const int g = i / nrows, rr = row_first + (i - g * nrows);
-      double a0[8], a1[8];
-      poly_window(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, w0, w1, n, a0, a1);
-      double *t = Ts + rr * F0_TPITCH + 16 * g;
-#pragma unroll
-      for (int k = 0; k < 8; k++) { t[2 * k] = a0[k]; t[2 * k + 1] = a1[k]; }
-    }
-    __syncthreads();
-
-    // ---- V pass
+    // ---- V pass of level s
     double a0[8], a1[8];
-    poly_window(Ts + (F0_HALO + 8 * rg + clo0) * F0_TPITCH + X, F0_TPITCH, w0, w1, n, a0, a1);
+    poly_window(Ts + (F0_HALO + 8 * rg + clo0) * F0_TPITCH + X, F0_TPITCH, Wt + s * 2 * F0_WSTRIDE, n, a0, a1);
 
     // ---- epilogue: G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172), seed of the next octave
     if (col_ok) {
-      float *gp = A.oct.gauss[s] + o_first;
+      float *gp = A.oct.gauss[s] + o_first;          // rows 2k (phase 0) and 2k+1 (phase 1)
+      float *gq = gp + A.oct.pitch;
       float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o_first;
+      float *dq = dp + A.oct.pitch;
       const bool wg = A.keep_gauss != 0, wd = s > 0;
       if (rows_full) {
+        if (wg) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (wg) { gp[(2 * k) * pitch] = (float)a0[k]; gp[(2 * k + 1) * pitch] = (float)a1[k]; }
-          if (wd) {
-            dp[(2 * k) * pitch] = (float)(prev[2 * k] - a0[k]);
-            dp[(2 * k + 1) * pitch] = (float)(prev[2 * k + 1] - a1[k]);
+          for (int k = 0; k < 8; k++) { gp[k * pitch2] = (float)a0[k]; gq[k * pitch2] = (float)a1[k]; }
+        }
+        if (wd) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            dp[k * pitch2] = (float)(prev[2 * k] - a0[k]);
+            dq[k * pitch2] = (float)(prev[2 * k + 1] - a1[k]);
           }
         }
       } else {
@@ -213,8 +237,8 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
           for (int q = 0; q < 2; q++) {
             if (y_first + 2 * k + q < h) {
               const double v = q ? a1[k] : a0[k];
-              if (wg) gp[(2 * k + q) * pitch] = (float)v;
-              if (wd) dp[(2 * k + q) * pitch] = (float)(prev[2 * k + q] - v);
+              if (wg) (q ? gq : gp)[k * pitch2] = (float)v;
+              if (wd) (q ? dq : dp)[k * pitch2] = (float)(prev[2 * k + q] - v);
             }
           }
         }
@@ -232,24 +256,29 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) { prev[2 * k] = a0[k]; prev[2 * k + 1] = a1[k]; }
-    __syncthreads();                                 // Ts is rewritten by the next level
+
+    // ---- H pass of level s+1 into the other buffer (nobody reads it: its V pass ended before the last barrier)
+    if (s + 1 < A.nlev) fused0_hpass(S, (s & 1) ? Ts0 : Ts1, Wt, s + 1, A.radius[s + 1], tid);
+    __syncthreads();
   }
 }
 
-// Host: zero-padded merged polyphase taps of one level into out[2][F0_WSTRIDE].
-//   phase 0: out[0][j] = W0[j], j = c - floor(-R/2);  phase 1: out[1][j + d] = W0[R - j], d = R & 1.
+// Host: zero-padded merged polyphase taps of one level, the two phases interleaved: out[F0_WSTRIDE]{w0, w1}.
+//   phase 0: w0[j] = W0[j], j = c - floor(-R/2);  phase 1: w1[j + d] = W0[R - j], d = R & 1.
 void fused0_merge_taps(const double *w, int R, double *out)
 {
-  for (int i = 0; i < 2 * F0_WSTRIDE; i++) out[i] = 0.0;
+  double w0[F0_WSTRIDE], w1[F0_WSTRIDE];
+  for (int i = 0; i < F0_WSTRIDE; i++) w0[i] = w1[i] = 0.0;
   const int clo0 = -((R + 1) / 2), d = R & 1;
   for (int j = 0; j <= R; j++) {
     const int c = clo0 + j;
     const int i0 = 2 * c, i1 = 2 * c + 1;
     const double t0 = (i0 >= -R && i0 <= R) ? w[i0 + R] : 0.0;
     const double t1 = (i1 >= -R && i1 <= R) ? w[i1 + R] : 0.0;
-    out[j] = t0 + t1;
+    w0[j] = t0 + t1;
   }
-  for (int j = 0; j <= R; j++) out[F0_WSTRIDE + j + d] = out[R - j];
+  for (int j = 0; j <= R; j++) w1[j + d] = w0[R - j];
+  for (int i = 0; i < F0_WSTRIDE; i++) { out[2 * i] = w0[i]; out[2 * i + 1] = w1[i]; }
 }
 
 int fused0_taps_per_level(void) { return 2 * F0_WSTRIDE; }
@@ -274,7 +303,7 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
   A.woff = poly_woff;
   A.u8lut = d_u8lut;
   dim3 grid((src_w + F0_SW - 1) / F0_SW, (src_h + F0_SH - 1) / F0_SH);
-  const size_t smem = (size_t)(F0_SROWS * F0_SPITCH + F0_TROWS * F0_TPITCH + nlev * 2 * F0_WSTRIDE) * sizeof(double);
+  const size_t smem = (size_t)(F0_SROWS * F0_SPITCH + 2 * F0_TROWS * F0_TPITCH + nlev * 2 * F0_WSTRIDE) * sizeof(double);
   cudaFuncSetAttribute(fused_octave0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fused_octave0_kernel<<<grid, F0_THREADS, smem, st>>>(d_weights, A);
 }
