@@ -195,3 +195,45 @@ def test_batch_overflow_falls_back_and_stays_correct(engine):
     for i in range(5):
         single, _ = engine.detect(frames[i], prm)
         assert kps[offs[i]:offs[i + 1]].tobytes() == single.tobytes()
+
+
+def test_4k_six_octaves_properties(engine):
+    """BASELINE configs[3] at full size (3840x2160, 6 octaves: radii up to 463, wider than the last octave's
+    image -> the large-radius fallback kernels run).  Size-independent properties: determinism, reference
+    order, every record inside its octave, counters add up, and the octave-0 result does not depend on how
+    many octaves follow (octaves only feed forward, background.js:114-130)."""
+    w, h = 3840, 2160
+    u8 = fixtures.synthetic_u8(w, h, 99)
+    p6 = L.default_params(numberOfOctaves=6, minBlurLevel=1.6)
+    a, sa = engine.detect(u8, p6)
+    b, _ = engine.detect(u8, p6)
+    assert a.tobytes() == b.tobytes() and len(a) > 5000
+    key = [(int(k["octave"]), int(k["candScale"]), int(k["candY"]), int(k["candX"])) for k in a]
+    assert key == sorted(key)
+    sizes = [engine.octave_size(o) for o in range(6)]
+    assert sizes == [(7680, 4320), (3840, 2160), (1920, 1080), (960, 540), (480, 270), (240, 135)]
+    for o, (ow, oh) in enumerate(sizes):
+        k = a[a["octave"] == o]
+        assert ((k["localX"] >= 1) & (k["localX"] <= ow - 2) & (k["localY"] >= 1) & (k["localY"] <= oh - 2)).all()
+        assert ((k["scaleLevel"] >= 1) & (k["scaleLevel"] <= 3)).all()
+    assert sa["keypoints"] == len(a)
+    assert sa["candidates"] == sa["keypoints"] + sum(sa[r] for r in ("rejLowContrast", "rejEdge", "rejLeftScale", "rejLeftRows",
+                                                                   "rejLeftCols", "rejNoConvergence", "rejSingular"))
+    assert sa["rejSingular"] == 0
+    p2 = L.default_params(numberOfOctaves=2, minBlurLevel=1.6)
+    c, _ = engine.detect(u8, p2)
+    assert a[a["octave"] <= 1].tobytes() == c.tobytes()
+
+
+def test_720p_batch_properties(engine):
+    """BASELINE configs[2] frame shape (1280x720), a slice of the batch: frames in flight must not change results
+    (batch == one frame at a time), per-frame offsets are consistent, distinct seeds give distinct keypoints."""
+    n = 6
+    frames = np.stack([fixtures.synthetic_u8(1280, 720, 1234 + i) for i in range(n)])
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    kps, offs, st = engine.detect_batch(frames, prm)
+    assert offs[0] == 0 and offs[-1] == len(kps) == st["keypoints"] and (np.diff(offs) > 500).all()
+    for i in (0, 3, 5):
+        single, _ = engine.detect(frames[i], prm)
+        assert kps[offs[i]:offs[i + 1]].tobytes() == single.tobytes()
+    assert kps[offs[0]:offs[1]].tobytes() != kps[offs[1]:offs[2]].tobytes()
