@@ -130,7 +130,7 @@ __device__ __forceinline__ void fused0_hpass(const double *__restrict__ S, doubl
   const int nrows = F0_SH + n - 1;
   const int row_first = F0_HALO + clo0;
   for (int i = tid; i < nrows * (F0_SW / 8); i += F0_THREADS) {
-    const int g = i / nrows, rr = row_first + (i - g * nrows);
+    const int g = (i >= nrows) + (i >= 2 * nrows) + (i >= 3 * nrows), rr = row_first + (i - g * nrows);
     double a0[8], a1[8];
     poly_window(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, w, n, a0, a1);
     double *t = Ts + rr * F0_TPITCH + 16 * g;
@@ -190,7 +190,6 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
   const int X = tid & (2 * F0_SW - 1), rg = tid / (2 * F0_SW);
   const int x = 2 * a_tile + X;
   const int w = A.oct.w, h = A.oct.h;
-  const int pitch2 = 2 * A.oct.pitch;
   const int y_first = 2 * (b_tile + 8 * rg);
   const size_t o_first = (size_t)y_first * A.oct.pitch + x;
   const bool col_ok = x < w;
@@ -213,21 +212,22 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
 
     // ---- epilogue: G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172), seed of the next octave
     if (col_ok) {
-      float *gp = A.oct.gauss[s] + o_first;          // rows 2k (phase 0) and 2k+1 (phase 1)
-      float *gq = gp + A.oct.pitch;
+      // rows y_first + 2k (phase 0) and y_first + 2k + 1 (phase 1): one running pointer per plane, bumped one
+      // row per store (two 32-bit adds), instead of a 64-bit multiply-add per store
+      float *gp = A.oct.gauss[s] + o_first;
       float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o_first;
-      float *dq = dp + A.oct.pitch;
+      const size_t rowp = (size_t)A.oct.pitch;
       const bool wg = A.keep_gauss != 0, wd = s > 0;
       if (rows_full) {
         if (wg) {
 #pragma unroll
-          for (int k = 0; k < 8; k++) { gp[k * pitch2] = (float)a0[k]; gq[k * pitch2] = (float)a1[k]; }
+          for (int k = 0; k < 8; k++) { *gp = (float)a0[k]; gp += rowp; *gp = (float)a1[k]; gp += rowp; }
         }
         if (wd) {
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            dp[k * pitch2] = (float)(prev[2 * k] - a0[k]);
-            dq[k * pitch2] = (float)(prev[2 * k + 1] - a1[k]);
+            *dp = (float)(prev[2 * k] - a0[k]); dp += rowp;
+            *dp = (float)(prev[2 * k + 1] - a1[k]); dp += rowp;
           }
         }
       } else {
@@ -237,8 +237,8 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
           for (int q = 0; q < 2; q++) {
             if (y_first + 2 * k + q < h) {
               const double v = q ? a1[k] : a0[k];
-              if (wg) (q ? gq : gp)[k * pitch2] = (float)v;
-              if (wd) (q ? dq : dp)[k * pitch2] = (float)(prev[2 * k + q] - v);
+              if (wg) gp[(size_t)(2 * k + q) * rowp] = (float)v;
+              if (wd) dp[(size_t)(2 * k + q) * rowp] = (float)(prev[2 * k + q] - v);
             }
           }
         }

@@ -19,6 +19,7 @@
 //     8 DFMAs, 2R+1 taps exactly.
 //   * pass B keeps the previous level's unrounded fp64 values in registers, so DoG is formed from the
 //     accumulators and each Gaussian / DoG value is written exactly once.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -156,8 +157,11 @@ __device__ __forceinline__ void fir_stage(const FirArgs &A, const void *src, dou
 // window prefetch (NO) + tap padding (up to 3) + weight prefetch group read past the last real sample
 #define FIR_SLACK(NO) ((NO) + 4)
 
+#ifndef FIR_NO8_BLOCKS
+#define FIR_NO8_BLOCKS 3
+#endif
 template <int NW, int NO, int MODE>
-__global__ void __launch_bounds__(32 * NW, (NO == 16 || NW == 4) ? 2 : 3)
+__global__ void __launch_bounds__(32 * NW, (NO == 16 || NW == 4) ? 2 : FIR_NO8_BLOCKS)
 fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
 {
   extern __shared__ double smem[];
@@ -209,37 +213,37 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
       fir_window<NO>(wsm + wo, npad, cur + (warp * NO + (per_level ? 0 : A.rmax - R)) * FP_PITCH + lane, acc);
       if (!per_level) {
         double *out = A.T[li] + (size_t)b0 * A.t_pitch + a;
-        const int tp = (int)A.t_pitch;
+        const size_t tp = A.t_pitch;
         if (full) {
 #pragma unroll
-          for (int k = 0; k < NO; k++) out[k * tp] = acc[k];
+          for (int k = 0; k < NO; k++) { *out = acc[k]; out += tp; }       // running pointer: two adds per store
         } else {
 #pragma unroll
           for (int k = 0; k < NO; k++)
-            if (b0 + k < A.nb) out[k * tp] = acc[k];
+            if (b0 + k < A.nb) out[(size_t)k * tp] = acc[k];
         }
       } else {
         // G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded accumulators, seed of the next octave
         const int s = A.level[li];
-        const int pitch = A.oct.pitch;
+        const size_t pitch = (size_t)A.oct.pitch;
         const size_t o = (size_t)b0 * pitch + a;
         float *gp = A.oct.gauss[s] + o;
         float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o;
         if (full) {
           if (A.keep_gauss) {
 #pragma unroll
-            for (int k = 0; k < NO; k++) gp[k * pitch] = (float)acc[k];
+            for (int k = 0; k < NO; k++) { *gp = (float)acc[k]; gp += pitch; }
           }
           if (s > 0) {
 #pragma unroll
-            for (int k = 0; k < NO; k++) dp[k * pitch] = (float)(prev[k] - acc[k]);
+            for (int k = 0; k < NO; k++) { *dp = (float)(prev[k] - acc[k]); dp += pitch; }
           }
         } else {
 #pragma unroll
           for (int k = 0; k < NO; k++) {
             if (b0 + k < A.nb) {
-              if (A.keep_gauss) gp[k * pitch] = (float)acc[k];
-              if (s > 0) dp[k * pitch] = (float)(prev[k] - acc[k]);
+              if (A.keep_gauss) gp[(size_t)k * pitch] = (float)acc[k];
+              if (s > 0) dp[(size_t)k * pitch] = (float)(prev[k] - acc[k]);
             }
           }
         }
@@ -269,7 +273,8 @@ struct FirShape { int nw, no; };
 static FirShape fir_shape(int na, int nb)
 {
   const long long px = (long long)na * nb;
-  if (px >= (1 << 20)) return { 8, 16 };
+  static const char *no8 = getenv("SIFT_B200_FIR_NO8");
+  if (px >= (1 << 20)) return (no8 && no8[0] == '1') ? FirShape{ 8, 8 } : FirShape{ 8, 16 };
   if (px >= (1 << 18)) return { 8, 8 };
   return { 4, 8 };
 }
