@@ -3,6 +3,7 @@
 // pipeline driver (background.js:71-237 octave/scale loop, :258 DoG loop, :359
 // candidate loop, :455 refinement loop); the arithmetic lives in the kernels.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -561,39 +562,46 @@ static inline uint64_t cand_key(int o, int s, int y, int x)
 }
 
 // Reference output order = candidate order: octave, scale, row, column (background.js:468-471, sift.js:221-222).
-// LSD radix sort of (key, index) and a gather into `dst` (may alias nothing in `src`).
+// LSD radix sort of (compact key, index) and a gather into `dst` (may alias nothing in `src`).  The key packs
+// only as many bits as the pyramid needs (octave-0 size), so a 1080p frame sorts in three 11-bit passes.
 static void sort_keypoints_into(sift_ctx *ctx, const sift_keypoint *src, int n, sift_keypoint *dst, int dst_cap)
 {
   if (n <= 0) return;
+  int bx = 1, by = 1;
+  while ((1 << bx) < ctx->ow[0]) bx++;
+  const int gh0 = ctx->is_strip ? ctx->strip.height[0] : ctx->oh[0];      // candY is a row of the whole image
+  while ((1 << by) < gh0) by++;
   std::vector<uint64_t> &a = ctx->sort_a, &b = ctx->sort_b;
   a.resize((size_t)n); b.resize((size_t)n);
-  uint64_t ormask = 0;
   for (int i = 0; i < n; i++) {
-    const uint64_t k = cand_key(src[i].octave, src[i].candScale, src[i].candY, src[i].candX);
-    ormask |= k;
-    a[i] = k;   // index carried separately below
+    const uint64_t k = ((((uint64_t)(uint32_t)src[i].octave * 16 + (uint32_t)src[i].candScale) << by | (uint32_t)src[i].candY) << bx) |
+                       (uint32_t)src[i].candX;
+    a[i] = (k << 24) | (uint32_t)i;                       // n < 2^24 per frame; larger lists take the generic path
   }
-  // keys are < 2^62; pack index (n < 2^26) is not possible in 64 bits for large images, so sort index pairs
-  std::vector<uint32_t> ia((size_t)n), ib((size_t)n);
-  for (int i = 0; i < n; i++) ia[i] = (uint32_t)i;
+  const int key_bits = 8 + by + bx;
+  if (n >= (1 << 24) || key_bits > 40) {
+    std::vector<uint32_t> idx((size_t)n);
+    for (int i = 0; i < n; i++) idx[i] = (uint32_t)i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t p, uint32_t q) {
+      return cand_key(src[p].octave, src[p].candScale, src[p].candY, src[p].candX) <
+             cand_key(src[q].octave, src[q].candScale, src[q].candY, src[q].candX);
+    });
+    const int m = std::min(n, dst_cap);
+    for (int i = 0; i < m; i++) dst[i] = src[idx[i]];
+    return;
+  }
   const int DIG = 11, NB = 1 << DIG;
-  std::vector<uint32_t> hist((size_t)NB);
-  for (int shift = 0; shift < 64; shift += DIG) {
-    if (((ormask >> shift) & (NB - 1)) == 0 && (ormask >> shift) != 0 && false) continue;
-    if ((ormask >> shift) == 0) break;
-    if (((ormask >> shift) & (uint64_t)(NB - 1)) == 0) continue;   // digit is zero in every key
-    std::fill(hist.begin(), hist.end(), 0u);
+  uint32_t hist[1 << 11];
+  for (int shift = 24; shift < 24 + key_bits; shift += DIG) {
+    memset(hist, 0, sizeof hist);
     for (int i = 0; i < n; i++) hist[(a[i] >> shift) & (NB - 1)]++;
     uint32_t sum = 0;
     for (int d = 0; d < NB; d++) { const uint32_t c = hist[d]; hist[d] = sum; sum += c; }
-    for (int i = 0; i < n; i++) {
-      const uint32_t pos = hist[(a[i] >> shift) & (NB - 1)]++;
-      b[pos] = a[i]; ib[pos] = ia[i];
-    }
-    a.swap(b); ia.swap(ib);
+    for (int i = 0; i < n; i++) b[hist[(a[i] >> shift) & (NB - 1)]++] = a[i];
+    a.swap(b);
   }
   const int m = std::min(n, dst_cap);
-  for (int i = 0; i < m; i++) dst[i] = src[ia[i]];
+  for (int i = 0; i < m; i++) dst[i] = src[a[i] & 0xffffffu];
 }
 
 static void sort_candidates(sift_candidate *c, int n)
@@ -935,11 +943,15 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
   if ((rc = prepare_lanes())) { ctx->L = &ctx->lanes[0]; return rc; }
   const int64_t l0 = ctx->launches;
   int n = 0, overflow = 0;
+  static const bool trace = getenv("SIFT_B200_TRACE") != nullptr;
+  double t_issue = 0, t_wait = 0, t_sort = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   int done = 0, issued = 0;     // frames consumed by the host / frames whose device work has been issued
   CK(cudaEventRecord(ctx->ev0, ctx->lanes[0].stream));
   auto take = [&](int j, int ni, const sift_stats &si) { n += ni; offsets[j + 1] = n; add_stats(total, si); };
 
   auto issue = [&](int i) -> int {
+    const double t0 = now();
     Lane *ln = &ctx->lanes[i % NL];
     ctx->L = ln;
     const void *img = (const char *)images + (size_t)i * image_stride_bytes;
@@ -954,6 +966,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     CK(cudaMemcpyAsync(ln->h_out, ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
     CK(cudaEventRecord(ln->ev_done, ln->stream));
     issued = i + 1;
+    t_issue += now() - t0;
     return SIFT_OK;
   };
 
@@ -962,7 +975,10 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     const int j = done;
     Lane *ln = &ctx->lanes[j % NL];
     ctx->L = ln;
+    const double t0 = now();
     CK(cudaEventSynchronize(ln->ev_done));
+    const double t1 = now();
+    t_wait += t1 - t0;
     Counters c = *(Counters *)ln->h_out;
     sift_stats si;
     memset(&si, 0, sizeof si);
@@ -1004,6 +1020,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     ctx->last = c;
     take(j, c.n_kp, si);
     done = j + 1;
+    t_sort += now() - t1;
     return SIFT_OK;
   };
 
@@ -1026,6 +1043,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   total.msDevice = ms;
   total.kernelLaunches = (int)(ctx->launches - l0);
+  if (trace) fprintf(stderr, "[sift_detect_batch] %d frames: device span %.3f ms, host issue %.3f, wait %.3f, order %.3f ms\n", n_images, ms, t_issue, t_wait, t_sort);
   if (stats) *stats = total;
   if (overflow) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints in the batch, capacity %d", n, cap);
   return SIFT_OK;
