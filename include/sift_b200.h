@@ -154,6 +154,10 @@ SIFT_API int sift_synchronize(sift_ctx *ctx);
  * (without blocking the host): queue it before consuming device results or recording an event there. */
 SIFT_API void *sift_stream(sift_ctx *ctx);
 SIFT_API int sift_flush(sift_ctx *ctx);
+/* Keypoint-only callers do not read the Gaussian levels back: keep == 0 stops the blur kernels from writing
+ * them (the DoG levels and the seeds are unaffected; sift_get_level(GAUSSIAN) then returns stale data for
+ * levels >= 1).  Default 1: every level of the pyramid is materialised once, like the reference's reply. */
+SIFT_API int sift_set_keep_gaussian(sift_ctx *ctx, int keep);
 /* Frames in flight for sift_detect_device / sift_detect_batch (1..4, default 3, env SIFT_B200_LANES). */
 SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes);
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for the context */

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "sift_stream": (_VP, [_VP]),
     "sift_flush": (C.c_int, [_VP]),
     "sift_set_lanes": (C.c_int, [_VP, C.c_int]),
+    "sift_set_keep_gaussian": (C.c_int, [_VP, C.c_int]),
     "sift_kernel_launches": (C.c_int64, [_VP]),
     "sift_set_profiling": (C.c_int, [_VP, C.c_int]),
     "sift_get_profile": (C.c_int, [_VP, _FP, _IP, C.c_int]),

@@ -789,6 +789,15 @@ SIFT_API int sift_synchronize(sift_ctx *ctx)
   return SIFT_OK;
 }
 
+SIFT_API int sift_set_keep_gaussian(sift_ctx *ctx, int keep)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  int rc;
+  if ((rc = sift_synchronize(ctx))) return rc;
+  ctx->keep_gauss = keep ? 1 : 0;
+  return SIFT_OK;
+}
+
 SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;

@@ -89,6 +89,10 @@ class Engine:
         """Frames in flight for detect_device / detect_batch (1..4)."""
         self._check(self._lib.sift_set_lanes(self._h, int(n)))
 
+    def set_keep_gaussian(self, keep: bool):
+        """False: keypoint-only mode, the Gaussian levels are computed but not written to HBM."""
+        self._check(self._lib.sift_set_keep_gaussian(self._h, 1 if keep else 0))
+
     def set_profiling(self, enabled: bool):
         self._check(self._lib.sift_set_profiling(self._h, 1 if enabled else 0))
 

@@ -237,3 +237,16 @@ def test_720p_batch_properties(engine):
         single, _ = engine.detect(frames[i], prm)
         assert kps[offs[i]:offs[i + 1]].tobytes() == single.tobytes()
     assert kps[offs[0]:offs[1]].tobytes() != kps[offs[1]:offs[2]].tobytes()
+
+
+def test_keypoint_only_mode_gives_the_same_keypoints(engine):
+    """sift_set_keep_gaussian(0): the Gaussian levels stay in registers; DoG, seeds and keypoints are unchanged."""
+    u8 = fixtures.synthetic_u8(320, 240, 21)
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    a, _ = engine.detect(u8, prm)
+    engine.set_keep_gaussian(False)
+    try:
+        b, _ = engine.detect(u8, prm)
+    finally:
+        engine.set_keep_gaussian(True)
+    assert a.tobytes() == b.tobytes() and len(a) > 50
