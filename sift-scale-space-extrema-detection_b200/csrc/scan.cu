@@ -290,7 +290,7 @@ __device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t
 
 // Persistent CTAs, two tile buffers: while the CTA tests tile k out of one buffer the TMA unit fills the
 // other with tile k + 1, so the HBM latency of a tile is hidden behind the arithmetic of the previous one.
-template <int ND>   // DoG levels per octave (spo + 2)
+template <int ND, bool COUNT_LOW>   // DoG levels per octave (spo + 2); also materialise the low-contrast list
 __global__ void __launch_bounds__(ST_THREADS, ST_STAGES == 1 ? 4 : 2)
 scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_candidate *__restrict__ cand,
                 int cand_cap, sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
@@ -385,7 +385,8 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
               m9[p][i] = fmaxf(fmaxf(hmax[as][p][i], hmax[bs][p][i]), hmax[cs][p][i]);
               n9[p][i] = fminf(fminf(hmin[as][p][i], hmin[bs][p][i]), hmin[cs][p][i]);
             }
-          unsigned hits = 0;                                 // bit (s-1)*2 + i: candidate; bit 16 + ...: low contrast
+          // one predicate per voxel; nothing else is materialised unless some lane of the warp has a hit
+          bool ext[ND][2], any_ext = false;
 #pragma unroll
           for (int s = 1; s < ND - 1; s++) {                 // background.js:377
 #pragma unroll
@@ -395,26 +396,25 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
               const float ring_min = fminf(fminf(hmin[as][s][i], hmin[cs][s][i]), lrmin[bs][s][i]);
               const float nmax = fmaxf(fmaxf(m9[s - 1][i], m9[s + 1][i]), ring_max);
               const float nmin = fminf(fminf(n9[s - 1][i], n9[s + 1][i]), ring_min);
-              const bool ext = (c > nmax || c < nmin) && row_ok && col_ok[i];           // sift.js:261, 266
-              const bool strong = fabsf(c) >= A.thr_f;                                  // sift.js:294 (see launch_scan_tma)
-              hits |= (ext && strong) ? 1u << ((s - 1) * 2 + i) : 0u;
-              hits |= (ext && !strong) ? 1u << (16 + (s - 1) * 2 + i) : 0u;
+              bool e = (c > nmax || c < nmin) && col_ok[i];                             // sift.js:261, 266
+              if (!COUNT_LOW) e = e && fabsf(c) >= A.thr_f;                             // sift.js:294 (see launch_scan_tma)
+              ext[s][i] = e;
+              any_ext = any_ext || e;
             }
           }
-          if (!A.count_low) hits &= 0xffffu;
-          if (__any_sync(0xffffffffu, hits != 0)) {          // rare: ~3e-4 of the voxels
+          if (__any_sync(0xffffffffu, any_ext && row_ok)) {  // rare: ~3e-4 of the voxels
+#pragma unroll
             for (int s = 1; s < ND - 1; s++)
+#pragma unroll
               for (int i = 0; i < 2; i++) {
-                float c = 0.f;
-#pragma unroll
-                for (int ss = 1; ss < ND - 1; ss++)
-#pragma unroll
-                  for (int ii = 0; ii < 2; ii++) if (ss == s && ii == i) c = cen[bs][ss][ii];
+                const float c = cen[bs][s][i];
+                const bool e = ext[s][i] && row_ok;
+                const bool strong = fabsf(c) >= A.thr_f;
                 sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = yg; rec.value = c; rec.reserved0 = 0;
-                int slot = warp_append((hits >> ((s - 1) * 2 + i)) & 1u, &ctr->n_cand);
+                int slot = warp_append(e && strong, &ctr->n_cand);
                 if (slot >= 0 && slot < cand_cap) cand[slot] = rec;
-                if (A.count_low) {
-                  slot = warp_append((hits >> (16 + (s - 1) * 2 + i)) & 1u, &ctr->n_low);
+                if (COUNT_LOW) {
+                  slot = warp_append(e && !strong, &ctr->n_low);
                   if (low && slot >= 0 && slot < low_cap) low[slot] = rec;
                 }
               }
@@ -492,8 +492,13 @@ void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_map
   const CUtensorMap *maps = (const CUtensorMap *)d_maps;
 #define LAUNCH_ND(N)                                                                                         \
   case N:                                                                                                    \
-    cudaFuncSetAttribute(scan_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    scan_tma_kernel<N><<<grid, ST_THREADS, smem, st>>>(maps, A, cand, cand_cap, low, low_cap, ctr);         \
+    if (count_low) {                                                                                         \
+      cudaFuncSetAttribute(scan_tma_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      scan_tma_kernel<N, true><<<grid, ST_THREADS, smem, st>>>(maps, A, cand, cand_cap, low, low_cap, ctr);  \
+    } else {                                                                                                 \
+      cudaFuncSetAttribute(scan_tma_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      scan_tma_kernel<N, false><<<grid, ST_THREADS, smem, st>>>(maps, A, cand, cand_cap, low, low_cap, ctr); \
+    }                                                                                                        \
     break;
   switch (nd) { LAUNCH_ND(3) LAUNCH_ND(4) LAUNCH_ND(5) LAUNCH_ND(6) }
 #undef LAUNCH_ND
