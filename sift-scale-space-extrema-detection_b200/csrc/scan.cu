@@ -321,7 +321,6 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
   }
   __syncthreads();
   if (tid == 0 && (int)blockIdx.x < A.total_tiles) issue(blockIdx.x, 0);
-
   // thread -> 2 pixels (columns 2*cx, 2*cx+1 of the tile) x rows [8*ry, 8*ry + 8)
   const int cx = tid & (ST_TW / 2 - 1), ry = tid / (ST_TW / 2);
   const int xl = 2 * cx;                                  // tile-local column of pixel 0
@@ -347,16 +346,18 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
     const float *tile = tiles + stage * ND * ST_PLANE;
     const int x0 = T.x_tile + xl;
     const bool col_ok[2] = { x0 >= 1 && x0 < T.w - 1, x0 + 1 >= 1 && x0 + 1 < T.w - 1 };      // sift.js:222
-    // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3): horizontal
-    // 3-max / 3-min, and for the centre levels the row's own values and its left/right-only max / min
-    float hmax[3][ND][2], hmin[3][ND][2], cen[3][ND][2], lrmax[3][ND][2], lrmin[3][ND][2];
+    // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3) of the horizontal
+    // 3-max / 3-min, and the centre levels' own values.  Fast path: a pixel can only be an extremum if it EQUALS
+    // the max (or min) of its 3x3x3 block, centre included -- two 3-input min/max per voxel on top of the shared
+    // 3x3 block extrema.  The rare survivors (true extrema and ties) get the exact strict 26-neighbour test
+    // from shared memory (sift.js:261, 266: ties are never extrema).
+    float hmax[3][ND][2], hmin[3][ND][2], cen[3][ND][2];
 #pragma unroll 1
     for (int r3 = 0; r3 < ST_ROWS + 2; r3 += 3) {
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         const int r = r3 + j;
         if (r >= ST_ROWS + 2) break;
-        constexpr int dummy = 0; (void)dummy;
         const int cs = j, bs = (j + 2) % 3, as = (j + 1) % 3;          // slots of rows r, r-1, r-2
         // box row of tile-local row (row_first - 1 + r) is (row_first + r): the box starts one row above the tile
 #pragma unroll
@@ -367,11 +368,7 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
           const float mx = fmaxf(v.x, v.y), mn = fminf(v.x, v.y);
           hmax[cs][p][0] = fmaxf(L, mx); hmax[cs][p][1] = fmaxf(mx, Rr);
           hmin[cs][p][0] = fminf(L, mn); hmin[cs][p][1] = fminf(mn, Rr);
-          if (p >= 1 && p < ND - 1) {
-            cen[cs][p][0] = v.x; cen[cs][p][1] = v.y;
-            lrmax[cs][p][0] = fmaxf(L, v.y); lrmax[cs][p][1] = fmaxf(v.x, Rr);
-            lrmin[cs][p][0] = fminf(L, v.y); lrmin[cs][p][1] = fminf(v.x, Rr);
-          }
+          if (p >= 1 && p < ND - 1) { cen[cs][p][0] = v.x; cen[cs][p][1] = v.y; }
         }
         if (r >= 2) {
           const int y = T.y_tile + row_first + r - 2;        // the middle row (slots as, bs, cs = rows y-1, y, y+1)
@@ -385,30 +382,43 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
               m9[p][i] = fmaxf(fmaxf(hmax[as][p][i], hmax[bs][p][i]), hmax[cs][p][i]);
               n9[p][i] = fminf(fminf(hmin[as][p][i], hmin[bs][p][i]), hmin[cs][p][i]);
             }
-          // one predicate per voxel; nothing else is materialised unless some lane of the warp has a hit
-          bool ext[ND][2], any_ext = false;
+          bool maybe[ND][2], any = false;
 #pragma unroll
           for (int s = 1; s < ND - 1; s++) {                 // background.js:377
 #pragma unroll
             for (int i = 0; i < 2; i++) {
               const float c = cen[bs][s][i];
-              const float ring_max = fmaxf(fmaxf(hmax[as][s][i], hmax[cs][s][i]), lrmax[bs][s][i]);
-              const float ring_min = fminf(fminf(hmin[as][s][i], hmin[cs][s][i]), lrmin[bs][s][i]);
-              const float nmax = fmaxf(fmaxf(m9[s - 1][i], m9[s + 1][i]), ring_max);
-              const float nmin = fminf(fminf(n9[s - 1][i], n9[s + 1][i]), ring_min);
-              bool e = (c > nmax || c < nmin) && col_ok[i];                             // sift.js:261, 266
+              const float m27 = fmaxf(fmaxf(m9[s - 1][i], m9[s][i]), m9[s + 1][i]);
+              const float n27 = fminf(fminf(n9[s - 1][i], n9[s][i]), n9[s + 1][i]);
+              bool e = (c == m27 || c == n27) && col_ok[i];
               if (!COUNT_LOW) e = e && fabsf(c) >= A.thr_f;                             // sift.js:294 (see launch_scan_tma)
-              ext[s][i] = e;
-              any_ext = any_ext || e;
+              maybe[s][i] = e;
+              any = any || e;
             }
           }
-          if (__any_sync(0xffffffffu, any_ext && row_ok)) {  // rare: ~3e-4 of the voxels
+          if (__any_sync(0xffffffffu, any && row_ok)) {      // rare
 #pragma unroll
             for (int s = 1; s < ND - 1; s++)
 #pragma unroll
               for (int i = 0; i < 2; i++) {
                 const float c = cen[bs][s][i];
-                const bool e = ext[s][i] && row_ok;
+                bool e = false;
+                if (maybe[s][i] && row_ok) {                 // exact strict test of the 26 neighbours
+                  const float *ctr_px = tile + s * ST_PLANE + (row_first + r - 1) * ST_BW + 4 + xl + i;
+                  bool is_max = true, is_min = true;
+#pragma unroll
+                  for (int dp = -1; dp <= 1; dp++)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                      for (int dx = -1; dx <= 1; dx++) {
+                        if (dp == 0 && dy == 0 && dx == 0) continue;
+                        const float v = ctr_px[dp * ST_PLANE + dy * ST_BW + dx];
+                        is_max = is_max && (v < c);          // sift.js:266
+                        is_min = is_min && (v > c);          // sift.js:261
+                      }
+                  e = is_max || is_min;
+                }
                 const bool strong = fabsf(c) >= A.thr_f;
                 sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = yg; rec.value = c; rec.reserved0 = 0;
                 int slot = warp_append(e && strong, &ctr->n_cand);
