@@ -245,13 +245,19 @@ void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *
 // are never extrema).  Hits are compacted with ballot / popc and one atomic per warp.
 #include <cuda.h>
 
+#ifndef ST_PX
+#define ST_PX 2                // pixels per thread along x (1 or 2)
+#endif
+#ifndef ST_TW
 #define ST_TW 128
+#endif
 #define ST_TH 16
 #define ST_BW (ST_TW + 8)      // box: 4 columns left (alignment) + tile + 4 right
 #define ST_BH (ST_TH + 2)
 #define ST_PLANE ((ST_BH * ST_BW + 31) & ~31)   // floats per staged level: TMA destinations are 128-byte aligned
 #define ST_ROWS 8              // rows marched by one thread
-#define ST_THREADS ((ST_TW / 2) * (ST_TH / ST_ROWS))   // 128
+#define ST_THREADS ((ST_TW / ST_PX) * (ST_TH / ST_ROWS))   // 128
+#define ST_CTAS_PER_SM 4
 #ifndef ST_STAGES
 #define ST_STAGES 1            // 1: one tile per CTA, four CTAs per SM hide the load; 2: persistent CTAs, double buffer
 #endif
@@ -291,7 +297,7 @@ __device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t
 // Persistent CTAs, two tile buffers: while the CTA tests tile k out of one buffer the TMA unit fills the
 // other with tile k + 1, so the HBM latency of a tile is hidden behind the arithmetic of the previous one.
 template <int ND, bool COUNT_LOW>   // DoG levels per octave (spo + 2); also materialise the low-contrast list
-__global__ void __launch_bounds__(ST_THREADS, ST_STAGES == 1 ? 4 : 2)
+__global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
 scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_candidate *__restrict__ cand,
                 int cand_cap, sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
 {
@@ -322,8 +328,8 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
   __syncthreads();
   if (tid == 0 && (int)blockIdx.x < A.total_tiles) issue(blockIdx.x, 0);
   // thread -> 2 pixels (columns 2*cx, 2*cx+1 of the tile) x rows [8*ry, 8*ry + 8)
-  const int cx = tid & (ST_TW / 2 - 1), ry = tid / (ST_TW / 2);
-  const int xl = 2 * cx;                                  // tile-local column of pixel 0
+  const int cx = tid & (ST_TW / ST_PX - 1), ry = tid / (ST_TW / ST_PX);
+  const int xl = ST_PX * cx;                                  // tile-local column of pixel 0
   const int row_first = ry * ST_ROWS;                     // tile-local row of the first output row
 
   int k = 0;
@@ -345,13 +351,15 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
     const ScanTile T = scan_decode_tile(A, t);
     const float *tile = tiles + stage * ND * ST_PLANE;
     const int x0 = T.x_tile + xl;
-    const bool col_ok[2] = { x0 >= 1 && x0 < T.w - 1, x0 + 1 >= 1 && x0 + 1 < T.w - 1 };      // sift.js:222
+    bool col_ok[ST_PX];                                                                  // sift.js:222
+#pragma unroll
+    for (int i = 0; i < ST_PX; i++) col_ok[i] = x0 + i >= 1 && x0 + i < T.w - 1;
     // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3) of the horizontal
     // 3-max / 3-min, and the centre levels' own values.  Fast path: a pixel can only be an extremum if it EQUALS
     // the max (or min) of its 3x3x3 block, centre included -- two 3-input min/max per voxel on top of the shared
     // 3x3 block extrema.  The rare survivors (true extrema and ties) get the exact strict 26-neighbour test
     // from shared memory (sift.js:261, 266: ties are never extrema).
-    float hmax[3][ND][2], hmin[3][ND][2], cen[3][ND][2];
+    float hmax[3][ND][ST_PX], hmin[3][ND][ST_PX], cen[3][ND][ST_PX];
 #pragma unroll 1
     for (int r3 = 0; r3 < ST_ROWS + 2; r3 += 3) {
 #pragma unroll
@@ -363,30 +371,37 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
 #pragma unroll
         for (int p = 0; p < ND; p++) {
           const float *rowp = tile + p * ST_PLANE + (row_first + r) * ST_BW + 4 + xl;
+#if ST_PX == 2
           const float2 v = *reinterpret_cast<const float2 *>(rowp);
           const float L = rowp[-1], Rr = rowp[2];
           const float mx = fmaxf(v.x, v.y), mn = fminf(v.x, v.y);
           hmax[cs][p][0] = fmaxf(L, mx); hmax[cs][p][1] = fmaxf(mx, Rr);
           hmin[cs][p][0] = fminf(L, mn); hmin[cs][p][1] = fminf(mn, Rr);
           if (p >= 1 && p < ND - 1) { cen[cs][p][0] = v.x; cen[cs][p][1] = v.y; }
+#else
+          const float L = rowp[-1], v = rowp[0], Rr = rowp[1];
+          hmax[cs][p][0] = fmaxf(fmaxf(L, v), Rr);
+          hmin[cs][p][0] = fminf(fminf(L, v), Rr);
+          if (p >= 1 && p < ND - 1) cen[cs][p][0] = v;
+#endif
         }
         if (r >= 2) {
           const int y = T.y_tile + row_first + r - 2;        // the middle row (slots as, bs, cs = rows y-1, y, y+1)
           const int yg = y + T.y_top;                        // row of the whole image (strips)
           const bool row_ok = yg >= 1 && yg < T.gh - 1 && y >= T.own0 && y < T.own1;   // sift.js:221
-          float m9[ND][2], n9[ND][2];                        // 3x3 max / min per level (centre included)
+          float m9[ND][ST_PX], n9[ND][ST_PX];                        // 3x3 max / min per level (centre included)
 #pragma unroll
           for (int p = 0; p < ND; p++)
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < ST_PX; i++) {
               m9[p][i] = fmaxf(fmaxf(hmax[as][p][i], hmax[bs][p][i]), hmax[cs][p][i]);
               n9[p][i] = fminf(fminf(hmin[as][p][i], hmin[bs][p][i]), hmin[cs][p][i]);
             }
-          bool maybe[ND][2], any = false;
+          bool maybe[ND][ST_PX], any = false;
 #pragma unroll
           for (int s = 1; s < ND - 1; s++) {                 // background.js:377
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < ST_PX; i++) {
               const float c = cen[bs][s][i];
               const float m27 = fmaxf(fmaxf(m9[s - 1][i], m9[s][i]), m9[s + 1][i]);
               const float n27 = fminf(fminf(n9[s - 1][i], n9[s][i]), n9[s + 1][i]);
@@ -400,7 +415,7 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
 #pragma unroll
             for (int s = 1; s < ND - 1; s++)
 #pragma unroll
-              for (int i = 0; i < 2; i++) {
+              for (int i = 0; i < ST_PX; i++) {
                 const float c = cen[bs][s][i];
                 bool e = false;
                 if (maybe[s][i] && row_ok) {                 // exact strict test of the 26 neighbours
@@ -498,7 +513,7 @@ void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_map
   if (total == 0) return;
   const int nd = spo + 2;
   const size_t smem = (size_t)ST_STAGES * nd * ST_PLANE * sizeof(float);
-  const int grid = (ST_STAGES == 1 || total < 148 * 2) ? total : 148 * 2;      // persistent: two CTAs per SM
+  const int grid = (ST_STAGES == 1 || total < 148 * ST_CTAS_PER_SM) ? total : 148 * ST_CTAS_PER_SM;      // persistent CTAs when double-buffered
   const CUtensorMap *maps = (const CUtensorMap *)d_maps;
 #define LAUNCH_ND(N)                                                                                         \
   case N:                                                                                                    \
