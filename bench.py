@@ -36,8 +36,8 @@ METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200
 W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
 FRAMES = 16                    # frames per GPU per step (distinct seeds)
-# dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0.txt), ncu --set full
-NCU_TRAFFIC_OCT0_BYTES = 332.6e6
+# dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0_1.txt), ncu --set full
+NCU_TRAFFIC_OCT0_BYTES = 333.5e6
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
 CPU_TILE = 256                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
@@ -336,7 +336,7 @@ def run_own(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_OCT0_BYTES, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of fused_octave0_kernel, "
-                                           "ncu --set full, profiles/r01_ncu_fused_octave0.txt",
+                                           "ncu --set full, profiles/r01_ncu_fused_octave0_1.txt",
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "whole_path": {"algorithmic_bytes_per_input_px": ab["total"],
                                         "achieved": whole_gbs, "frac": whole_gbs / peak},
