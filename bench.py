@@ -39,7 +39,7 @@ FRAMES = 16                    # frames per GPU per step (distinct seeds)
 # dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0_1.txt), ncu --set full
 NCU_TRAFFIC_OCT0_BYTES = 333.5e6
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
-CPU_TILE = 256                 # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
+CPU_TILE = int(os.environ.get("SIFT_BENCH_CPU_TILE", "256"))   # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
 
 def algorithmic_bytes_per_input_px(n_oct: int = N_OCT) -> dict:
