@@ -25,6 +25,7 @@
 // samples (static rotation, no moves): every loaded sample feeds 16 DFMAs, the hot
 // code is a few KB (a first version unrolled per radius stalled 32 % on instruction
 // fetch), and any radius <= 16 runs the same code.
+#include <cstdlib>
 #include "common.cuh"
 
 #define F0_SW 32
@@ -88,17 +89,18 @@ __device__ __forceinline__ double src0_at(const Fused0Args &A, const char *p)
       a0[k] = fma(c.x, vw[(k + (U)) & 7], a0[k]);                                           \
       a1[k] = fma(c.y, vw[(k + (U)) & 7], a1[k]);                                           \
     }                                                                                       \
-    vw[(U) & 7] = nxt[(JJ) * stride];                                                       \
+    vw[(U) & 7] = (double)nxt[(JJ) * stride];                                                       \
   }
-__device__ __forceinline__ void poly_window(const double *__restrict__ base, const int stride,
+template <typename TS>
+__device__ __forceinline__ void poly_window(const TS *__restrict__ base, const int stride,
                                             const double *__restrict__ w, const int n, double (&a0)[8],
                                             double (&a1)[8])
 {
   const double2 *__restrict__ w2 = reinterpret_cast<const double2 *>(w);
   double vw[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) { vw[k] = base[k * stride]; a0[k] = 0.0; a1[k] = 0.0; }
-  const double *nxt = base + 8 * stride;
+  for (int k = 0; k < 8; k++) { vw[k] = (double)base[k * stride]; a0[k] = 0.0; a1[k] = 0.0; }
+  const TS *nxt = base + 8 * stride;
   int j = 0;
   for (; j + 8 <= n; j += 8) {
 #pragma unroll
@@ -263,6 +265,131 @@ fused_octave0_kernel(const double *__restrict__ weights, const Fused0Args A)
   }
 }
 
+// ---- the same tile computation at 3 CTAs per SM (u8 / f32 sources) ---------------------------------------
+// The kernel above needs 128 registers (16 accumulators x 2 phases, the window, and the previous level's 16
+// unrounded values for the DoG): 2 CTAs = 16 warps per SM.  Here the previous level lives in shared memory
+// ([16][256] doubles, conflict-free), the source tile is stored as float (u8 and f32 samples are exact in
+// float; for u8 the 1/255 of image-utils.js:114 is folded into the H-pass taps), and one Ts buffer is used:
+// 73 KB and <= 85 registers -> 3 CTAs = 24 warps per SM.
+#define F0H_S_FLOATS (F0_SROWS * F0_SPITCH)                         // 2352 floats
+#define F0H_TS_OFF ((F0H_S_FLOATS / 2 + 1) & ~1)                    // in doubles, 16-byte aligned
+#define F0H_WV_OFF (F0H_TS_OFF + ((F0_TROWS * F0_TPITCH + 1) & ~1))
+#define F0H_WH_OFF(nlev) (F0H_WV_OFF + (nlev) * 2 * F0_WSTRIDE)
+#define F0H_P_OFF(nlev) (F0H_WH_OFF(nlev) + (nlev) * 2 * F0_WSTRIDE)
+#define F0H_DOUBLES(nlev) (F0H_P_OFF(nlev) + 16 * F0_THREADS)
+
+__global__ void __launch_bounds__(F0_THREADS, 3)
+fused_octave0_hi_kernel(const double *__restrict__ weights, const Fused0Args A)
+{
+  extern __shared__ double smem[];
+  float *S = reinterpret_cast<float *>(smem);           // [48][49] source tile (exact u8 / f32 values)
+  double *Ts = smem + F0H_TS_OFF;                        // [49][65] horizontally blurred rows, both phases
+  double *Wv = smem + F0H_WV_OFF;                        // V-pass taps [nlev][F0_WSTRIDE]{w0, w1}
+  double *Wh = smem + F0H_WH_OFF(A.nlev);                // H-pass taps (scaled by 1/255 for u8 sources)
+  double *P = smem + F0H_P_OFF(A.nlev);                  // previous level, unrounded: P[k * 256 + tid]
+  const int tid = threadIdx.x;
+  const int a_tile = blockIdx.x * F0_SW, b_tile = blockIdx.y * F0_SH;
+
+  {
+    const double hscale = A.dtype == SIFT_U8 ? 1.0 / 255.0 : 1.0;
+    for (int e = tid; e < A.nlev * 2 * F0_WSTRIDE; e += F0_THREADS) {
+      const double wv = __ldg(weights + A.woff + e);
+      Wv[e] = wv;
+      Wh[e] = wv * hscale;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) {                          // 48*48 samples, 9 per thread
+    const int e = tid + i * F0_THREADS;
+    const int rr = e / F0_SCOLS, cc = e - rr * F0_SCOLS;
+    const int gy = min(max(b_tile - F0_HALO + rr, 0), A.src_h - 1);          // clamp-to-edge, sift.js:116-119
+    const int gx = min(max(a_tile - F0_HALO + cc, 0), A.src_w - 1);
+    const char *row = (const char *)A.src + (size_t)gy * A.src_pitch;
+    S[rr * F0_SPITCH + cc] = A.dtype == SIFT_U8 ? (float)__ldg((const unsigned char *)row + gx) : __ldg((const float *)row + gx);
+  }
+  for (int e = tid; e < F0_TPITCH; e += F0_THREADS) Ts[(F0_TROWS - 1) * F0_TPITCH + e] = 0.0;    // slack row
+  if (tid < F0_SROWS) S[tid * F0_SPITCH + F0_SCOLS] = 0.f;                                       // pad column
+
+  // V-pass ownership: output column X of the tile, source rows 8*rg .. 8*rg+7, both row phases
+  const int X = tid & (2 * F0_SW - 1), rg = tid / (2 * F0_SW);
+  const int x = 2 * a_tile + X;
+  const int w = A.oct.w, h = A.oct.h;
+  const int y_first = 2 * (b_tile + 8 * rg);
+  const size_t o_first = (size_t)y_first * A.oct.pitch + x;
+  const bool col_ok = x < w;
+  const bool rows_full = y_first + 16 <= h;
+  const bool seed_lane = A.has_next && (X & 1) == 0 && col_ok;
+  double *Pt = P + tid;
+
+  for (int s = 0; s < A.nlev; s++) {                     // octave 0 blurs every level from the base (background.js:110)
+    const int R = A.radius[s];
+    const int clo0 = -((R + 1) / 2);
+    const int n = R + 1 + (R & 1);                       // taps per phase incl. the phase-1 shift for odd R
+    __syncthreads();                                     // source tile ready (s = 0) / Ts free again (s > 0)
+    {                                                    // ---- H pass: one row x 8 source columns x 2 phases per item
+      const int nrows = F0_SH + n - 1;
+      if (tid < nrows * (F0_SW / 8)) {
+        const int g = (tid >= nrows) + (tid >= 2 * nrows) + (tid >= 3 * nrows), rr = F0_HALO + clo0 + (tid - g * nrows);
+        double a0[8], a1[8];
+        poly_window<float>(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, Wh + s * 2 * F0_WSTRIDE, n, a0, a1);
+        double *t = Ts + rr * F0_TPITCH + 16 * g;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { t[2 * k] = a0[k]; t[2 * k + 1] = a1[k]; }
+      }
+    }
+    __syncthreads();
+    // ---- V pass
+    double a0[8], a1[8];
+    poly_window<double>(Ts + (F0_HALO + 8 * rg + clo0) * F0_TPITCH + X, F0_TPITCH, Wv + s * 2 * F0_WSTRIDE, n, a0, a1);
+    // ---- epilogue: G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) against the unrounded previous level in P
+    if (col_ok) {
+      float *gp = A.oct.gauss[s] + o_first;
+      float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o_first;
+      const size_t rowp = (size_t)A.oct.pitch;
+      const bool wg = A.keep_gauss != 0, wd = s > 0;
+      if (rows_full) {
+        if (wg) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) { *gp = (float)a0[k]; gp += rowp; *gp = (float)a1[k]; gp += rowp; }
+        }
+        if (wd) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            *dp = (float)(Pt[(2 * k) * F0_THREADS] - a0[k]); dp += rowp;
+            *dp = (float)(Pt[(2 * k + 1) * F0_THREADS] - a1[k]); dp += rowp;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            if (y_first + 2 * k + q < h) {
+              const double v = q ? a1[k] : a0[k];
+              if (wg) gp[(size_t)(2 * k + q) * rowp] = (float)v;
+              if (wd) dp[(size_t)(2 * k + q) * rowp] = (float)(Pt[(2 * k + q) * F0_THREADS] - v);
+            }
+          }
+        }
+      }
+      if (s == A.spo && seed_lane) {                     // in[2a][2b] (matrix2d.js:129): even rows (phase 0), even columns
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int nr = b_tile + 8 * rg + k + A.oct.seed_off;        // row of the next octave (strip-local)
+          if (y_first + 2 * k < h && nr >= 0 && nr < A.next.h) {
+            A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = a0[k];
+            A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)a0[k];
+          }
+        }
+      }
+    }
+    if (s + 1 < A.nlev) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { Pt[(2 * k) * F0_THREADS] = a0[k]; Pt[(2 * k + 1) * F0_THREADS] = a1[k]; }
+    }
+  }
+}
+
 // Host: zero-padded merged polyphase taps of one level, the two phases interleaved: out[F0_WSTRIDE]{w0, w1}.
 //   phase 0: w0[j] = W0[j], j = c - floor(-R/2);  phase 1: w1[j + d] = W0[R - j], d = R & 1.
 void fused0_merge_taps(const double *w, int R, double *out)
@@ -303,6 +430,15 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
   A.woff = poly_woff;
   A.u8lut = d_u8lut;
   dim3 grid((src_w + F0_SW - 1) / F0_SW, (src_h + F0_SH - 1) / F0_SH);
+  static const bool no_hi = getenv("SIFT_B200_FUSED0_LO") != nullptr;
+  if (!no_hi && (dtype == SIFT_U8 || dtype == SIFT_F32)) {
+    const size_t smem_hi = (size_t)F0H_DOUBLES(nlev) * sizeof(double);
+    if (smem_hi <= 75 * 1024) {
+      cudaFuncSetAttribute(fused_octave0_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hi);
+      fused_octave0_hi_kernel<<<grid, F0_THREADS, smem_hi, st>>>(d_weights, A);
+      return;
+    }
+  }
   const size_t smem = (size_t)(F0_SROWS * F0_SPITCH + 2 * F0_TROWS * F0_TPITCH + nlev * 2 * F0_WSTRIDE) * sizeof(double);
   cudaFuncSetAttribute(fused_octave0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fused_octave0_kernel<<<grid, F0_THREADS, smem, st>>>(d_weights, A);
