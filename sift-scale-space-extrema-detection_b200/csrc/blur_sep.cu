@@ -41,7 +41,12 @@ struct FirArgs {
   // ---- output
   int mode;              // 0: T^T planes, 1: Gaussian / DoG / seed
   double *T[SIFT_MAX_LEVELS];
-  size_t t_pitch;        // doubles per T^T line
+  size_t t_pitch;        // doubles per T^T line, pads included
+  int t_off;             // sample 0 of a line sits t_off doubles into it: [t_off - padL, t_off) and [t_off + n, pitch) are
+                         // clamp-to-edge replicas written by pass A, so pass B never clamps (and can use TMA)
+  int t_padl, t_padr;
+  int t_pads;            // pass A writes the pads / pass B relies on them (only when pass B runs the TMA kernel)
+  const void *tmaps;     // pass B: one CUtensorMap per level over its T^T plane (box = level's span x 32 lines), or null
   OctaveDev oct, next;
   int has_next, spo, keep_gauss, seed_is_level0;
 };
@@ -51,14 +56,14 @@ struct FirArgs {
 // group are fetched (2 x LDS.128, broadcast) while the current group is consumed, the window of NO samples
 // rotates through registers with compile-time indices, and the accumulators never change registers.
 // Positions up to npad + NO - 1 are read.
-template <int NO>
+template <int NO, int STRIDE>
 __device__ __forceinline__ void fir_window(const double *__restrict__ w, const int npad,
                                            const double *__restrict__ base, double (&a)[NO])
 {
   double vw[NO];
 #pragma unroll
-  for (int k = 0; k < NO; k++) { vw[k] = base[k * FP_PITCH]; a[k] = 0.0; }
-  const double *nxt = base + NO * FP_PITCH;
+  for (int k = 0; k < NO; k++) { vw[k] = base[k * STRIDE]; a[k] = 0.0; }
+  const double *nxt = base + NO * STRIDE;
   double2 wa = *reinterpret_cast<const double2 *>(w), wb = *reinterpret_cast<const double2 *>(w + 2);
 #define FIR_GROUP(G)                                                                              \
   {                                                                                               \
@@ -67,7 +72,7 @@ __device__ __forceinline__ void fir_window(const double *__restrict__ w, const i
     wb = *reinterpret_cast<const double2 *>(w + j + 4 * (G) + 6);                                 \
     _Pragma("unroll") for (int u = 0; u < 4; u++) {                                               \
       _Pragma("unroll") for (int k = 0; k < NO; k++) a[k] = fma(c[u], vw[(k + 4 * (G) + u) & (NO - 1)], a[k]); \
-      vw[(4 * (G) + u) & (NO - 1)] = nxt[(j + 4 * (G) + u) * FP_PITCH];                            \
+      vw[(4 * (G) + u) & (NO - 1)] = nxt[(j + 4 * (G) + u) * STRIDE];                              \
     }                                                                                             \
   }
   int j = 0;
@@ -113,12 +118,12 @@ __device__ __forceinline__ void fir_stage(const FirArgs &A, const void *src, dou
                                           int b_first, int span, int lane, int warp)
 {
   if (A.src_kind == SIFT_F64 && !A.ups) {
-    const bool interior = b_first >= 0 && b_first + span <= A.nb;
+    const bool interior = (b_first >= 0 && b_first + span <= A.nb) || (A.mode == 1 && A.t_pads);   // T^T lines carry clamp pads
 #pragma unroll
     for (int i = 0; i < FP_LINES / NW; i++) {
       const int al = warp + i * NW;
       const int a = min(a0 + al, A.na - 1);                 // lines past the end replicate the last one (never stored)
-      const double *line = (const double *)((const char *)src + (size_t)a * A.in_pitch);
+      const double *line = (const double *)((const char *)src + (size_t)a * A.in_pitch) + (A.mode == 1 ? A.t_off : 0);
       double *dst = tile + lane * FP_PITCH + al;
       if (interior) {
         const double *p = line + b_first + lane;
@@ -140,7 +145,7 @@ __device__ __forceinline__ void fir_stage(const FirArgs &A, const void *src, dou
   } else {
     for (int al = warp; al < FP_LINES; al += NW) {
       const int a = min(a0 + al, A.na - 1);
-      const char *line = (const char *)src + (size_t)a * A.in_pitch;
+      const char *line = (const char *)src + (size_t)a * A.in_pitch + (A.mode == 1 ? (size_t)A.t_off * sizeof(double) : 0);
       for (int e = lane; e < span; e += 32) {
         int b = min(max(b_first + e, 0), A.nb - 1);
         if (A.ups) b = min(b >> 1, A.in_nb - 1);             // matrix2d.js:129 floor(j * 0.5)
@@ -169,8 +174,8 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
   double *tile0 = smem + A.wtotal;                          // [span][FP_PITCH]
   double *tile1 = tile0 + (size_t)(NW * NO + 2 * A.rmax + FIR_SLACK(NO)) * FP_PITCH;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int a0 = blockIdx.y * FP_LINES;
-  const int b_tile = blockIdx.x * (NW * NO);
+  const int a0 = (MODE == 0 ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y) * FP_LINES;   // pass A: the row that writes
+  const int b_tile = blockIdx.x * (NW * NO);                                                     // the right pads goes first
   constexpr bool per_level = MODE == 1;
 
   {
@@ -185,13 +190,14 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
 
   const int a = a0 + lane;
   const int b0 = b_tile + warp * NO;
-  const bool active = a < A.na && b0 < A.nb;
+  const bool active = b0 < A.nb;                           // warp-uniform
+  const bool line_ok = a < A.na;                           // lanes past the last line compute on its replica, store nothing
   const bool full = b0 + NO <= A.nb;                       // warp-uniform
 
   double prev[NO];
 #pragma unroll
   for (int k = 0; k < NO; k++) prev[k] = 0.0;
-  if (per_level && A.seed_is_level0 && active) {             // octaves >= 1: level 0 is the unblurred seed
+  if (per_level && A.seed_is_level0 && active && line_ok) {  // octaves >= 1: level 0 is the unblurred seed
 #pragma unroll
     for (int k = 0; k < NO; k++) prev[k] = A.oct.seed64[(size_t)min(b0 + k, A.nb - 1) * A.oct.w + a];
   }
@@ -210,17 +216,38 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
     if (per_level || li == 0) __syncthreads();               // the tile (and, first time, the taps) visible to the CTA
     if (active) {
       double acc[NO];
-      fir_window<NO>(wsm + wo, npad, cur + (warp * NO + (per_level ? 0 : A.rmax - R)) * FP_PITCH + lane, acc);
+      fir_window<NO, FP_PITCH>(wsm + wo, npad, cur + (warp * NO + (per_level ? 0 : A.rmax - R)) * FP_PITCH + lane, acc);
       if (!per_level) {
-        double *out = A.T[li] + (size_t)b0 * A.t_pitch + a;
+        double *out = A.T[li] + (size_t)b0 * A.t_pitch + A.t_off + a;
         const size_t tp = A.t_pitch;
-        if (full) {
+        if (full && line_ok) {
 #pragma unroll
           for (int k = 0; k < NO; k++) { *out = acc[k]; out += tp; }       // running pointer: two adds per store
-        } else {
+        } else if (line_ok) {
 #pragma unroll
           for (int k = 0; k < NO; k++)
             if (b0 + k < A.nb) out[(size_t)k * tp] = acc[k];
+        }
+        // clamp-to-edge replicas beyond the first / last line (sift.js:118-119), so that pass B reads plain
+        // tiles: the warp holding line 0 (resp. na-1) writes the left (right) pad of its NO columns
+        if (A.t_pads && (a0 == 0 || a0 + FP_LINES >= A.na)) {
+          const unsigned m = 0xffffffffu;
+          const int last = A.na - 1 - a0;                      // lane of the last line, if it is in this CTA
+          double *line0 = A.T[li] + (size_t)b0 * A.t_pitch + A.t_off;
+#pragma unroll
+          for (int k = 0; k < NO; k++) {                       // static indices: acc stays in registers
+            if (b0 + k >= A.nb) continue;
+            double *ln = line0 + (size_t)k * tp;
+            if (a0 == 0) {
+              const double v0 = __shfl_sync(m, acc[k], 0);
+              for (int p = lane; p < A.rmax + 2; p += 32) ln[-1 - p] = v0;      // taps reach rmax (+1: even-aligned boxes) before line 0
+            }
+            if (last >= 0 && last < FP_LINES) {
+              const double v1 = __shfl_sync(m, acc[k], last);
+              for (int p = lane; p < A.rmax + 8; p += 32) ln[A.na + p] = v1;    // ... and rmax (+ zero-padded taps) past the last one;
+                                                                                   // what lies beyond only feeds outputs that are never stored
+            }
+          }
         }
       } else {
         // G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded accumulators, seed of the next octave
@@ -229,7 +256,7 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
         const size_t o = (size_t)b0 * pitch + a;
         float *gp = A.oct.gauss[s] + o;
         float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o;
-        if (full) {
+        if (full && line_ok) {
           if (A.keep_gauss) {
 #pragma unroll
             for (int k = 0; k < NO; k++) { *gp = (float)acc[k]; gp += pitch; }
@@ -238,7 +265,7 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
 #pragma unroll
             for (int k = 0; k < NO; k++) { *dp = (float)(prev[k] - acc[k]); dp += pitch; }
           }
-        } else {
+        } else if (line_ok) {
 #pragma unroll
           for (int k = 0; k < NO; k++) {
             if (b0 + k < A.nb) {
@@ -247,7 +274,7 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
             }
           }
         }
-        if (A.has_next && s == A.spo && (a & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
+        if (A.has_next && s == A.spo && (a & 1) == 0 && line_ok) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
 #pragma unroll
           for (int k = 0; k < NO; k += 2) {
             const int nr = ((b0 + k) >> 1) + A.oct.seed_off;     // row of the next octave (strip-local)
@@ -263,6 +290,140 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
     }
     wo += npad + 4;
     if (per_level) __syncthreads();                          // `cur` is overwritten by the copy issued next iteration
+  }
+}
+
+// ---- pass B with TMA tile loads ---------------------------------------------------------------------------
+// The T^T planes carry clamp pads, so the tile a CTA needs for level s -- 32 lines x (outputs + 2 R_s) samples --
+// is a plain box: ONE cp.async.bulk.tensor.2d per level, issued by one thread a level ahead and completed on
+// an mbarrier, replaces ~25 cp.async + address arithmetic per thread per level.  The box lands line-major
+// ([line][sample], dense): a lane walks its own line with unit stride, the row length is chosen = 2 (mod 4)
+// doubles so that the 32 lanes of a load fall on 8 bank pairs (2-way conflicts on one load per 16 DFMAs).
+#include <cuda.h>
+
+__device__ __forceinline__ unsigned fir_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// The box starts (radius rounded up to even) samples before the tile, so that its first sample is 16-byte aligned.
+__host__ __device__ __forceinline__ int fir_box_halo(int radius) { return (radius + 1) & ~1; }
+
+__host__ __device__ __forceinline__ int fir_box_span(int outputs, int radius, int no)
+{
+  const int span = outputs + 2 * fir_box_halo(radius) + FIR_SLACK(no);
+  return span + ((2 - (span & 3)) & 3);                     // smallest s >= span with s % 4 == 2
+}
+
+template <int NW, int NO>
+__global__ void __launch_bounds__(32 * NW, 2)
+fir_pass_b_tma_kernel(const double *__restrict__ weights, const FirArgs A)
+{
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long bar[2];
+  const int span_max = fir_box_span(NW * NO, A.rmax, NO);
+  const int buf_doubles = (FP_LINES * span_max + 15) & ~15;  // 128-byte multiples: TMA destinations
+  double *buf0 = smem, *buf1 = smem + buf_doubles;
+  double *wsm = smem + 2 * buf_doubles;                     // per level: taps zero-padded to a multiple of 4 (+ one zero group)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a0 = blockIdx.y * FP_LINES;
+  const int b_tile = blockIdx.x * (NW * NO);
+  const CUtensorMap *maps = (const CUtensorMap *)A.tmaps;
+
+  auto issue = [&](int li) {                                // one thread: arm the barrier, one box
+    const int R = A.radius[li];
+    const unsigned bytes = (unsigned)(FP_LINES * fir_box_span(NW * NO, R, NO) * sizeof(double));
+    const unsigned b = fir_smem_u32(&bar[li & 1]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(fir_smem_u32((li & 1) ? buf1 : buf0)), "l"(maps + li), "r"(b), "r"(A.t_off + b_tile - fir_box_halo(R)), "r"(a0)
+        : "memory");
+  };
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fir_smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fir_smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int li = 0, wo = 0; li < A.nlev; li++) {
+    const int n = 2 * A.radius[li] + 1, npad = ((n + 3) & ~3) + 4;
+    for (int e = threadIdx.x; e < npad; e += 32 * NW) wsm[wo + e] = e < n ? __ldg(weights + A.woff[li] + e) : 0.0;
+    wo += npad;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) issue(0);
+
+  const int a = a0 + lane;
+  const int b0 = b_tile + warp * NO;
+  const bool active = b0 < A.nb;                           // warp-uniform
+  const bool line_ok = a < A.na;                           // lines past the end are zero-filled by the TMA unit
+  const bool full = b0 + NO <= A.nb;
+
+  double prev[NO];
+#pragma unroll
+  for (int k = 0; k < NO; k++) prev[k] = 0.0;
+  if (A.seed_is_level0 && active && line_ok) {               // octaves >= 1: level 0 is the unblurred seed
+#pragma unroll
+    for (int k = 0; k < NO; k++) prev[k] = A.oct.seed64[(size_t)min(b0 + k, A.nb - 1) * A.oct.w + a];
+  }
+
+  int wo = 0;
+  for (int li = 0; li < A.nlev; li++) {
+    const int R = A.radius[li], npad = (2 * R + 4) & ~3;
+    // the other buffer was released by the barrier that ended level li-1: fill it with level li+1
+    if (threadIdx.x == 0 && li + 1 < A.nlev) issue(li + 1);
+    {
+      const unsigned parity = (li >> 1) & 1;
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(fir_smem_u32(&bar[li & 1])), "r"(parity) : "memory");
+      }
+    }
+    if (active) {
+      const double *cur = (li & 1) ? buf1 : buf0;
+      double acc[NO];
+      fir_window<NO, 1>(wsm + wo, npad, cur + lane * fir_box_span(NW * NO, R, NO) + warp * NO + (fir_box_halo(R) - R), acc);
+      // G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded accumulators, seed of the next octave
+      const int s = A.level[li];
+      const size_t pitch = (size_t)A.oct.pitch;
+      const size_t o = (size_t)b0 * pitch + a;
+      float *gp = A.oct.gauss[s] + o;
+      float *dp = A.oct.dog[s > 0 ? s - 1 : 0] + o;
+      if (full && line_ok) {
+        if (A.keep_gauss) {
+#pragma unroll
+          for (int k = 0; k < NO; k++) { *gp = (float)acc[k]; gp += pitch; }
+        }
+        if (s > 0) {
+#pragma unroll
+          for (int k = 0; k < NO; k++) { *dp = (float)(prev[k] - acc[k]); dp += pitch; }
+        }
+      } else if (line_ok) {
+#pragma unroll
+        for (int k = 0; k < NO; k++) {
+          if (b0 + k < A.nb) {
+            if (A.keep_gauss) gp[(size_t)k * pitch] = (float)acc[k];
+            if (s > 0) dp[(size_t)k * pitch] = (float)(prev[k] - acc[k]);
+          }
+        }
+      }
+      if (A.has_next && s == A.spo && (a & 1) == 0 && line_ok) {   // matrix2d.js:129 in[2a][2b]: even rows, even columns
+#pragma unroll
+        for (int k = 0; k < NO; k += 2) {
+          const int nr = ((b0 + k) >> 1) + A.oct.seed_off;     // row of the next octave (strip-local)
+          if (b0 + k < A.nb && nr >= 0 && nr < A.next.h) {
+            A.next.seed64[(size_t)nr * A.next.w + (a >> 1)] = acc[k];
+            A.next.gauss[0][(size_t)nr * A.next.pitch + (a >> 1)] = (float)acc[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NO; k++) prev[k] = acc[k];
+    }
+    wo += npad + 4;
+    __syncthreads();                                         // this buffer may be refilled (level li+2)
   }
 }
 
@@ -285,10 +446,31 @@ static size_t fir_smem_bytes(int wtotal_padded, int rmax, FirShape sh, int tiles
   return ((size_t)wtotal_padded + (size_t)tiles * span * FP_PITCH) * sizeof(double);
 }
 
-size_t sep_t_pitch(int nb_stored) { return (size_t)((nb_stored + 3) & ~3); }
+// T^T line layout: [left pad | nb samples | right pad], pads = clamp replicas written by pass A.
+struct TLayout { size_t pitch; int off, padl, padr; };
+static TLayout sep_t_layout(int nb_stored, int rmax, FirShape sh)
+{
+  TLayout t;
+  t.padl = (rmax + 15) & ~15;                                         // sample 0 of every line on a 128-byte boundary:
+  t.padr = (sh.nw * sh.no + rmax + FIR_SLACK(sh.no) + 8 + 1) & ~1;    // pass A's stores (32 lanes x 8 B) stay sector-aligned
+  t.off = t.padl;                                                     // padr: last (partial) tile + halo + window / tap slack
+  t.pitch = (size_t)((t.padl + nb_stored + t.padr + 15) & ~15);
+  return t;
+}
+
+static int level_rmax(const LevelPlan *plans, int first_level, int nlev)
+{
+  int rmax = 0;
+  for (int s = first_level; s < nlev; s++) rmax = max(rmax, plans[s].radius);
+  return rmax;
+}
 
 // Doubles of intermediate storage the two passes need for one octave (all blurred levels).
-size_t sep_t_elems(int w, int trows, int n_levels) { return (size_t)n_levels * w * sep_t_pitch(trows); }
+size_t sep_t_elems(int w, int h, int trows, const LevelPlan *plans, int first_level, int nlev)
+{
+  const TLayout t = sep_t_layout(trows, level_rmax(plans, first_level, nlev), fir_shape(w, h));
+  return (size_t)(nlev - first_level) * w * t.pitch;
+}
 
 static int padded_taps(int radius) { return ((2 * radius + 4) & ~3) + 4; }
 
@@ -299,8 +481,11 @@ bool sep_supported(const LevelPlan *plans, int first_level, int nlev, int w, int
   return fir_smem_bytes(wtotal, rmax, fir_shape(w, h), 2) <= 220 * 1024;
 }
 
-static void fill_levels(FirArgs &A, const LevelPlan *plans, int first_level, int nlev, double *tbase, size_t plane)
+static void fill_levels(FirArgs &A, const LevelPlan *plans, int first_level, int nlev, double *tbase, int w, int h, int trows)
 {
+  const TLayout t = sep_t_layout(trows, level_rmax(plans, first_level, nlev), fir_shape(w, h));
+  const size_t plane = (size_t)w * t.pitch;
+  A.t_pitch = t.pitch; A.t_off = t.off; A.t_padl = t.padl; A.t_padr = t.padr;
   A.nlev = nlev - first_level;
   A.rmax = 0; A.wtotal = 0;
   for (int i = 0; i < A.nlev; i++) {
@@ -334,32 +519,97 @@ static void fir_dispatch(cudaStream_t st, const double *d_weights, const FirArgs
 // pass A: base (seed64 of octaves >= 1, or the source image doubled along x for a generic octave 0) -> T^T
 void launch_sep_pass_a(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int upsample,
                        int w, int hrows, int h, const double *d_weights, const LevelPlan *plans, int first_level,
-                       int nlev, double *tbase)
+                       int nlev, double *tbase, int write_pads)
 {
   FirArgs A;
   memset(&A, 0, sizeof A);
   A.src = src; A.src_kind = dtype; A.in_pitch = src_pitch_bytes; A.in_nb = src_w;
   A.na = hrows; A.nb = w; A.ups = upsample;
   A.mode = 0;
-  A.t_pitch = sep_t_pitch(hrows);
-  fill_levels(A, plans, first_level, nlev, tbase, (size_t)w * A.t_pitch);
+  A.t_pads = write_pads;
+  fill_levels(A, plans, first_level, nlev, tbase, w, h, hrows);
   fir_dispatch<0>(st, d_weights, A, fir_shape(w, h));
 }
 
+// One CUtensorMap per blurred level over its T^T plane (fp64, [w lines][pitch]), box = level's span x 32 lines.
+// Returns the number of maps written (0: TMA path not usable for this octave).
+typedef CUresult (*FirEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+size_t sep_tma_map_bytes(int n_levels) { return (size_t)n_levels * sizeof(CUtensorMap); }
+
+int sep_tma_build_maps(const LevelPlan *plans, int first_level, int nlev, double *tbase, int w, int h, int trows, void *h_maps)
+{
+  static FirEncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+      return 0;
+    encode = (FirEncodeTiledFn)fn;
+  }
+  const FirShape sh = fir_shape(w, h);
+  const int rmax = level_rmax(plans, first_level, nlev);
+  const TLayout t = sep_t_layout(trows, rmax, sh);
+  if (fir_box_span(sh.nw * sh.no, rmax, sh.no) > 256) return 0;           // TMA boxes are at most 256 elements wide
+  CUtensorMap *maps = (CUtensorMap *)h_maps;
+  for (int i = 0; i < nlev - first_level; i++) {
+    const cuuint64_t gdim[2] = { (cuuint64_t)t.pitch, (cuuint64_t)w };
+    const cuuint64_t gstride[1] = { (cuuint64_t)t.pitch * sizeof(double) };
+    const cuuint32_t box[2] = { (cuuint32_t)fir_box_span(sh.nw * sh.no, plans[first_level + i].radius, sh.no), FP_LINES };
+    const cuuint32_t estride[2] = { 1, 1 };
+    // 64-bit elements: the driver has no FLOAT64 tile type restriction issue -- use FLOAT64
+    if (encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)(tbase + (size_t)i * w * t.pitch), gdim, gstride, box,
+               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 0;
+  }
+  return nlev - first_level;
+}
+
+// Whether pass B of an octave will run the TMA kernel (pass A must then write the clamp pads).
+bool sep_pass_b_uses_tma(const void *d_tmaps, int upsample)
+{
+  static const bool no_tma = getenv("SIFT_B200_NO_TMA") != nullptr || getenv("SIFT_B200_NO_TMA_BLUR") != nullptr;
+  return d_tmaps && !upsample && !no_tma;
+}
+
+template <int NW, int NO>
+static void fir_launch_tma(cudaStream_t st, const double *d_weights, const FirArgs &A)
+{
+  const int span_max = fir_box_span(NW * NO, A.rmax, NO);
+  const size_t smem = ((size_t)2 * ((FP_LINES * span_max + 15) & ~15) + A.wtotal) * sizeof(double);
+  dim3 grid((A.nb + NW * NO - 1) / (NW * NO), (A.na + FP_LINES - 1) / FP_LINES);
+  cudaFuncSetAttribute(fir_pass_b_tma_kernel<NW, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fir_pass_b_tma_kernel<NW, NO><<<grid, 32 * NW, smem, st>>>(d_weights, A);
+}
+
 // pass B: T^T -> Gaussian / DoG levels (+ next seed).  `upsample`: T holds hrows = h/2 source rows (generic octave 0).
+// d_tmaps: device array of this octave's tensor maps (sep_tma_build_maps), or null for the cp.async path.
 void launch_sep_pass_b(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
                        const LevelPlan *plans, int first_level, double *tbase, int hrows, const OctaveDev *next,
-                       int spo, int keep_gauss)
+                       int spo, int keep_gauss, const void *d_tmaps)
 {
   FirArgs A;
   memset(&A, 0, sizeof A);
   A.src = tbase; A.src_kind = SIFT_F64;
-  A.t_pitch = sep_t_pitch(hrows);
-  A.in_pitch = A.t_pitch * sizeof(double); A.in_nb = hrows;
+  A.in_nb = hrows;
   A.na = oct.w; A.nb = oct.h; A.ups = upsample;
   A.mode = 1;
   A.oct = oct; A.next = next ? *next : oct; A.has_next = next ? 1 : 0;
   A.spo = spo; A.keep_gauss = keep_gauss; A.seed_is_level0 = first_level > 0;
-  fill_levels(A, plans, first_level, oct.nlev, tbase, (size_t)oct.w * A.t_pitch);
-  fir_dispatch<1>(st, d_weights, A, fir_shape(oct.w, oct.h));
+  fill_levels(A, plans, first_level, oct.nlev, tbase, oct.w, oct.h, hrows);
+  A.in_pitch = A.t_pitch * sizeof(double);
+  const FirShape sh = fir_shape(oct.w, oct.h);
+  if (sep_pass_b_uses_tma(d_tmaps, upsample) && fir_box_span(sh.nw * sh.no, A.rmax, sh.no) <= 256) {
+    A.tmaps = d_tmaps;
+    A.t_pads = 1;
+    if (sh.no == 16) fir_launch_tma<8, 16>(st, d_weights, A);
+    else if (sh.nw == 8) fir_launch_tma<8, 8>(st, d_weights, A);
+    else fir_launch_tma<4, 8>(st, d_weights, A);
+    return;
+  }
+  fir_dispatch<1>(st, d_weights, A, sh);
 }

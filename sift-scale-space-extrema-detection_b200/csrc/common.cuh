@@ -72,13 +72,16 @@ void launch_seed_to_f32(cudaStream_t st, const double *seed, int w, int h, float
 
 // blur_sep.cu: pass A (along x) -> fp64 T^T planes -> pass B (along y), all levels of an octave per launch
 bool sep_supported(const LevelPlan *plans, int first_level, int nlev, int w, int h);
-size_t sep_t_elems(int w, int trows, int n_levels);
+size_t sep_t_elems(int w, int h, int trows, const LevelPlan *plans, int first_level, int nlev);
+size_t sep_tma_map_bytes(int n_levels);
+int sep_tma_build_maps(const LevelPlan *plans, int first_level, int nlev, double *tbase, int w, int h, int trows, void *h_maps);
 void launch_sep_pass_a(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int upsample,
                        int w, int hrows, int h, const double *d_weights, const LevelPlan *plans, int first_level,
-                       int nlev, double *tbase);
+                       int nlev, double *tbase, int write_pads);
+bool sep_pass_b_uses_tma(const void *d_tmaps, int upsample);
 void launch_sep_pass_b(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
                        const LevelPlan *plans, int first_level, double *tbase, int hrows, const OctaveDev *next,
-                       int spo, int keep_gauss);
+                       int spo, int keep_gauss, const void *d_tmaps);
 
 // blur_fused.cu
 void fused0_merge_taps(const double *w, int R, double *out /* fused0_taps_per_level() doubles */);

@@ -33,8 +33,9 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t;
   bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
+  int tma_blur[SIFT_MAX_OCTAVES];   // per octave: maps of its T^T planes start at tmaps_t[tma_blur[o]] (-1: none)
   int cand_cap = 0, kp_cap = 0;
   void *h_out = nullptr;       // pinned mirror of outbuf
   size_t h_out_cap = 0;
@@ -352,7 +353,7 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
     const size_t trows = (o == 0) ? (size_t)h : (size_t)oh[o];
     const size_t tl = (o == 0) ? nlev : nlev - 1;
     if (o > 0 || !ctx->fused0)
-      t_bytes = std::max(t_bytes, std::max(tl * trows * ow[o], sep_t_elems(ow[o], (int)trows, (int)tl)) * sizeof(double));
+      t_bytes = std::max(t_bytes, std::max(tl * trows * ow[o], sep_t_elems(ow[o], oh[o], (int)trows, ctx->plans[o], o == 0 ? 0 : 1, nlev)) * sizeof(double));
   }
   int rc = SIFT_OK;
   do {
@@ -397,6 +398,26 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
           break;
         }
         ln->tma_scan = true;
+      }
+    }
+    // TMA descriptors of the fp64 T^T planes (pass B of octaves >= 1); the planes of every octave alias tbuf
+    for (int o = 0; o < SIFT_MAX_OCTAVES; o++) ln->tma_blur[o] = -1;
+    if (!ctx->no_tma) {
+      std::vector<char> hm(sep_tma_map_bytes(n_oct * nlev));
+      int used = 0;
+      for (int o = 1; o < n_oct; o++) {
+        if (!sep_supported(ctx->plans[o], 1, nlev, ow[o], oh[o])) continue;
+        const int n = sep_tma_build_maps(ctx->plans[o], 1, nlev, (double *)ln->tbuf.p, ow[o], oh[o], oh[o],
+                                         hm.data() + sep_tma_map_bytes(used));
+        if (n > 0) { ln->tma_blur[o] = used; used += n; }
+      }
+      if (used > 0) {
+        if ((rc = grow(ctx, ln->tmaps_t, hm.size()))) break;
+        if (cudaMemcpyAsync(ln->tmaps_t.p, hm.data(), sep_tma_map_bytes(used), cudaMemcpyHostToDevice, ln->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ln->stream) != cudaSuccess) {
+          rc = fail(ctx, SIFT_ERR_CUDA, "upload of the blur TMA descriptors failed");
+          break;
+        }
       }
     }
     // candidate / keypoint capacity: extrema are ~3e-4 of the voxels on the synthetic frames
@@ -448,13 +469,15 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
   if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
     double *tb = (double *)ctx->L->tbuf.p;
+    const void *tm = (o > 0 && ctx->L->tma_blur[o] >= 0) ? (const char *)ctx->L->tmaps_t.p + sep_tma_map_bytes(ctx->L->tma_blur[o]) : nullptr;
+    const int pads = sep_pass_b_uses_tma(tm, o == 0) ? 1 : 0;
     if (o == 0)
       launch_sep_pass_a(st, d_image, dtype, pitch_bytes, ctx->in_w, 1, od.w, hrows, od.h, ctx->d_weights,
-                        ctx->plans[o], first, ctx->nlev, tb);
+                        ctx->plans[o], first, ctx->nlev, tb, pads);
     else
       launch_sep_pass_a(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, 0, od.w, hrows, od.h,
-                        ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb);
-    launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss);
+                        ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb, pads);
+    launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss, tm);
   } else {
     // radii too large for the staged tiles (octaves >= 4): row-major T, level-parallel kernels
     double *T[SIFT_MAX_LEVELS];
@@ -738,7 +761,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);
