@@ -41,11 +41,7 @@ struct FirArgs {
   // ---- output
   int mode;              // 0: T^T planes, 1: Gaussian / DoG / seed
   double *T[SIFT_MAX_LEVELS];
-  size_t t_pitch;        // doubles per T^T line, pads included
-  int t_off;             // sample 0 of a line sits t_off doubles into it: [t_off - padL, t_off) and [t_off + n, pitch) are
-                         // clamp-to-edge replicas written by pass A, so pass B never clamps (and can use TMA)
-  int t_padl, t_padr;
-  int t_pads;            // pass A writes the pads / pass B relies on them (only when pass B runs the TMA kernel)
+  size_t t_pitch;        // doubles per T^T line (multiple of 16: lines start on 128-byte boundaries)
   const void *tmaps;     // pass B: one CUtensorMap per level over its T^T plane (box = level's span x 32 lines), or null
   OctaveDev oct, next;
   int has_next, spo, keep_gauss, seed_is_level0;
@@ -118,12 +114,12 @@ __device__ __forceinline__ void fir_stage(const FirArgs &A, const void *src, dou
                                           int b_first, int span, int lane, int warp)
 {
   if (A.src_kind == SIFT_F64 && !A.ups) {
-    const bool interior = (b_first >= 0 && b_first + span <= A.nb) || (A.mode == 1 && A.t_pads);   // T^T lines carry clamp pads
+    const bool interior = b_first >= 0 && b_first + span <= A.nb;
 #pragma unroll
     for (int i = 0; i < FP_LINES / NW; i++) {
       const int al = warp + i * NW;
       const int a = min(a0 + al, A.na - 1);                 // lines past the end replicate the last one (never stored)
-      const double *line = (const double *)((const char *)src + (size_t)a * A.in_pitch) + (A.mode == 1 ? A.t_off : 0);
+      const double *line = (const double *)((const char *)src + (size_t)a * A.in_pitch);
       double *dst = tile + lane * FP_PITCH + al;
       if (interior) {
         const double *p = line + b_first + lane;
@@ -145,7 +141,7 @@ __device__ __forceinline__ void fir_stage(const FirArgs &A, const void *src, dou
   } else {
     for (int al = warp; al < FP_LINES; al += NW) {
       const int a = min(a0 + al, A.na - 1);
-      const char *line = (const char *)src + (size_t)a * A.in_pitch + (A.mode == 1 ? (size_t)A.t_off * sizeof(double) : 0);
+      const char *line = (const char *)src + (size_t)a * A.in_pitch;
       for (int e = lane; e < span; e += 32) {
         int b = min(max(b_first + e, 0), A.nb - 1);
         if (A.ups) b = min(b >> 1, A.in_nb - 1);             // matrix2d.js:129 floor(j * 0.5)
@@ -174,8 +170,8 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
   double *tile0 = smem + A.wtotal;                          // [span][FP_PITCH]
   double *tile1 = tile0 + (size_t)(NW * NO + 2 * A.rmax + FIR_SLACK(NO)) * FP_PITCH;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int a0 = (MODE == 0 ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y) * FP_LINES;   // pass A: the row that writes
-  const int b_tile = blockIdx.x * (NW * NO);                                                     // the right pads goes first
+  const int a0 = blockIdx.y * FP_LINES;
+  const int b_tile = blockIdx.x * (NW * NO);
   constexpr bool per_level = MODE == 1;
 
   {
@@ -218,7 +214,7 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
       double acc[NO];
       fir_window<NO, FP_PITCH>(wsm + wo, npad, cur + (warp * NO + (per_level ? 0 : A.rmax - R)) * FP_PITCH + lane, acc);
       if (!per_level) {
-        double *out = A.T[li] + (size_t)b0 * A.t_pitch + A.t_off + a;
+        double *out = A.T[li] + (size_t)b0 * A.t_pitch + a;
         const size_t tp = A.t_pitch;
         if (full && line_ok) {
 #pragma unroll
@@ -227,27 +223,6 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
 #pragma unroll
           for (int k = 0; k < NO; k++)
             if (b0 + k < A.nb) out[(size_t)k * tp] = acc[k];
-        }
-        // clamp-to-edge replicas beyond the first / last line (sift.js:118-119), so that pass B reads plain
-        // tiles: the warp holding line 0 (resp. na-1) writes the left (right) pad of its NO columns
-        if (A.t_pads && (a0 == 0 || a0 + FP_LINES >= A.na)) {
-          const unsigned m = 0xffffffffu;
-          const int last = A.na - 1 - a0;                      // lane of the last line, if it is in this CTA
-          double *line0 = A.T[li] + (size_t)b0 * A.t_pitch + A.t_off;
-#pragma unroll
-          for (int k = 0; k < NO; k++) {                       // static indices: acc stays in registers
-            if (b0 + k >= A.nb) continue;
-            double *ln = line0 + (size_t)k * tp;
-            if (a0 == 0) {
-              const double v0 = __shfl_sync(m, acc[k], 0);
-              for (int p = lane; p < A.rmax + 2; p += 32) ln[-1 - p] = v0;      // taps reach rmax (+1: even-aligned boxes) before line 0
-            }
-            if (last >= 0 && last < FP_LINES) {
-              const double v1 = __shfl_sync(m, acc[k], last);
-              for (int p = lane; p < A.rmax + 8; p += 32) ln[A.na + p] = v1;    // ... and rmax (+ zero-padded taps) past the last one;
-                                                                                   // what lies beyond only feeds outputs that are never stored
-            }
-          }
         }
       } else {
         // G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded accumulators, seed of the next octave
@@ -294,8 +269,8 @@ fir_pass_kernel(const double *__restrict__ weights, const FirArgs A)
 }
 
 // ---- pass B with TMA tile loads ---------------------------------------------------------------------------
-// The T^T planes carry clamp pads, so the tile a CTA needs for level s -- 32 lines x (outputs + 2 R_s) samples --
-// is a plain box: ONE cp.async.bulk.tensor.2d per level, issued by one thread a level ahead and completed on
+// The tile a CTA needs for level s -- 32 lines x (outputs + 2 R_s) samples of T_s^T -- is a plain box (the TMA unit
+// zero-fills what lies outside a line, border tiles then replicate the edge sample): ONE cp.async.bulk.tensor.2d per level, issued by one thread a level ahead and completed on
 // an mbarrier, replaces ~25 cp.async + address arithmetic per thread per level.  The box lands line-major
 // ([line][sample], dense): a lane walks its own line with unit stride, the row length is chosen = 2 (mod 4)
 // doubles so that the 32 lanes of a load fall on 8 bank pairs (2-way conflicts on one load per 16 DFMAs).
@@ -334,7 +309,7 @@ fir_pass_b_tma_kernel(const double *__restrict__ weights, const FirArgs A)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(fir_smem_u32((li & 1) ? buf1 : buf0)), "l"(maps + li), "r"(b), "r"(A.t_off + b_tile - fir_box_halo(R)), "r"(a0)
+        ::"r"(fir_smem_u32((li & 1) ? buf1 : buf0)), "l"(maps + li), "r"(b), "r"(b_tile - fir_box_halo(R)), "r"(a0)
         : "memory");
   };
 
@@ -381,10 +356,31 @@ fir_pass_b_tma_kernel(const double *__restrict__ weights, const FirArgs A)
             : "=r"(done) : "r"(fir_smem_u32(&bar[li & 1])), "r"(parity) : "memory");
       }
     }
+    const int pitch_l = fir_box_span(NW * NO, R, NO);
+    {
+      // clamp-to-edge (sift.js:118-119): the TMA unit zero-filled what lies before sample 0 / after sample nb-1;
+      // border tiles replicate the edge sample over those entries (each thread: its lane's line, entries warp, warp+NW ..)
+      double *cur = (li & 1) ? buf1 : buf0;
+      const int b_first = b_tile - fir_box_halo(R);
+      const bool left = b_first < 0, right = b_first + pitch_l > A.nb;        // CTA-uniform
+      if (left || right) {
+        double *ln = cur + lane * pitch_l;
+        if (left) {
+          const double v = ln[-b_first];
+          for (int e = warp; e < -b_first; e += NW) ln[e] = v;
+        }
+        if (right) {
+          const int last = A.nb - 1 - b_first;                                  // >= 0: the tile starts inside the line
+          const double v = ln[last];
+          for (int e = last + 1 + warp; e < pitch_l; e += NW) ln[e] = v;
+        }
+        __syncthreads();
+      }
+    }
     if (active) {
       const double *cur = (li & 1) ? buf1 : buf0;
       double acc[NO];
-      fir_window<NO, 1>(wsm + wo, npad, cur + lane * fir_box_span(NW * NO, R, NO) + warp * NO + (fir_box_halo(R) - R), acc);
+      fir_window<NO, 1>(wsm + wo, npad, cur + lane * pitch_l + warp * NO + (fir_box_halo(R) - R), acc);
       // G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded accumulators, seed of the next octave
       const int s = A.level[li];
       const size_t pitch = (size_t)A.oct.pitch;
@@ -446,17 +442,10 @@ static size_t fir_smem_bytes(int wtotal_padded, int rmax, FirShape sh, int tiles
   return ((size_t)wtotal_padded + (size_t)tiles * span * FP_PITCH) * sizeof(double);
 }
 
-// T^T line layout: [left pad | nb samples | right pad], pads = clamp replicas written by pass A.
-struct TLayout { size_t pitch; int off, padl, padr; };
-static TLayout sep_t_layout(int nb_stored, int rmax, FirShape sh)
-{
-  TLayout t;
-  t.padl = (rmax + 15) & ~15;                                         // sample 0 of every line on a 128-byte boundary:
-  t.padr = (sh.nw * sh.no + rmax + FIR_SLACK(sh.no) + 8 + 1) & ~1;    // pass A's stores (32 lanes x 8 B) stay sector-aligned
-  t.off = t.padl;                                                     // padr: last (partial) tile + halo + window / tap slack
-  t.pitch = (size_t)((t.padl + nb_stored + t.padr + 15) & ~15);
-  return t;
-}
+// T^T line layout: nb samples per line, lines on 128-byte boundaries (pass A's 32 x 8 B stores stay sector-aligned;
+// TMA needs 16-byte multiples).  No clamp pads in global memory: the TMA unit zero-fills what lies outside a
+// line and the pass-B kernel replicates the edge sample inside the staged tile (border tiles only).
+static size_t sep_t_pitch(int nb_stored) { return (size_t)((nb_stored + 15) & ~15); }
 
 static int level_rmax(const LevelPlan *plans, int first_level, int nlev)
 {
@@ -468,8 +457,8 @@ static int level_rmax(const LevelPlan *plans, int first_level, int nlev)
 // Doubles of intermediate storage the two passes need for one octave (all blurred levels).
 size_t sep_t_elems(int w, int h, int trows, const LevelPlan *plans, int first_level, int nlev)
 {
-  const TLayout t = sep_t_layout(trows, level_rmax(plans, first_level, nlev), fir_shape(w, h));
-  return (size_t)(nlev - first_level) * w * t.pitch;
+  (void)h; (void)plans;
+  return (size_t)(nlev - first_level) * w * sep_t_pitch(trows);
 }
 
 static int padded_taps(int radius) { return ((2 * radius + 4) & ~3) + 4; }
@@ -483,9 +472,9 @@ bool sep_supported(const LevelPlan *plans, int first_level, int nlev, int w, int
 
 static void fill_levels(FirArgs &A, const LevelPlan *plans, int first_level, int nlev, double *tbase, int w, int h, int trows)
 {
-  const TLayout t = sep_t_layout(trows, level_rmax(plans, first_level, nlev), fir_shape(w, h));
-  const size_t plane = (size_t)w * t.pitch;
-  A.t_pitch = t.pitch; A.t_off = t.off; A.t_padl = t.padl; A.t_padr = t.padr;
+  (void)h;
+  A.t_pitch = sep_t_pitch(trows);
+  const size_t plane = (size_t)w * A.t_pitch;
   A.nlev = nlev - first_level;
   A.rmax = 0; A.wtotal = 0;
   for (int i = 0; i < A.nlev; i++) {
@@ -519,14 +508,13 @@ static void fir_dispatch(cudaStream_t st, const double *d_weights, const FirArgs
 // pass A: base (seed64 of octaves >= 1, or the source image doubled along x for a generic octave 0) -> T^T
 void launch_sep_pass_a(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int upsample,
                        int w, int hrows, int h, const double *d_weights, const LevelPlan *plans, int first_level,
-                       int nlev, double *tbase, int write_pads)
+                       int nlev, double *tbase)
 {
   FirArgs A;
   memset(&A, 0, sizeof A);
   A.src = src; A.src_kind = dtype; A.in_pitch = src_pitch_bytes; A.in_nb = src_w;
   A.na = hrows; A.nb = w; A.ups = upsample;
   A.mode = 0;
-  A.t_pads = write_pads;
   fill_levels(A, plans, first_level, nlev, tbase, w, h, hrows);
   fir_dispatch<0>(st, d_weights, A, fir_shape(w, h));
 }
@@ -552,16 +540,16 @@ int sep_tma_build_maps(const LevelPlan *plans, int first_level, int nlev, double
   }
   const FirShape sh = fir_shape(w, h);
   const int rmax = level_rmax(plans, first_level, nlev);
-  const TLayout t = sep_t_layout(trows, rmax, sh);
+  const size_t pitch = sep_t_pitch(trows);
   if (fir_box_span(sh.nw * sh.no, rmax, sh.no) > 256) return 0;           // TMA boxes are at most 256 elements wide
   CUtensorMap *maps = (CUtensorMap *)h_maps;
   for (int i = 0; i < nlev - first_level; i++) {
-    const cuuint64_t gdim[2] = { (cuuint64_t)t.pitch, (cuuint64_t)w };
-    const cuuint64_t gstride[1] = { (cuuint64_t)t.pitch * sizeof(double) };
+    const cuuint64_t gdim[2] = { (cuuint64_t)pitch, (cuuint64_t)w };
+    const cuuint64_t gstride[1] = { (cuuint64_t)pitch * sizeof(double) };
     const cuuint32_t box[2] = { (cuuint32_t)fir_box_span(sh.nw * sh.no, plans[first_level + i].radius, sh.no), FP_LINES };
     const cuuint32_t estride[2] = { 1, 1 };
     // 64-bit elements: the driver has no FLOAT64 tile type restriction issue -- use FLOAT64
-    if (encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)(tbase + (size_t)i * w * t.pitch), gdim, gstride, box,
+    if (encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)(tbase + (size_t)i * w * pitch), gdim, gstride, box,
                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return 0;
@@ -569,7 +557,7 @@ int sep_tma_build_maps(const LevelPlan *plans, int first_level, int nlev, double
   return nlev - first_level;
 }
 
-// Whether pass B of an octave will run the TMA kernel (pass A must then write the clamp pads).
+// Whether pass B of an octave will run the TMA kernel.
 bool sep_pass_b_uses_tma(const void *d_tmaps, int upsample)
 {
   static const bool no_tma = getenv("SIFT_B200_NO_TMA") != nullptr || getenv("SIFT_B200_NO_TMA_BLUR") != nullptr;
@@ -605,7 +593,6 @@ void launch_sep_pass_b(cudaStream_t st, int upsample, const OctaveDev &oct, cons
   const FirShape sh = fir_shape(oct.w, oct.h);
   if (sep_pass_b_uses_tma(d_tmaps, upsample) && fir_box_span(sh.nw * sh.no, A.rmax, sh.no) <= 256) {
     A.tmaps = d_tmaps;
-    A.t_pads = 1;
     if (sh.no == 16) fir_launch_tma<8, 16>(st, d_weights, A);
     else if (sh.nw == 8) fir_launch_tma<8, 8>(st, d_weights, A);
     else fir_launch_tma<4, 8>(st, d_weights, A);

@@ -77,7 +77,7 @@ size_t sep_tma_map_bytes(int n_levels);
 int sep_tma_build_maps(const LevelPlan *plans, int first_level, int nlev, double *tbase, int w, int h, int trows, void *h_maps);
 void launch_sep_pass_a(cudaStream_t st, const void *src, int dtype, size_t src_pitch_bytes, int src_w, int upsample,
                        int w, int hrows, int h, const double *d_weights, const LevelPlan *plans, int first_level,
-                       int nlev, double *tbase, int write_pads);
+                       int nlev, double *tbase);
 bool sep_pass_b_uses_tma(const void *d_tmaps, int upsample);
 void launch_sep_pass_b(cudaStream_t st, int upsample, const OctaveDev &oct, const double *d_weights,
                        const LevelPlan *plans, int first_level, double *tbase, int hrows, const OctaveDev *next,

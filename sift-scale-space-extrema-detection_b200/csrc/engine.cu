@@ -470,13 +470,12 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
     double *tb = (double *)ctx->L->tbuf.p;
     const void *tm = (o > 0 && ctx->L->tma_blur[o] >= 0) ? (const char *)ctx->L->tmaps_t.p + sep_tma_map_bytes(ctx->L->tma_blur[o]) : nullptr;
-    const int pads = sep_pass_b_uses_tma(tm, o == 0) ? 1 : 0;
     if (o == 0)
       launch_sep_pass_a(st, d_image, dtype, pitch_bytes, ctx->in_w, 1, od.w, hrows, od.h, ctx->d_weights,
-                        ctx->plans[o], first, ctx->nlev, tb, pads);
+                        ctx->plans[o], first, ctx->nlev, tb);
     else
       launch_sep_pass_a(st, od.seed64, SIFT_F64, (size_t)od.w * sizeof(double), od.w, 0, od.w, hrows, od.h,
-                        ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb, pads);
+                        ctx->d_weights, ctx->plans[o], first, ctx->nlev, tb);
     launch_sep_pass_b(st, o == 0, od, ctx->d_weights, ctx->plans[o], first, tb, hrows, next, spo, ctx->keep_gauss, tm);
   } else {
     // radii too large for the staged tiles (octaves >= 4): row-major T, level-parallel kernels
