@@ -185,8 +185,8 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
                          sift_keypoint *out, int cap, int *n_out, sift_stats *stats);
 
 /* Same, image already in device memory; keypoints stay in device memory
- * (d_out, unordered unless `ordered` != 0) and *d_count (device int) receives
- * the count.  Asynchronous: ordered after what is already queued on sift_stream(ctx);
+ * (d_out; in the reference's order when `ordered` != 0, which adds a device-side radix sort, else in
+ * completion order) and *d_count (device int) receives the count (which may exceed cap: only cap are written).  Asynchronous: ordered after what is already queued on sift_stream(ctx);
  * sift_flush() / sift_synchronize() order the results before later work on that stream. */
 SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
                                 size_t pitch_bytes, const sift_params *params,

@@ -33,7 +33,7 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, order;
   bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
   int tma_blur[SIFT_MAX_OCTAVES];   // per octave: maps of its T^T planes start at tmaps_t[tma_blur[o]] (-1: none)
   int cand_cap = 0, kp_cap = 0;
@@ -760,7 +760,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.order };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);
@@ -895,7 +895,6 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;
   if (!d_image || !d_out || !d_count || cap <= 0) return fail(ctx, SIFT_ERR_BAD_ARGS, "NULL device pointer or cap <= 0");
-  if (ordered) return fail(ctx, SIFT_ERR_UNSUPPORTED, "device-side ordering is not implemented yet; use sift_detect");
   const size_t es = dtype_size(dtype);
   if (!es) return fail(ctx, SIFT_ERR_BAD_ARGS, "unknown dtype %d", dtype);
   CK(cudaSetDevice(ctx->device));
@@ -912,11 +911,24 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
   rc = run_pyramid(ctx, d_image, dtype, pitch_bytes);
   if (!rc) rc = cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream) == cudaSuccess ? SIFT_OK : fail(ctx, SIFT_ERR_CUDA, "memset failed");
   if (!rc) rc = run_scan(ctx, 0);
-  if (!rc) rc = run_refine(ctx, -1, d_out, cap);
-  if (!rc) {
-    copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), d_count);
-    ctx->launches += 1;
-    if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "copy_count launch failed");
+  if (!ordered) {
+    if (!rc) rc = run_refine(ctx, -1, d_out, cap);
+    if (!rc) {
+      copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), d_count);
+      ctx->launches += 1;
+      if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "copy_count launch failed");
+    }
+  } else {
+    // refine into the lane's own buffer, then order (key, index) pairs on the device and gather into d_out
+    const int n_sort = std::min(cap, ln->kp_cap);
+    const size_t need = order_scratch_bytes(n_sort);
+    if (!rc) rc = grow(ctx, ln->order, need);
+    if (!rc) rc = run_refine(ctx, -1, dev_keypoints(ctx), n_sort);
+    if (!rc) {
+      ctx->launches += launch_order_keypoints(ln->stream, dev_keypoints(ctx), dev_counters(ctx), n_sort, ln->order.p, ln->order.cap,
+                                              d_out, cap, d_count);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "ordering launch failed");
+    }
   }
   ln->busy = true;
   ctx->pyramid_built = false;          // the stage API reads lane 0, which this call may not have used

@@ -186,6 +186,36 @@ def test_device_resident_frames_in_flight_equal_single(engine):
     engine.set_lanes(3)
 
 
+def test_device_resident_ordered_output(engine):
+    """sift_detect_device(ordered=1): the device-side sort + gather must give exactly sift_detect's record order
+    (octave, scale, row, column: background.js:468-471 / sift.js:221-222), also when cap truncates the output."""
+    import torch
+    w, h = 320, 240
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    rec = L.KEYPOINT_DTYPE.itemsize
+    for seed, cap in ((61, 4096), (62, 4096), (61, 37)):
+        u8 = fixtures.synthetic_u8(w, h, seed, blobs=300)
+        d = torch.from_numpy(u8).cuda()
+        out = torch.zeros(cap * rec, dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        engine.detect_device(d.data_ptr(), L.SIFT_U8, w, h, 0, prm, out.data_ptr(), cap, cnt.data_ptr(), ordered=True)
+        engine.synchronize()
+        want, _ = engine.detect(u8, prm)
+        k = int(cnt.item())
+        got = np.frombuffer(out.cpu().numpy().tobytes(), dtype=L.KEYPOINT_DTYPE)
+        if cap >= len(want):
+            assert k == len(want) and k > 40
+            assert got[:k].tobytes() == want.tobytes()
+        else:
+            # truncated: count reports what was found (>= cap); the cap records written are valid keypoints in order
+            assert k >= cap
+            keys = [(int(r["octave"]), int(r["candScale"]), int(r["candY"]), int(r["candX"])) for r in got[:cap]]
+            assert keys == sorted(keys)
+            wk = {(int(r["octave"]), int(r["candScale"]), int(r["candY"]), int(r["candX"])) for r in want}
+            assert set(keys) <= wk
+
+
 def test_batch_overflow_falls_back_and_stays_correct(engine):
     """More keypoints than the device buffers were sized for: the batch path regrows and still matches."""
     frames = np.stack([fixtures.synthetic_u8(96, 96, 300 + i, blobs=400, sigma_lo=0.7, sigma_hi=2.0) for i in range(5)])
