@@ -258,9 +258,6 @@ void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *
 #define ST_ROWS 8              // rows marched by one thread
 #define ST_THREADS ((ST_TW / ST_PX) * (ST_TH / ST_ROWS))   // 128
 #define ST_CTAS_PER_SM 4
-#ifndef ST_STAGES
-#define ST_STAGES 1            // 1: one tile per CTA, four CTAs per SM hide the load; 2: persistent CTAs, double buffer
-#endif
 
 struct ScanTmaArgs {
   int n_oct, spo, ndog, count_low, total_tiles;
@@ -294,161 +291,153 @@ __device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t
   return T;
 }
 
-// Persistent CTAs, two tile buffers: while the CTA tests tile k out of one buffer the TMA unit fills the
-// other with tile k + 1, so the HBM latency of a tile is hidden behind the arithmetic of the previous one.
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }   // one FMNMX3
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// One CTA = one tile.  Thread 0 decodes the tile, arms the mbarrier and issues one TMA box per DoG level; the
+// four CTAs resident on an SM hide each other's load.  The min/max network runs on the half-rate ALU pipe, which
+// bounds this kernel next to HBM, so the per-voxel test is kept off it: with m27 / n27 the max / min of the
+// 3x3x3 block (centre included), t = (m27 - c) * (c - n27) is zero iff the centre equals one of them -- two
+// FADD and one FMUL on the FMA pipe and a single compare.  Underflow can only produce false positives, and
+// every positive (true extrema, ties, underflow) is settled by the exact strict 26-neighbour test.
 template <int ND, bool COUNT_LOW>   // DoG levels per octave (spo + 2); also materialise the low-contrast list
 __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
 scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_candidate *__restrict__ cand,
                 int cand_cap, sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
 {
-  extern __shared__ __align__(128) float tiles[];       // [ST_STAGES][ND][ST_PLANE], each level [ST_BH][ST_BW]
-  __shared__ __align__(8) unsigned long long bar[ST_STAGES];
+  extern __shared__ __align__(128) float tiles[];       // [ND][ST_PLANE], each level [ST_BH][ST_BW]
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ ScanTile tile_s;
   const int tid = threadIdx.x;
 
-  auto issue = [&](int t, int stage) {                  // one thread: arm the barrier, one TMA tile load per level
-    const ScanTile T = scan_decode_tile(A, t);
+  if (tid == 0) {
+    const ScanTile T0 = scan_decode_tile(A, blockIdx.x);
+    tile_s = T0;
+    const unsigned b = smem_u32(&bar);
     const unsigned bytes = ND * ST_BH * ST_BW * sizeof(float);
-    const unsigned b = smem_u32(&bar[stage]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 #pragma unroll
     for (int p = 0; p < ND; p++) {
-      const CUtensorMap *m = maps + T.o * ND + p;
+      const CUtensorMap *m = maps + T0.o * ND + p;
       asm volatile(
           "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-          ::"r"(smem_u32(tiles + (stage * ND + p) * ST_PLANE)), "l"(m), "r"(b), "r"(T.x_tile - 4), "r"(T.y_tile - 1)
+          ::"r"(smem_u32(tiles + p * ST_PLANE)), "l"(m), "r"(b), "r"(T0.x_tile - 4), "r"(T0.y_tile - 1)
           : "memory");
     }
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < ST_STAGES; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < A.total_tiles) issue(blockIdx.x, 0);
-  // thread -> 2 pixels (columns 2*cx, 2*cx+1 of the tile) x rows [8*ry, 8*ry + 8)
+  const ScanTile T = tile_s;
+  // thread -> ST_PX pixels (columns ST_PX*cx ...) x rows [8*ry, 8*ry + 8)
   const int cx = tid & (ST_TW / ST_PX - 1), ry = tid / (ST_TW / ST_PX);
-  const int xl = ST_PX * cx;                                  // tile-local column of pixel 0
+  const int xl = ST_PX * cx;                              // tile-local column of pixel 0
   const int row_first = ry * ST_ROWS;                     // tile-local row of the first output row
-
-  int k = 0;
-  for (int t = blockIdx.x; t < A.total_tiles; t += gridDim.x, k++) {
-    const int stage = ST_STAGES > 1 ? (k & 1) : 0;
-    if (ST_STAGES > 1 && tid == 0 && t + (int)gridDim.x < A.total_tiles) issue(t + gridDim.x, stage ^ 1);   // that buffer was released by the
-                                                                                             // __syncthreads of iteration k-1
-    {
-      const unsigned parity = ST_STAGES > 1 ? ((k >> 1) & 1) : (k & 1);
-      unsigned done = 0;
-      while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(&bar[stage])), "r"(parity) : "memory");
-      }
+  const int x0 = T.x_tile + xl;
+  const float thr = A.thr_f;
+  bool col_ok[ST_PX];                                                                  // sift.js:222
+#pragma unroll
+  for (int i = 0; i < ST_PX; i++) col_ok[i] = x0 + i >= 1 && x0 + i < T.w - 1;
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
     }
-    const ScanTile T = scan_decode_tile(A, t);
-    const float *tile = tiles + stage * ND * ST_PLANE;
-    const int x0 = T.x_tile + xl;
-    bool col_ok[ST_PX];                                                                  // sift.js:222
-#pragma unroll
-    for (int i = 0; i < ST_PX; i++) col_ok[i] = x0 + i >= 1 && x0 + i < T.w - 1;
-    // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3) of the horizontal
-    // 3-max / 3-min, and the centre levels' own values.  Fast path: a pixel can only be an extremum if it EQUALS
-    // the max (or min) of its 3x3x3 block, centre included -- two 3-input min/max per voxel on top of the shared
-    // 3x3 block extrema.  The rare survivors (true extrema and ties) get the exact strict 26-neighbour test
-    // from shared memory (sift.js:261, 266: ties are never extrema).
-    float hmax[3][ND][ST_PX], hmin[3][ND][ST_PX], cen[3][ND][ST_PX];
+  }
+  const float *tile = tiles;
+  // per level, three rolling rows (slot = row % 3, compile-time: the row loop advances by 3) of the horizontal
+  // 3-max / 3-min, and the centre levels' own values.
+  float hmax[3][ND][ST_PX], hmin[3][ND][ST_PX], cen[3][ND][ST_PX];
 #pragma unroll 1
-    for (int r3 = 0; r3 < ST_ROWS + 2; r3 += 3) {
+  for (int r3 = 0; r3 < ST_ROWS + 2; r3 += 3) {
 #pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const int r = r3 + j;
-        if (r >= ST_ROWS + 2) break;
-        const int cs = j, bs = (j + 2) % 3, as = (j + 1) % 3;          // slots of rows r, r-1, r-2
-        // box row of tile-local row (row_first - 1 + r) is (row_first + r): the box starts one row above the tile
+    for (int j = 0; j < 3; j++) {
+      const int r = r3 + j;
+      if (r >= ST_ROWS + 2) break;
+      const int cs = j, bs = (j + 2) % 3, as = (j + 1) % 3;          // slots of rows r, r-1, r-2
+      // box row of tile-local row (row_first - 1 + r) is (row_first + r): the box starts one row above the tile
 #pragma unroll
-        for (int p = 0; p < ND; p++) {
-          const float *rowp = tile + p * ST_PLANE + (row_first + r) * ST_BW + 4 + xl;
+      for (int p = 0; p < ND; p++) {
+        const float *rowp = tile + p * ST_PLANE + (row_first + r) * ST_BW + 4 + xl;
 #if ST_PX == 2
-          const float2 v = *reinterpret_cast<const float2 *>(rowp);
-          const float L = rowp[-1], Rr = rowp[2];
-          const float mx = fmaxf(v.x, v.y), mn = fminf(v.x, v.y);
-          hmax[cs][p][0] = fmaxf(L, mx); hmax[cs][p][1] = fmaxf(mx, Rr);
-          hmin[cs][p][0] = fminf(L, mn); hmin[cs][p][1] = fminf(mn, Rr);
-          if (p >= 1 && p < ND - 1) { cen[cs][p][0] = v.x; cen[cs][p][1] = v.y; }
+        const float2 v = *reinterpret_cast<const float2 *>(rowp);
+        const float L = rowp[-1], Rr = rowp[2];
+        hmax[cs][p][0] = max3f(L, v.x, v.y); hmax[cs][p][1] = max3f(Rr, v.y, v.x);
+        hmin[cs][p][0] = min3f(L, v.x, v.y); hmin[cs][p][1] = min3f(Rr, v.y, v.x);
+        if (p >= 1 && p < ND - 1) { cen[cs][p][0] = v.x; cen[cs][p][1] = v.y; }
 #else
-          const float L = rowp[-1], v = rowp[0], Rr = rowp[1];
-          hmax[cs][p][0] = fmaxf(fmaxf(L, v), Rr);
-          hmin[cs][p][0] = fminf(fminf(L, v), Rr);
-          if (p >= 1 && p < ND - 1) cen[cs][p][0] = v;
+        const float L = rowp[-1], v = rowp[0], Rr = rowp[1];
+        hmax[cs][p][0] = max3f(L, v, Rr);
+        hmin[cs][p][0] = min3f(L, v, Rr);
+        if (p >= 1 && p < ND - 1) cen[cs][p][0] = v;
 #endif
+      }
+      if (r >= 2) {
+        float m9[ND][ST_PX], n9[ND][ST_PX];                  // 3x3 max / min per level (centre included)
+#pragma unroll
+        for (int p = 0; p < ND; p++)
+#pragma unroll
+          for (int i = 0; i < ST_PX; i++) {
+            m9[p][i] = max3f(hmax[as][p][i], hmax[bs][p][i], hmax[cs][p][i]);
+            n9[p][i] = min3f(hmin[as][p][i], hmin[bs][p][i], hmin[cs][p][i]);
+          }
+        float tz[ND][ST_PX];
+        bool any = false;
+#pragma unroll
+        for (int s = 1; s < ND - 1; s++) {                   // background.js:377
+#pragma unroll
+          for (int i = 0; i < ST_PX; i++) {
+            const float c = cen[bs][s][i];
+            const float m27 = max3f(m9[s - 1][i], m9[s][i], m9[s + 1][i]);
+            const float n27 = min3f(n9[s - 1][i], n9[s][i], n9[s + 1][i]);
+            tz[s][i] = __fmul_rn(__fsub_rn(m27, c), __fsub_rn(c, n27));
+            any = any || tz[s][i] == 0.f;
+          }
         }
-        if (r >= 2) {
+        if (__any_sync(0xffffffffu, any)) {                  // rare: a few per cent of the warp rows
           const int y = T.y_tile + row_first + r - 2;        // the middle row (slots as, bs, cs = rows y-1, y, y+1)
           const int yg = y + T.y_top;                        // row of the whole image (strips)
           const bool row_ok = yg >= 1 && yg < T.gh - 1 && y >= T.own0 && y < T.own1;   // sift.js:221
-          float m9[ND][ST_PX], n9[ND][ST_PX];                        // 3x3 max / min per level (centre included)
 #pragma unroll
-          for (int p = 0; p < ND; p++)
-#pragma unroll
-            for (int i = 0; i < ST_PX; i++) {
-              m9[p][i] = fmaxf(fmaxf(hmax[as][p][i], hmax[bs][p][i]), hmax[cs][p][i]);
-              n9[p][i] = fminf(fminf(hmin[as][p][i], hmin[bs][p][i]), hmin[cs][p][i]);
-            }
-          bool maybe[ND][ST_PX], any = false;
-#pragma unroll
-          for (int s = 1; s < ND - 1; s++) {                 // background.js:377
+          for (int s = 1; s < ND - 1; s++)
 #pragma unroll
             for (int i = 0; i < ST_PX; i++) {
               const float c = cen[bs][s][i];
-              const float m27 = fmaxf(fmaxf(m9[s - 1][i], m9[s][i]), m9[s + 1][i]);
-              const float n27 = fminf(fminf(n9[s - 1][i], n9[s][i]), n9[s + 1][i]);
-              bool e = (c == m27 || c == n27) && col_ok[i];
-              if (!COUNT_LOW) e = e && fabsf(c) >= A.thr_f;                             // sift.js:294 (see launch_scan_tma)
-              maybe[s][i] = e;
-              any = any || e;
-            }
-          }
-          if (__any_sync(0xffffffffu, any && row_ok)) {      // rare
+              const bool strong = fabsf(c) >= thr;           // sift.js:294 (see launch_scan_tma)
+              const bool maybe = tz[s][i] == 0.f && row_ok && col_ok[i] && (COUNT_LOW || strong);
+              if (!__any_sync(0xffffffffu, maybe)) continue;
+              bool e = false;
+              if (maybe) {                                   // exact strict test of the 26 neighbours
+                const float *ctr_px = tile + s * ST_PLANE + (row_first + r - 1) * ST_BW + 4 + xl + i;
+                bool is_max = true, is_min = true;
 #pragma unroll
-            for (int s = 1; s < ND - 1; s++)
+                for (int dp = -1; dp <= 1; dp++)
 #pragma unroll
-              for (int i = 0; i < ST_PX; i++) {
-                const float c = cen[bs][s][i];
-                bool e = false;
-                if (maybe[s][i] && row_ok) {                 // exact strict test of the 26 neighbours
-                  const float *ctr_px = tile + s * ST_PLANE + (row_first + r - 1) * ST_BW + 4 + xl + i;
-                  bool is_max = true, is_min = true;
+                  for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-                  for (int dp = -1; dp <= 1; dp++)
-#pragma unroll
-                    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                      for (int dx = -1; dx <= 1; dx++) {
-                        if (dp == 0 && dy == 0 && dx == 0) continue;
-                        const float v = ctr_px[dp * ST_PLANE + dy * ST_BW + dx];
-                        is_max = is_max && (v < c);          // sift.js:266
-                        is_min = is_min && (v > c);          // sift.js:261
-                      }
-                  e = is_max || is_min;
-                }
-                const bool strong = fabsf(c) >= A.thr_f;
-                sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = yg; rec.value = c; rec.reserved0 = 0;
-                int slot = warp_append(e && strong, &ctr->n_cand);
-                if (slot >= 0 && slot < cand_cap) cand[slot] = rec;
-                if (COUNT_LOW) {
-                  slot = warp_append(e && !strong, &ctr->n_low);
-                  if (low && slot >= 0 && slot < low_cap) low[slot] = rec;
-                }
+                    for (int dx = -1; dx <= 1; dx++) {
+                      if (dp == 0 && dy == 0 && dx == 0) continue;
+                      const float v = ctr_px[dp * ST_PLANE + dy * ST_BW + dx];
+                      is_max = is_max && (v < c);            // sift.js:266
+                      is_min = is_min && (v > c);            // sift.js:261
+                    }
+                e = is_max || is_min;
               }
-          }
+              sift_candidate rec; rec.octave = T.o; rec.scaleLevel = s; rec.x = x0 + i; rec.y = yg; rec.value = c; rec.reserved0 = 0;
+              int slot = warp_append(e && strong, &ctr->n_cand);
+              if (slot >= 0 && slot < cand_cap) cand[slot] = rec;
+              if (COUNT_LOW) {
+                slot = warp_append(e && !strong, &ctr->n_low);
+                if (low && slot >= 0 && slot < low_cap) low[slot] = rec;
+              }
+            }
         }
       }
     }
-    __syncthreads();                                        // every thread is done with this buffer: it may be refilled
-    if (ST_STAGES == 1 && tid == 0 && t + (int)gridDim.x < A.total_tiles) issue(t + gridDim.x, 0);
   }
 }
 
@@ -512,8 +501,8 @@ void launch_scan_tma(cudaStream_t st, const OctaveDev *h_octs, const void *d_map
   A.total_tiles = total;
   if (total == 0) return;
   const int nd = spo + 2;
-  const size_t smem = (size_t)ST_STAGES * nd * ST_PLANE * sizeof(float);
-  const int grid = (ST_STAGES == 1 || total < 148 * ST_CTAS_PER_SM) ? total : 148 * ST_CTAS_PER_SM;      // persistent CTAs when double-buffered
+  const size_t smem = (size_t)nd * ST_PLANE * sizeof(float);
+  const int grid = total;
   const CUtensorMap *maps = (const CUtensorMap *)d_maps;
 #define LAUNCH_ND(N)                                                                                         \
   case N:                                                                                                    \
