@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200"
 W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
-FRAMES = 16                    # frames per GPU per step (distinct seeds)
+FRAMES = 64                    # frames per GPU per step (distinct seeds)
 # dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0_1.txt), ncu --set full
 NCU_TRAFFIC_OCT0_BYTES = 345.5e6
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)

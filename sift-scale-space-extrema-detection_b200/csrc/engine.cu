@@ -39,6 +39,8 @@ struct Lane {
   int cand_cap = 0, kp_cap = 0;
   void *h_out = nullptr;       // pinned mirror of outbuf
   size_t h_out_cap = 0;
+  void *h_out2 = nullptr;      // second mirror: sift_detect_batch alternates, so a lane is re-issued while the host still
+  size_t h_out2_cap = 0;       // orders its previous frame
   OctaveDev octs[SIFT_MAX_OCTAVES];
   OctaveDev *d_octs = nullptr;
   uint64_t plan_id = 0;        // plan the buffers above are laid out for
@@ -764,6 +766,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);
+    if (ln.h_out2) cudaFreeHost(ln.h_out2);
     if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
     if (ln.ev_done) cudaEventDestroy(ln.ev_done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -980,9 +983,12 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
       if ((r = grow(ctx, ln->image, row * height))) return r;
       if ((r = grow_pinned(ctx, &ln->h_out, &ln->h_out_cap, sizeof(Counters) + (size_t)ln->kp_cap * sizeof(sift_keypoint))))
         return r;
+      if ((r = grow_pinned(ctx, &ln->h_out2, &ln->h_out2_cap, sizeof(Counters) + (size_t)ln->kp_cap * sizeof(sift_keypoint))))
+        return r;
     }
     return SIFT_OK;
   };
+  auto hbuf = [&](Lane *ln, int frame) { return ((frame / NL) & 1) ? ln->h_out2 : ln->h_out; };
   if ((rc = prepare_lanes())) { ctx->L = &ctx->lanes[0]; return rc; }
   const int64_t l0 = ctx->launches;
   int n = 0, overflow = 0;
@@ -1006,28 +1012,28 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     if ((r = run_scan(ctx, 0))) return r;
     if ((r = run_refine(ctx, -1, dev_keypoints(ctx), ln->kp_cap))) return r;
     const size_t first = sizeof(Counters) + (size_t)std::min(ln->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
-    CK(cudaMemcpyAsync(ln->h_out, ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
+    CK(cudaMemcpyAsync(hbuf(ln, i), ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
     CK(cudaEventRecord(ln->ev_done, ln->stream));
     issued = i + 1;
     t_issue += now() - t0;
     return SIFT_OK;
   };
 
-  // consume frame `done`: order its keypoints into `out`
-  auto consume = [&]() -> int {
-    const int j = done;
+  // wait for frame j = `done` (device work and downloads complete).  handled: the overflow fallback consumed it.
+  auto wait_frame = [&](int j, Counters &c, bool &handled) -> int {
     Lane *ln = &ctx->lanes[j % NL];
     ctx->L = ln;
+    handled = false;
     const double t0 = now();
     CK(cudaEventSynchronize(ln->ev_done));
-    const double t1 = now();
-    t_wait += t1 - t0;
-    Counters c = *(Counters *)ln->h_out;
-    sift_stats si;
-    memset(&si, 0, sizeof si);
+    t_wait += now() - t0;
+    c = *(Counters *)hbuf(ln, j);
     if (c.n_cand > ln->cand_cap || c.n_kp > ln->kp_cap) {
       // rare: device buffers too small -- drain every lane and redo the issued frames on the growing
       // single-frame path (lane 0), then size the other lanes like it
+      handled = true;
+      sift_stats si;
+      memset(&si, 0, sizeof si);
       for (int l = 0; l < NL; l++) CK(cudaStreamSynchronize(ctx->lanes[l].stream));
       for (int q = j; q < issued; q++) {
         int ni = 0;
@@ -1051,11 +1057,19 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     }
     if (c.n_kp > FIRST_CHUNK) {
       const size_t first = sizeof(Counters) + (size_t)FIRST_CHUNK * sizeof(sift_keypoint);
-      CK(cudaMemcpyAsync((char *)ln->h_out + first, (char *)ln->outbuf.p + first,
+      CK(cudaMemcpyAsync((char *)hbuf(ln, j) + first, (char *)ln->outbuf.p + first,
                          (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ln->stream));
       CK(cudaStreamSynchronize(ln->stream));
     }
-    const sift_keypoint *kps = (const sift_keypoint *)((char *)ln->h_out + sizeof(Counters));
+    return SIFT_OK;
+  };
+  // order frame j's keypoints (in its lane's host buffer) into `out`
+  auto order_frame = [&](int j, const Counters &c) {
+    const double t0 = now();
+    Lane *ln = &ctx->lanes[j % NL];
+    sift_stats si;
+    memset(&si, 0, sizeof si);
+    const sift_keypoint *kps = (const sift_keypoint *)((char *)hbuf(ln, j) + sizeof(Counters));
     const int room = overflow ? 0 : std::max(0, cap - n);
     sort_keypoints_into(ctx, kps, c.n_kp, room ? out + n : nullptr, room);
     if (c.n_kp > room) overflow = 1;
@@ -1063,18 +1077,23 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     ctx->last = c;
     take(j, c.n_kp, si);
     done = j + 1;
-    t_sort += now() - t1;
-    return SIFT_OK;
+    t_sort += now() - t0;
   };
 
+  // Frame i runs on lane i % NL.  When frame j completes, its lane gets frame j + NL at once -- the device
+  // buffers are free and the download goes to the lane's other host buffer -- and only then the host orders
+  // frame j, so NL frames stay in flight while the host works.
   rc = SIFT_OK;
-  for (int i = 0; i < n_images && !rc; i++) {
-    while (!rc && i - done >= NL) rc = consume();          // the lane's previous frame must be off its buffers
-    if (!rc && issued <= i) rc = issue(i);                  // (an overflow fallback may already have covered frame i)
-  }
   while (!rc && done < n_images) {
-    if (issued <= done) rc = issue(done);
-    if (!rc) rc = consume();
+    while (!rc && issued < n_images && issued - done < NL) rc = issue(issued);
+    if (rc) break;
+    const int j = done;
+    Counters c;
+    bool handled = false;
+    rc = wait_frame(j, c, handled);
+    if (rc || handled) continue;
+    if (issued < n_images) rc = issue(issued);
+    if (!rc) order_frame(j, c);
   }
   ctx->L = &ctx->lanes[0];
   ctx->pyramid_built = false;

@@ -251,13 +251,19 @@ void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *
 #ifndef ST_TW
 #define ST_TW 128
 #endif
+#ifndef ST_TH
 #define ST_TH 16
+#endif
 #define ST_BW (ST_TW + 8)      // box: 4 columns left (alignment) + tile + 4 right
 #define ST_BH (ST_TH + 2)
 #define ST_PLANE ((ST_BH * ST_BW + 31) & ~31)   // floats per staged level: TMA destinations are 128-byte aligned
+#ifndef ST_ROWS
 #define ST_ROWS 8              // rows marched by one thread
+#endif
 #define ST_THREADS ((ST_TW / ST_PX) * (ST_TH / ST_ROWS))   // 128
+#ifndef ST_CTAS_PER_SM
 #define ST_CTAS_PER_SM 4
+#endif
 
 struct ScanTmaArgs {
   int n_oct, spo, ndog, count_low, total_tiles;
@@ -274,20 +280,14 @@ struct ScanTile { int o, x_tile, y_tile, w, h, y_top, gh, own0, own1; };
 
 __device__ __forceinline__ ScanTile scan_decode_tile(const ScanTmaArgs &A, int t)
 {
-  // static indices only: a dynamically indexed kernel-parameter array is copied to local memory
-  ScanTile T;
-  int o = 0, t0 = 0, ntx = A.tiles_x[0], w = A.w[0], h = A.h[0];
-  int y_top = A.y_top[0], gh = A.gh[0], own0 = A.own0[0], own1 = A.own1[0];
-#pragma unroll
-  for (int i = 1; i < SIFT_MAX_OCTAVES; i++)
-    if (i < A.n_oct && t >= A.tile_start[i]) {
-      o = i; t0 = A.tile_start[i]; ntx = A.tiles_x[i]; w = A.w[i]; h = A.h[i];
-      y_top = A.y_top[i]; gh = A.gh[i]; own0 = A.own0[i]; own1 = A.own1[i];
-    }
-  const int tt = t - t0;
+  // A is a __grid_constant__ parameter: dynamic indices read the constant bank directly (no local copy)
+  int o = 0;
+  while (o + 1 < A.n_oct && t >= A.tile_start[o + 1]) o++;
+  const int tt = t - A.tile_start[o], ntx = A.tiles_x[o];
   const int ty = tt / ntx, tx = tt - ty * ntx;
-  T.o = o; T.x_tile = tx * ST_TW; T.y_tile = ty * ST_TH; T.w = w; T.h = h;
-  T.y_top = y_top; T.gh = gh; T.own0 = own0; T.own1 = own1;
+  ScanTile T;
+  T.o = o; T.x_tile = tx * ST_TW; T.y_tile = ty * ST_TH; T.w = A.w[o]; T.h = A.h[o];
+  T.y_top = A.y_top[o]; T.gh = A.gh[o]; T.own0 = A.own0[o]; T.own1 = A.own1[o];
   return T;
 }
 
@@ -302,17 +302,15 @@ __device__ __forceinline__ float min3f(float a, float b, float c) { return fminf
 // every positive (true extrema, ties, underflow) is settled by the exact strict 26-neighbour test.
 template <int ND, bool COUNT_LOW>   // DoG levels per octave (spo + 2); also materialise the low-contrast list
 __global__ void __launch_bounds__(ST_THREADS, ST_CTAS_PER_SM)
-scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_candidate *__restrict__ cand,
+scan_tma_kernel(const CUtensorMap *__restrict__ maps, const __grid_constant__ ScanTmaArgs A, sift_candidate *__restrict__ cand,
                 int cand_cap, sift_candidate *__restrict__ low, int low_cap, Counters *ctr)
 {
   extern __shared__ __align__(128) float tiles[];       // [ND][ST_PLANE], each level [ST_BH][ST_BW]
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ ScanTile tile_s;
   const int tid = threadIdx.x;
+  const ScanTile T = scan_decode_tile(A, blockIdx.x);
 
   if (tid == 0) {
-    const ScanTile T0 = scan_decode_tile(A, blockIdx.x);
-    tile_s = T0;
     const unsigned b = smem_u32(&bar);
     const unsigned bytes = ND * ST_BH * ST_BW * sizeof(float);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
@@ -320,15 +318,14 @@ scan_tma_kernel(const CUtensorMap *__restrict__ maps, const ScanTmaArgs A, sift_
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 #pragma unroll
     for (int p = 0; p < ND; p++) {
-      const CUtensorMap *m = maps + T0.o * ND + p;
+      const CUtensorMap *m = maps + T.o * ND + p;
       asm volatile(
           "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-          ::"r"(smem_u32(tiles + p * ST_PLANE)), "l"(m), "r"(b), "r"(T0.x_tile - 4), "r"(T0.y_tile - 1)
+          ::"r"(smem_u32(tiles + p * ST_PLANE)), "l"(m), "r"(b), "r"(T.x_tile - 4), "r"(T.y_tile - 1)
           : "memory");
     }
   }
   __syncthreads();
-  const ScanTile T = tile_s;
   // thread -> ST_PX pixels (columns ST_PX*cx ...) x rows [8*ry, 8*ry + 8)
   const int cx = tid & (ST_TW / ST_PX - 1), ry = tid / (ST_TW / ST_PX);
   const int xl = ST_PX * cx;                              // tile-local column of pixel 0

@@ -7,7 +7,7 @@ import json
 l=[x for x in open("gpurun_out/bench.log") if x.startswith("{")]
 if not l: print(open("gpurun_out/bench.log").read()[-2000:])
 else:
-    d=json.loads(l[-1]); print("value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms/frame", round(d["ms_per_step"]/16,4))
+    d=json.loads(l[-1]); print("value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms/frame", round(d["ms_per_step"]/d["config"]["frames_per_gpu_per_step"],4))
     print({k:round(v["ms_per_frame"],4) for k,v in d["roofline"]["kernels"].items()})
     print("frac dom", round(d["roofline"]["frac"],3), "whole", round(d["roofline"]["whole_path"]["frac"],3), d["clocks"], "launches", d["gpu_launches"])
 PY
