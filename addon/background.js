@@ -30,6 +30,34 @@ function readLevels(kind, matrices) {
   return out;
 }
 
+export const PREVIEW = { GRAY: 0, SIGMOID: 1, MINMAX: 2 };
+
+/** The ImageData payloads the reference posts beside the stage replies (SURVEY 8f-3), one per level in the
+ *  reference's order: Gaussian levels as grey (background.js:136-143, 212-220; image-utils.js:171-220), DoG
+ *  levels min/max-normalised (background.js:331-338; matrix2d.js:169-192).  Each entry is
+ *  {octave, imageData:{width, height, data:Uint8ClampedArray}} -- an ImageData-shaped plain object (wrap it
+ *  with `new ImageData(data, width, height)` in a browser). */
+export function levelPreviews(kind) {
+  const info = native.pyramidInfo(context());
+  const out = [];
+  for (let o = 0; o < info.octaves; o++)
+    for (let s = 0; s < info.levels - (kind === LEVEL.DOG ? 1 : 0); s++) {
+      const p = native.levelPreview(context(), kind, o, s, kind === LEVEL.DOG ? PREVIEW.MINMAX : PREVIEW.GRAY, 1);
+      out.push({ octave: o, imageData: { width: p.width, height: p.height, data: p.data } });
+    }
+  return out;
+}
+
+/** One chunk of a DoG level as the reference paints it while subtracting: sigmoid-normalised with
+ *  coefficient 5 (background.js:303-317, matrix2d.js:148-156), cropped to the half-open chunk {x1,y1,x2,y2}. */
+export function dogChunkPreview(octave, scale, chunk) {
+  const p = native.levelPreview(context(), LEVEL.DOG, octave, scale, PREVIEW.SIGMOID, 5);
+  const cw = chunk.x2 - chunk.x1, ch = chunk.y2 - chunk.y1;
+  const data = new Uint8ClampedArray(cw * ch * 4);
+  for (let y = 0; y < ch; y++) data.set(p.data.subarray(((chunk.y1 + y) * p.width + chunk.x1) * 4, ((chunk.y1 + y) * p.width + chunk.x2) * 4), y * cw * 4);
+  return { imageData: { width: cw, height: ch, data }, dx: chunk.x1, dy: chunk.y1 };
+}
+
 /** background.js:71 -- request {inputImage, numberOfOctaves, scalesPerOctave, minBlurLevel, assumedBlur, chunkSize}. */
 export function computeGaussianScaleSpace(request, { matrices = Array.isArray(request.inputImage) } = {}) {
   const px = toPixels(request.inputImage);

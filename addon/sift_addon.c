@@ -284,6 +284,35 @@ static napi_value GetLevel(napi_env env, napi_callback_info info)
   return out;
 }
 
+/* levelPreview(ctx, kind, octave, level, mode, coefficient) -> {width, height, data:Uint8ClampedArray, min, max}
+ * -- the ImageData payload the reference posts beside a stage result (image-utils.js:171-220; mode 1 =
+ * Matrix2D_sigmoidNormalize first, mode 2 = Matrix2D_sampledNormalize first) */
+static napi_value LevelPreview(napi_env env, napi_callback_info info)
+{
+  ARGS(6);
+  sift_ctx *ctx = get_ctx(env, argv[0]);
+  const int kind = get_i32(env, argv[1]), o = get_i32(env, argv[2]), s = get_i32(env, argv[3]);
+  const int mode = get_i32(env, argv[4]);
+  double coefficient = 1.0, mm[2] = { 0.0, 1.0 };
+  napi_get_value_double(env, argv[5], &coefficient);
+  int w = 0, h = 0;
+  int rc = sift_get_octave_size(ctx, o, &w, &h);
+  if (rc != SIFT_OK) return throw_status(env, ctx, rc);
+  void *p = NULL;
+  napi_value ab, arr, out;
+  napi_create_arraybuffer(env, (size_t)w * h * 4, &p, &ab);
+  rc = sift_get_level_preview(ctx, kind, o, s, mode, coefficient, (unsigned char *)p, mm);
+  if (rc != SIFT_OK) return throw_status(env, ctx, rc);
+  napi_create_typedarray(env, napi_uint8_clamped_array, (size_t)w * h * 4, ab, 0, &arr);
+  napi_create_object(env, &out);
+  set_num(env, out, "width", w);
+  set_num(env, out, "height", h);
+  set_num(env, out, "min", mm[0]);
+  set_num(env, out, "max", mm[1]);
+  napi_set_named_property(env, out, "data", arr);
+  return out;
+}
+
 /* setPyramidShape(ctx, width0, height0, params); setLevel(ctx, kind, octave, level, Float32Array) */
 static napi_value SetPyramidShape(napi_env env, napi_callback_info info)
 {
@@ -493,7 +522,7 @@ NAPI_EXTERN napi_value napi_register_module_v1(napi_env env, napi_value exports)
 {
   static const struct { const char *name; napi_callback fn; } table[] = {
     { "create", Create }, { "version", Version }, { "detect", Detect }, { "detectBatch", DetectBatch },
-    { "buildScaleSpace", BuildScaleSpace }, { "pyramidInfo", PyramidInfo }, { "getLevel", GetLevel },
+    { "buildScaleSpace", BuildScaleSpace }, { "pyramidInfo", PyramidInfo }, { "getLevel", GetLevel }, { "levelPreview", LevelPreview },
     { "setPyramidShape", SetPyramidShape }, { "setLevel", SetLevel }, { "findCandidates", FindCandidates },
     { "refine", Refine }, { "blurChunk", BlurChunk }, { "subtractChunk", SubtractChunk },
     { "findExtremas", FindExtremas }, { "gradientHessian", GradientHessian }, { "linearResize", LinearResize },

@@ -233,6 +233,17 @@ int main(int argc, char **argv)
     napi_value lvl = call(env, exports, "getLevel", 4, gl), lw, lh;
     napi_get_named_property(env, lvl, "width", &lw);
     napi_get_named_property(env, lvl, "height", &lh);
+    /* display product: DoG level 1 of octave 0, min/max-normalised -> Uint8ClampedArray RGBA */
+    napi_value pv[6] = { ctx, mk_num(1), mk_num(0), mk_num(1), mk_num(2), mk_num(1) };
+    napi_value prev = call(env, exports, "levelPreview", 6, pv), pdata;
+    if (env->pending) { printf("threw %s: %s\n", env->code, env->msg); return 1; }
+    napi_get_named_property(env, prev, "data", &pdata);
+    {
+      unsigned long long sum = 0;
+      const unsigned char *pb = (const unsigned char *)pdata->ptr;
+      for (size_t i = 0; i < pdata->len; i++) sum += pb[i] * (unsigned long long)(1 + (i & 3));
+      printf("preview bytes %zu clamped %d checksum %llu\n", pdata->len, pdata->ta == napi_uint8_clamped_array, sum);
+    }
     napi_value fb = mk(V_BOOL);
     napi_value fc[3] = { ctx, mk(V_UNDEF), fb };
     napi_value cr = call(env, exports, "findCandidates", 3, fc), ccnt, crec;

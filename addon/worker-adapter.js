@@ -4,13 +4,16 @@
 // addon, so the reference's own main.js can run unmodified against the GPU engine:
 //   const background_thread = new SiftWorker();  background_thread.onmessage = e => ...;
 //   workerComputeGaussianScaleSpace(background_thread, {...})      // reference src/worker.js:29
-import { computeGaussianScaleSpace, computeDifferenceOfGaussians, findCandidateKeypoints, refineCandidateKeypoints } from './background.js';
+import { computeGaussianScaleSpace, computeDifferenceOfGaussians, findCandidateKeypoints, refineCandidateKeypoints, levelPreviews } from './background.js';
+import { LEVEL } from './native.js';
 
 export const WorkerMessageTypes = {
   COMPUTE_GAUSSIAN_SCALE_SPACE: 'compute-gaussian-scale-space',
   RECEIVED_GAUSSIAN_SCALE_SPACE: 'received-gaussian-scale-space',
+  RECEIVED_GAUSSIAN_BLURRED_IMAGE: 'received-gaussian-blurred-image',
   COMPUTE_DIFFERENCE_OF_GAUSSIANS: 'compute-difference-of-gaussians',
   RECEIVED_DIFFERENCE_OF_GAUSSIANS: 'received-difference-of-gaussians',
+  RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE: 'received-difference-of-gaussian-image',
   FIND_CANDIDATE_KEYPOINTS: 'find-candidate-keypoints',
   RECEIVED_CANDIDATE_KEYPOINTS: 'received-candidate-keypoints',
   REFINE_CANDIDATE_KEYPOINTS: 'refine-candidate-keypoints',
@@ -19,15 +22,22 @@ export const WorkerMessageTypes = {
 
 export class SiftWorker {
   onmessage = null;
+  // previews: also post the per-level images the reference's canvas consumes (main.js:150-165), before the
+  // stage reply as the reference does.  The per-chunk repaint messages (RECEIVED_*_CHUNK) and the candidate
+  // markers are progressive-display only and are not emitted.
+  constructor({ previews = false } = {}) { this.previews = previews; }
   postMessage(message) {
     const T = WorkerMessageTypes;
     let reply;
+    const extra = [];
     switch (message.type) {                                            // background.js:18-49
       case T.COMPUTE_GAUSSIAN_SCALE_SPACE:
         reply = { type: T.RECEIVED_GAUSSIAN_SCALE_SPACE, scaleSpace: computeGaussianScaleSpace(message) };
+        if (this.previews) for (const p of levelPreviews(LEVEL.GAUSSIAN)) extra.push({ type: T.RECEIVED_GAUSSIAN_BLURRED_IMAGE, ...p });
         break;
       case T.COMPUTE_DIFFERENCE_OF_GAUSSIANS:
         reply = { type: T.RECEIVED_DIFFERENCE_OF_GAUSSIANS, differenceOfGaussians: computeDifferenceOfGaussians(message.scaleSpace) };
+        if (this.previews) for (const p of levelPreviews(LEVEL.DOG)) extra.push({ type: T.RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE, ...p });
         break;
       case T.FIND_CANDIDATE_KEYPOINTS:
         reply = { type: T.RECEIVED_CANDIDATE_KEYPOINTS, candidateKeypoints: findCandidateKeypoints(message) };
@@ -38,6 +48,6 @@ export class SiftWorker {
       default:
         return;
     }
-    queueMicrotask(() => this.onmessage && this.onmessage({ data: reply }));
+    queueMicrotask(() => { if (this.onmessage) for (const m of [...extra, reply]) this.onmessage({ data: m }); });
   }
 }

@@ -223,6 +223,15 @@ SIFT_API int sift_get_pyramid_info(const sift_ctx *ctx, int *octaves, int *level
 SIFT_API int sift_get_octave_size(const sift_ctx *ctx, int octave, int *width, int *height);
 SIFT_API int sift_get_blur_level(const sift_ctx *ctx, int kind, int octave, int level, double *blur_level);
 SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, float *dst /* h*w dense */);
+/* Display products of one level of the held pyramid: an RGBA8 image in ImageData layout
+ * (w*h*4 bytes, R=G=B=grey, A=255), as the reference posts beside each stage result.
+ *   SIFT_PREVIEW_GRAY     Math.round(v*255)                    ImageUtils_convertMatrix2DToImageData, image-utils.js:171-220
+ *   SIFT_PREVIEW_SIGMOID  1/(1+exp(coefficient*(-v))) first    Matrix2D_sigmoidNormalize, matrix2d.js:148-156 (5: background.js:307)
+ *   SIFT_PREVIEW_MINMAX   (v-min)/(max-min) of the level first Matrix2D_sampledNormalize, matrix2d.js:169-192 (background.js:336)
+ * min_max (optional, 2 doubles) receives the level's min / max in MINMAX mode, {0, 1} otherwise. */
+enum { SIFT_PREVIEW_GRAY = 0, SIFT_PREVIEW_SIGMOID = 1, SIFT_PREVIEW_MINMAX = 2 };
+SIFT_API int sift_get_level_preview(sift_ctx *ctx, int kind, int octave, int level, int mode, double coefficient,
+                                    unsigned char *rgba_out /* h*w*4 */, double *min_max);
 /* Replace a DoG level of the held pyramid with caller data (used by the host mirror
  * when refineCandidateKeypoints / findCandidateKeypoints receive foreign matrices). */
 SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, const sift_params *params);

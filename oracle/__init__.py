@@ -82,6 +82,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.oracle_js_round.restype = C.c_double
         L.oracle_js_round.argtypes = [C.c_double]
+        L.oracle_preview.argtypes = [_DP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, _DP]
         L.oracle_contrast_threshold.restype = C.c_double
         L.oracle_contrast_threshold.argtypes = [C.c_int, C.c_double]
         L.oracle_kernel_radius.argtypes = [C.c_double]
@@ -145,6 +146,19 @@ def default_params(**kw) -> Params:
 
 def js_round(x: float) -> float:
     return lib().oracle_js_round(float(x))
+
+
+PREVIEW_GRAY, PREVIEW_SIGMOID, PREVIEW_MINMAX = 0, 1, 2
+
+
+def preview(m, mode: int = PREVIEW_GRAY, coefficient: float = 1.0):
+    """RGBA8 ImageData bytes [rows, cols, 4] of a matrix + (min, max) (image-utils.js:171-220, matrix2d.js:148-192)."""
+    a = _img(m)
+    out = np.zeros(a.shape + (4,), dtype=np.uint8)
+    mm = np.zeros(2, dtype=np.float64)
+    if lib().oracle_preview(_dp(a), a.shape[0], a.shape[1], mode, float(coefficient), out.ctypes.data, _dp(mm)) != 0:
+        raise ValueError("oracle_preview: bad arguments")
+    return out, (float(mm[0]), float(mm[1]))
 
 
 def kernel_radius(sigma: float) -> int:

@@ -209,6 +209,32 @@ def step_function_vectors(ref_root):
     return out
 
 
+def preview_vectors(ref_root):
+    """The display products: Matrix2D_sigmoidNormalize / Matrix2D_sampledNormalize /
+    ImageUtils_convertMatrix2DToImageData of the unmodified reference on small matrices."""
+    w = ReferenceWorker(ref_root)
+    rng = np.random.default_rng(77)
+    out = {}
+    g = rng.random((9, 13))
+    g[0, :6] = [0.0, 1.0, 0.5, 127.5 / 255, 1.2, -0.3]            # exact tie of Math.round, values outside [0, 1]
+    d = (rng.random((9, 13)) - 0.5) * 0.3
+    conv = w.image_utils["ImageUtils_convertMatrix2DToImageData"]
+
+    def pixels(image_data):
+        return np.frombuffer(bytes(image_data["data"].buf), dtype=np.uint8).reshape(9, 13, 4).copy()
+
+    out["gray_in"] = g
+    out["gray_rgba"] = pixels(conv(13, 9, jsmini.JSObject(grayChannelMatrix=g.tolist())))
+    out["dog_in"] = d
+    sig = w.matrix2d["Matrix2D_sigmoidNormalize"](d.tolist(), 5)                      # background.js:303-307
+    out["sigmoid_matrix"] = np.array(sig)
+    out["sigmoid_rgba"] = pixels(conv(13, 9, jsmini.JSObject(grayChannelMatrix=sig)))
+    mm = w.matrix2d["Matrix2D_sampledNormalize"](d.tolist())                          # background.js:336
+    out["minmax_matrix"] = np.array(mm)
+    out["minmax_rgba"] = pixels(conv(13, 9, jsmini.JSObject(grayChannelMatrix=mm)))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -225,6 +251,9 @@ def main():
         sv = step_function_vectors(args.ref)
         np.savez_compressed(os.path.join(args.out, "ref_steps.npz"), **sv)
         print(f"ref_steps.npz {time.time() - t0:.1f}s", flush=True)
+    if args.only in (None, "preview"):
+        np.savez_compressed(os.path.join(args.out, "ref_preview.npz"), **preview_vectors(args.ref))
+        print("ref_preview.npz", flush=True)
     for name, (w_, h_, seed, blobs, n_oct, spo, mb, ab, ingest) in CASES.items():
         if args.only not in (None, name):
             continue

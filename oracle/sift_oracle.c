@@ -43,6 +43,42 @@ double oracle_js_round(double x)
   return (x - f >= 0.5) ? f + 1.0 : f;
 }
 
+/* ------------------------------------------------------ display products -- */
+
+/* The ImageData the reference posts beside a stage result:
+ *   GRAY     image-utils.js:171-220  gray path: Math.round(v * 255) stored into a Uint8ClampedArray
+ *            (clamped to 0..255, NaN -> 0), alpha 255
+ *   SIGMOID  matrix2d.js:148-156     1 / (1 + Math.exp(coefficient * (-1 * v))) first (background.js:303-307)
+ *   MINMAX   matrix2d.js:169-192     (v - min) / (max - min), min/max sampled over the matrix, starting
+ *            from MAX_SAFE_INTEGER / MIN_SAFE_INTEGER (background.js:336) */
+int oracle_preview(const double *m, int rows, int cols, int mode, double coefficient,
+                   unsigned char *rgba, double *min_max)
+{
+  double mn = 9007199254740991.0, mx = -9007199254740991.0;
+  if (!m || !rgba || rows < 1 || cols < 1) return -1;
+  if (mode == ORACLE_PREVIEW_MINMAX) {
+    for (int i = 0; i < rows; i++)
+      for (int j = 0; j < cols; j++) {
+        const double v = m[(size_t)i * cols + j];
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+      }
+  }
+  if (min_max) { min_max[0] = mode == ORACLE_PREVIEW_MINMAX ? mn : 0.0; min_max[1] = mode == ORACLE_PREVIEW_MINMAX ? mx : 1.0; }
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      const double v = m[(size_t)i * cols + j];
+      double t = v;
+      if (mode == ORACLE_PREVIEW_SIGMOID) t = 1 / (1 + exp(coefficient * (-1 * v)));
+      else if (mode == ORACLE_PREVIEW_MINMAX) t = (v - mn) / (mx - mn);
+      const double r = oracle_js_round(t * 255);
+      const unsigned char g = (unsigned char)(r >= 255.0 ? 255 : (r >= 0.0 ? (int)r : 0));   /* NaN -> 0 */
+      unsigned char *px = rgba + ((size_t)i * cols + j) * 4;
+      px[0] = g; px[1] = g; px[2] = g; px[3] = 255;
+    }
+  return 0;
+}
+
 /* ---------------------------------------------------------------- resize -- */
 
 /* matrix2d.js:112-138  Matrix2D_linearResize.  The loop counters are doubles

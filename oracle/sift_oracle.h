@@ -55,6 +55,9 @@ enum {
 };
 
 double oracle_js_round(double x);
+enum { ORACLE_PREVIEW_GRAY = 0, ORACLE_PREVIEW_SIGMOID = 1, ORACLE_PREVIEW_MINMAX = 2 };
+int oracle_preview(const double *m, int rows, int cols, int mode, double coefficient,
+                   unsigned char *rgba, double *min_max);
 int oracle_linear_resize_dims(int rows, int cols, double rate, int *orows, int *ocols);
 int oracle_linear_resize(const double *in, int rows, int cols, double rate, double *out);
 int oracle_kernel_radius(double sigma);

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libsift_b200.so")
 SIFT_OK, SIFT_ERR_BAD_ARGS, SIFT_ERR_CUDA, SIFT_ERR_CAPACITY, SIFT_ERR_UNSUPPORTED, SIFT_ERR_NO_DEVICE, \
     SIFT_ERR_STATE = range(7)
 SIFT_U8, SIFT_F32, SIFT_F64, SIFT_RGBA8 = range(4)
+SIFT_PREVIEW_GRAY, SIFT_PREVIEW_SIGMOID, SIFT_PREVIEW_MINMAX = 0, 1, 2
 SIFT_LEVEL_GAUSSIAN, SIFT_LEVEL_DOG = 0, 1
 PROF_KINDS = ("blur_octave0", "blur_octave1", "blur_high_octaves", "scan", "refine")
 
@@ -114,6 +115,7 @@ PROTOTYPES = {
     "sift_get_octave_size": (C.c_int, [_VP, C.c_int, _IP, _IP]),
     "sift_get_blur_level": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _DP]),
     "sift_get_level": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _FP]),
+    "sift_get_level_preview": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, _DP]),
     "sift_set_pyramid_shape": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(Params)]),
     "sift_set_level": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _FP]),
     "sift_blur_chunk": (C.c_int, [_VP, _DP, C.c_int, C.c_int, _DP, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -33,10 +33,39 @@ def _params(number_of_octaves=5, scales_per_octave=3, min_blur_level=0.8, assume
                             minBlurLevel=float(min_blur_level), assumedBlur=float(assumed_blur), **extra)
 
 
+# message types of the per-level display products (src/worker.js:9, 14)
+RECEIVED_GAUSSIAN_BLURRED_IMAGE = "received-gaussian-blurred-image"
+RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE = "received-difference-of-gaussian-image"
+
+
+def _post_level_images(eng: Engine, kind: int, post_message):
+    """The ImageData the reference posts per level: Gaussian levels as grey (background.js:
+    136-143, 212-220), DoG levels min/max-normalised (background.js:331-338); {type, imageData, octave}."""
+    n_oct, nlev = eng.pyramid_info()
+    dog = kind == L.SIFT_LEVEL_DOG
+    for o in range(n_oct):
+        for s in range(nlev - (1 if dog else 0)):
+            rgba, _ = eng.level_preview(kind, o, s, L.SIFT_PREVIEW_MINMAX if dog else L.SIFT_PREVIEW_GRAY)
+            post_message({"type": RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE if dog else RECEIVED_GAUSSIAN_BLURRED_IMAGE,
+                          "imageData": {"width": rgba.shape[1], "height": rgba.shape[0], "data": rgba},
+                          "octave": o})
+
+
+def dogChunkPreview(octave: int, scale: int, chunk: dict, engine: Engine | None = None):
+    """One chunk of a resident DoG level as the reference paints it while subtracting: sigmoid-normalised,
+    coefficient 5 (background.js:303-317; matrix2d.js:148-156).  chunk = {x1, y1, x2, y2}, half-open."""
+    eng = engine or default_engine()
+    rgba, _ = eng.level_preview(L.SIFT_LEVEL_DOG, octave, scale, L.SIFT_PREVIEW_SIGMOID, 5.0)
+    crop = np.ascontiguousarray(rgba[chunk["y1"]:chunk["y2"], chunk["x1"]:chunk["x2"]])
+    return {"imageData": {"width": crop.shape[1], "height": crop.shape[0], "data": crop}, "dx": chunk["x1"], "dy": chunk["y1"]}
+
+
 def computeGaussianScaleSpace(input_image, number_of_octaves=5, scales_per_octave=3, min_blur_level=0.8,
-                              assumed_blur=0.5, chunk_size=32, engine: Engine | None = None, **thresholds):
+                              assumed_blur=0.5, chunk_size=32, engine: Engine | None = None, post_message=None,
+                              **thresholds):
     """scale_space[o][s] = {blurLevel, image} (background.js:57-70, 233-236).  chunk_size only
-    shaped the reference's progressive repaint (background.js:181-203); results do not depend on it."""
+    shaped the reference's progressive repaint (background.js:181-203); results do not depend on it.
+    post_message: optional callable receiving the per-level RECEIVED_GAUSSIAN_BLURRED_IMAGE messages."""
     eng = engine or default_engine()
     prm = _params(number_of_octaves, scales_per_octave, min_blur_level, assumed_blur, **thresholds)
     eng.build_scale_space(input_image, prm)
@@ -48,6 +77,8 @@ def computeGaussianScaleSpace(input_image, number_of_octaves=5, scales_per_octav
     _serial[0] += 1
     reply.engine, reply.params, reply.serial = eng, prm, _serial[0]
     eng._resident_serial = _serial[0]
+    if post_message is not None:
+        _post_level_images(eng, L.SIFT_LEVEL_GAUSSIAN, post_message)
     return reply
 
 
@@ -55,8 +86,10 @@ def _is_resident(obj, eng) -> bool:
     return isinstance(obj, _Resident) and obj.engine is eng and getattr(eng, "_resident_serial", None) == obj.serial
 
 
-def computeDifferenceOfGaussians(scale_space, chunk_size=32, engine: Engine | None = None):
-    """D[o][s-1] = S[o][s-1] - S[o][s], blurLevel of S[o][s-1] (background.js:258-354)."""
+def computeDifferenceOfGaussians(scale_space, chunk_size=32, engine: Engine | None = None, post_message=None):
+    """D[o][s-1] = S[o][s-1] - S[o][s], blurLevel of S[o][s-1] (background.js:258-354).
+    post_message: optional callable receiving the per-level RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE messages
+    (resident pyramids only)."""
     eng = engine or (scale_space.engine if isinstance(scale_space, _Resident) and scale_space.engine else default_engine())
     reply = _Resident()
     if _is_resident(scale_space, eng):
@@ -67,6 +100,8 @@ def computeDifferenceOfGaussians(scale_space, chunk_size=32, engine: Engine | No
             reply.append([{"blurLevel": eng.blur_level(L.SIFT_LEVEL_DOG, o, s),
                            "image": eng.get_level(L.SIFT_LEVEL_DOG, o, s)} for s in range(nlev - 1)])
         reply.engine, reply.params, reply.serial = eng, scale_space.params, scale_space.serial
+        if post_message is not None:
+            _post_level_images(eng, L.SIFT_LEVEL_DOG, post_message)
         return reply
     # foreign scale space: subtract level pairs on the GPU (SIFT_subtractMatrix2DChunk over the whole image)
     for octave in scale_space:

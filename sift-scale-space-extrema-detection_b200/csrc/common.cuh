@@ -110,6 +110,10 @@ void launch_scan_f64(cudaStream_t st, const double *d0, const double *d1, const 
                      double pix_threshold, int32_t *cand_xy, double *cand_val, int cand_cap,
                      int32_t *low_xy, double *low_val, int low_cap, int *counts /* [2] */);
 
+// preview.cu: display products (RGBA8) of one level
+int launch_preview(cudaStream_t st, const float *src, int w, int h, size_t pitch, int mode, double coefficient,
+                   void *scratch32, void *d_out);
+
 // order.cu: device-side ordering of keypoint records (reference order: octave, scale, row, column)
 size_t order_scratch_bytes(int n_sort);
 int launch_order_keypoints(cudaStream_t st, const sift_keypoint *kp, const Counters *ctr, int n_sort, void *scratch,

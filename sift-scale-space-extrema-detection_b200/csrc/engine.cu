@@ -1288,6 +1288,31 @@ SIFT_API int sift_get_level(sift_ctx *ctx, int kind, int octave, int level, floa
   return SIFT_OK;
 }
 
+SIFT_API int sift_get_level_preview(sift_ctx *ctx, int kind, int octave, int level, int mode, double coefficient,
+                                    unsigned char *rgba_out, double *min_max)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!rgba_out) return fail(ctx, SIFT_ERR_BAD_ARGS, "rgba_out is NULL");
+  if (mode < SIFT_PREVIEW_GRAY || mode > SIFT_PREVIEW_MINMAX) return fail(ctx, SIFT_ERR_BAD_ARGS, "unknown preview mode %d", mode);
+  if (!ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "no pyramid built");
+  float *p = plane_ptr(ctx, kind, octave, level);
+  if (!p) return fail(ctx, SIFT_ERR_BAD_ARGS, "no level kind %d octave %d level %d", kind, octave, level);
+  CK(cudaSetDevice(ctx->device));
+  const OctaveDev &od = ctx->L->octs[octave];
+  const size_t bytes = (size_t)od.w * od.h * 4;
+  int rc;
+  if ((rc = grow(ctx, ctx->L->order, bytes + 64))) return rc;          // scratch shared with the ordering path
+  char *d = (char *)ctx->L->order.p;
+  ctx->launches += launch_preview(ctx->L->stream, p, od.w, od.h, od.pitch, mode, coefficient, d, d + 64);
+  if (cudaGetLastError() != cudaSuccess) return fail(ctx, SIFT_ERR_CUDA, "preview launch failed");
+  CK(cudaMemcpyAsync(rgba_out, d + 64, bytes, cudaMemcpyDeviceToHost, ctx->L->stream));
+  double mm[2] = { 0.0, 1.0 };
+  CK(cudaMemcpyAsync(mm, d + 16, sizeof mm, cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
+  if (min_max) { min_max[0] = mm[0]; min_max[1] = mm[1]; }
+  return SIFT_OK;
+}
+
 SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, const sift_params *params)
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;

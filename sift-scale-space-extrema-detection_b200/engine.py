@@ -216,6 +216,17 @@ class Engine:
         self._check(self._lib.sift_get_level(self._h, kind, octave, level, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
+    def level_preview(self, kind: int, octave: int, level: int, mode: int = L.SIFT_PREVIEW_GRAY,
+                      coefficient: float = 1.0):
+        """RGBA8 display product of a level (ImageData layout [h, w, 4]) and the (min, max) used:
+        GRAY = image-utils.js:171-220, SIGMOID = matrix2d.js:148-156, MINMAX = matrix2d.js:169-192."""
+        w, h = self.octave_size(octave)
+        out = np.empty((h, w, 4), np.uint8)
+        mm = np.zeros(2, np.float64)
+        self._check(self._lib.sift_get_level_preview(self._h, kind, octave, level, mode, float(coefficient),
+                                                     out.ctypes.data, mm.ctypes.data_as(C.POINTER(C.c_double))))
+        return out, (float(mm[0]), float(mm[1]))
+
     def set_pyramid_shape(self, width0: int, height0: int, params: L.Params):
         self._check(self._lib.sift_set_pyramid_shape(self._h, width0, height0, C.byref(params)))
 

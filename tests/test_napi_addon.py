@@ -23,7 +23,7 @@ def _run(*args):
 def test_addon_registers_and_reports_its_version():
     r = _run("version")
     assert r.returncode == 0, r.stderr
-    assert "exports 16" in r.stdout and "version sift_b200" in r.stdout
+    assert "exports 17" in r.stdout and "version sift_b200" in r.stdout
 
 
 def test_addon_create_throws_without_a_gpu():
@@ -51,4 +51,8 @@ def test_addon_detect_equals_the_python_host(engine, tmp_path):
     assert f"count {len(want)} stats.keypoints {len(want)}" in r.stdout
     assert got.tobytes() == want.tobytes() and len(want) > 50
     assert "short buffer threw SIFT_ERR_BAD_ARGS" in r.stdout
+    engine.build_scale_space(u8, L.default_params(numberOfOctaves=4, minBlurLevel=1.6))
+    rgba, _ = engine.level_preview(L.SIFT_LEVEL_DOG, 0, 1, L.SIFT_PREVIEW_MINMAX)
+    checksum = int((rgba.reshape(-1, 4).astype(np.uint64) * np.array([1, 2, 3, 4], dtype=np.uint64)).sum())
+    assert f"preview bytes {rgba.size} clamped 1 checksum {checksum}" in r.stdout
     assert f"stages octaves 4 levels 6 dog0_1 {2 * w}x{2 * h} candidates {stats['candidates']} refined {len(want)}" in r.stdout
