@@ -268,6 +268,24 @@ SIFT_API int sift_strip_seed(sift_ctx *ctx, int octave, double **d_seed);
 SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave);
 /* Scan + refine over all octaves: keypoints of the owned rows, global coordinates, reference order. */
 SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *n_out, sift_stats *stats);
+/* A refinement walk (background.js:480-668) may jump to a row this strip does not hold: the reference moves
+ * the sample by Math.round(alpha) with no bound (background.js:638-640).  Such a walk is not decided here:
+ * it is handed out as a sift_walk -- the state of the loop at the jump -- and continued by the strip that
+ * owns the new row.  stats.leftStrip counts them; the walk's final outcome is counted by whoever ends it. */
+typedef struct sift_walk {
+  int32_t octave, scaleLevel, x, y; /* current sample: DoG scale s, column n, row m of the GLOBAL octave grid */
+  int32_t iteration;                /* iterations already spent: the loop resumes at this index (< maxIterations) */
+  float value;                      /* DoG value of the ORIGINAL candidate (background.js:565 keeps using it) */
+  int32_t candScale, candX, candY;  /* the original candidate (ordering key of the record it may become) */
+  int32_t reserved0;
+} sift_walk;                        /* 40 bytes */
+/* Walks that left this strip during the last sift_strip_finish / sift_strip_resume. */
+SIFT_API int sift_strip_escaped(sift_ctx *ctx, sift_walk *out, int cap, int *n_out);
+/* Continue walks on this strip's pyramid (call it on the strip that OWNS row walks[i].y; a walk whose row this
+ * strip does not hold comes straight back through sift_strip_escaped).  Keypoints in reference order; stats
+ * carries the outcomes of the walks ended here (candidates = 0). */
+SIFT_API int sift_strip_resume(sift_ctx *ctx, const sift_walk *walks, int n, sift_keypoint *out, int cap, int *n_out,
+                               sift_stats *stats);
 
 /* ----------------------------------------------------- fine step functions */
 /* src/sift.js:72  float64 in / out like Matrix2D; half-open chunk; writes only the chunk of output. */

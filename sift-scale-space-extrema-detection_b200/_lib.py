@@ -75,6 +75,10 @@ KEYPOINT_DTYPE = np.dtype([("octave", "<i4"), ("scaleLevel", "<i4"), ("localX", 
                            ("candScale", "<i4"), ("candX", "<i4"), ("candY", "<i4"), ("iterations", "<i4")])
 CANDIDATE_DTYPE = np.dtype([("octave", "<i4"), ("scaleLevel", "<i4"), ("x", "<i4"), ("y", "<i4"),
                             ("value", "<f4"), ("reserved0", "<i4")])
+# sift_walk: a refinement walk handed from one mosaic strip to another (include/sift_b200.h)
+WALK_DTYPE = np.dtype([("octave", "<i4"), ("scaleLevel", "<i4"), ("x", "<i4"), ("y", "<i4"), ("iteration", "<i4"),
+                       ("value", "<f4"), ("candScale", "<i4"), ("candX", "<i4"), ("candY", "<i4"), ("reserved0", "<i4")])
+assert WALK_DTYPE.itemsize == 40
 assert KEYPOINT_DTYPE.itemsize == C.sizeof(Keypoint) == 80
 assert CANDIDATE_DTYPE.itemsize == C.sizeof(Candidate) == 24
 
@@ -107,6 +111,8 @@ PROTOTYPES = {
     "sift_strip_seed": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "sift_strip_octave": (C.c_int, [_VP, C.c_int]),
     "sift_strip_finish": (C.c_int, [_VP, _VP, C.c_int, _IP, C.POINTER(Stats)]),
+    "sift_strip_escaped": (C.c_int, [_VP, _VP, C.c_int, _IP]),
+    "sift_strip_resume": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, _IP, C.POINTER(Stats)]),
     "sift_build_scale_space": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Params)]),
     "sift_build_dog": (C.c_int, [_VP]),
     "sift_find_candidates": (C.c_int, [_VP, C.POINTER(Params), _VP, C.c_int, _IP, _VP, C.c_int, _IP]),

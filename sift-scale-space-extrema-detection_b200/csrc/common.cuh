@@ -25,6 +25,9 @@ struct OctaveDev {
   // is the strip y_top = 0, gh = h, own = [0, h), seed_off = 0.
   int y_top, gh, own0, own1;
   int seed_off;        // local row (y >> 1) + seed_off of the next octave receives this octave's even row y
+  // local rows [valid0, valid1) hold the whole image's values: a level row within the largest radius of a strip
+  // edge that is not an image edge was blurred against the strip's clamp, not against the neighbour's rows
+  int valid0, valid1;
 };
 
 // Per-level blur description (host computed, background.js:156-177 + sift.js:38).
@@ -41,7 +44,7 @@ struct Counters {
   int n_low;           // low-contrast extrema (when counted)
   int n_kp;            // keypoints appended
   int outcomes[8];     // refine outcomes, index = REFINE_* below
-  int n_left_strip;    // refinement walks that left the strip's halo (not the image): resolved by a wider margin
+  int n_left_strip;    // refinement walks that left the rows this strip holds (not the image): handed out as sift_walk
   int pad[4];
 };
 
@@ -124,8 +127,11 @@ struct RefineParams {
   int spo, ndog, max_iter;
   double offset_bound, contrast_thr, edge_thr, min_blur, min_interpixel;
 };
+// walks / walk_cap: where walks that leave a strip's rows are recorded (slot = Counters::n_left_strip); may be NULL
 void launch_refine(cudaStream_t st, const OctaveDev *d_octs, int n_octs, const sift_candidate *cand,
                    const int *d_ncand, int n_cand_host /* -1: read d_ncand */, int cand_cap, RefineParams rp,
-                   sift_keypoint *out, int cap, Counters *ctr);
+                   sift_keypoint *out, int cap, Counters *ctr, sift_walk *walks, int walk_cap);
+void launch_refine_resume(cudaStream_t st, const OctaveDev *d_octs, const sift_walk *in, int n, RefineParams rp,
+                          sift_keypoint *out, int cap, Counters *ctr, sift_walk *walks, int walk_cap);
 void launch_grad_hess_f64(cudaStream_t st, const double *dm, const double *dc, const double *dp, int cols,
                           int m, int n, double *out12);

@@ -33,7 +33,7 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, order;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, order, walks;
   bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
   int tma_blur[SIFT_MAX_OCTAVES];   // per octave: maps of its T^T planes start at tmaps_t[tma_blur[o]] (-1: none)
   int cand_cap = 0, kp_cap = 0;
@@ -72,6 +72,7 @@ struct sift_ctx {
   int n_oct = 0, nlev = 0;
   int ow[SIFT_MAX_OCTAVES], oh[SIFT_MAX_OCTAVES];
   bool is_strip = false;                // the octave images are row strips of a mosaic (sift_strip_*)
+  std::vector<sift_walk> escaped;       // refinement walks that left the strip in the last finish / resume
   sift_strip_layout strip;
   int strip_next_octave = 0;            // octave sift_strip_octave expects next
   int strip_dtype = 0;
@@ -369,10 +370,15 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
       memset(&od, 0, sizeof od);
       od.w = ow[o]; od.h = oh[o]; od.pitch = (ow[o] + 31) & ~31; od.nlev = nlev;
       od.y_top = 0; od.gh = oh[o]; od.own0 = 0; od.own1 = oh[o]; od.seed_off = 0;
+      od.valid0 = 0; od.valid1 = oh[o];
       if (ctx->is_strip) {
         const sift_strip_layout &sl = ctx->strip;
         od.y_top = sl.top[o]; od.gh = sl.height[o]; od.own0 = sl.own0[o] - sl.top[o]; od.own1 = sl.own1[o] - sl.top[o];
         od.seed_off = (o + 1 < n_oct) ? sl.top[o] / 2 - sl.top[o + 1] : 0;
+        int rmax = 0;
+        for (int s = 0; s < nlev; s++) rmax = std::max(rmax, ctx->plans[o][s].radius);
+        od.valid0 = sl.top[o] == 0 ? 0 : std::min(rmax, od.own0);
+        od.valid1 = sl.bottom[o] == sl.height[o] ? oh[o] : std::max(oh[o] - rmax, od.own1);
       }
       const size_t pe = (size_t)od.h * od.pitch;
       for (int s = 0; s < nlev; s++) { od.gauss[s] = pp; pp += pe; }
@@ -550,12 +556,17 @@ static RefineParams refine_params(const sift_ctx *ctx, const sift_params *over)
   return rp;
 }
 
+#define WALK_CAP 65536       // refinement walks leaving a strip per finish / resume call (a handful in practice)
 static int run_refine(sift_ctx *ctx, int n_cand_host, sift_keypoint *d_out, int cap, const sift_params *over = nullptr)
 {
   prof_begin(ctx, SIFT_PROF_REFINE);
+  if (ctx->is_strip) {                                     // walks that leave the strip are recorded, not decided
+    int rc = grow(ctx, ctx->L->walks, 2 * (size_t)WALK_CAP * sizeof(sift_walk));   // [0, CAP): out, [CAP, 2 CAP): resume input
+    if (rc) return rc;
+  }
   launch_refine(ctx->L->stream, ctx->L->d_octs, ctx->n_oct, (const sift_candidate *)ctx->L->cand.p,
                 &dev_counters(ctx)->n_cand, n_cand_host, ctx->L->cand_cap, refine_params(ctx, over), d_out, cap,
-                dev_counters(ctx));
+                dev_counters(ctx), ctx->is_strip ? (sift_walk *)ctx->L->walks.p : nullptr, WALK_CAP);
   prof_end(ctx);
   ctx->launches += 1;
   CK(cudaGetLastError());
@@ -762,7 +773,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.order };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.order, &ln.walks };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);
@@ -1401,6 +1412,7 @@ SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave)
   return SIFT_OK;
 }
 
+static int fetch_escaped(sift_ctx *ctx, const Counters &c);
 SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *n_out, sift_stats *stats)
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;
@@ -1414,9 +1426,78 @@ SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *
   sift_keypoint *kps;
   if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
   ctx->last = c;
+  if ((rc = fetch_escaped(ctx, c))) return rc;
   fill_stats(stats, c, 0, 0.f, (int)(ctx->launches - l0));
   *n_out = c.n_kp;
   sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
+  if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
+  return SIFT_OK;
+}
+
+// Download the walks the last refine launch recorded (Counters::n_left_strip of them) into ctx->escaped.
+static int fetch_escaped(sift_ctx *ctx, const Counters &c)
+{
+  ctx->escaped.clear();
+  if (c.n_left_strip <= 0) return SIFT_OK;
+  if (c.n_left_strip > WALK_CAP) return fail(ctx, SIFT_ERR_CAPACITY, "%d refinement walks left the strip (capacity %d): widen the margin", c.n_left_strip, WALK_CAP);
+  ctx->escaped.resize((size_t)c.n_left_strip);
+  CK(cudaMemcpyAsync(ctx->escaped.data(), ctx->L->walks.p, (size_t)c.n_left_strip * sizeof(sift_walk), cudaMemcpyDeviceToHost, ctx->L->stream));
+  CK(cudaStreamSynchronize(ctx->L->stream));
+  // deterministic hand-over order, whatever order the threads finished in
+  std::sort(ctx->escaped.begin(), ctx->escaped.end(), [](const sift_walk &a, const sift_walk &b) {
+    return cand_key(a.octave, a.candScale, a.candY, a.candX) < cand_key(b.octave, b.candScale, b.candY, b.candX);
+  });
+  return SIFT_OK;
+}
+
+SIFT_API int sift_strip_escaped(sift_ctx *ctx, sift_walk *out, int cap, int *n_out)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!n_out || cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad output arguments");
+  if (!ctx->is_strip) return fail(ctx, SIFT_ERR_STATE, "no strip in progress");
+  *n_out = (int)ctx->escaped.size();
+  if (*n_out > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d walks, capacity %d", *n_out, cap);
+  if (*n_out) memcpy(out, ctx->escaped.data(), ctx->escaped.size() * sizeof(sift_walk));
+  return SIFT_OK;
+}
+
+SIFT_API int sift_strip_resume(sift_ctx *ctx, const sift_walk *walks, int n, sift_keypoint *out, int cap, int *n_out,
+                               sift_stats *stats)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  if (!n_out || n < 0 || (n > 0 && !walks) || cap < 0 || (cap > 0 && !out)) return fail(ctx, SIFT_ERR_BAD_ARGS, "bad arguments");
+  if (!ctx->is_strip || !ctx->pyramid_built) return fail(ctx, SIFT_ERR_STATE, "run every octave with sift_strip_octave first");
+  if (n > WALK_CAP) return fail(ctx, SIFT_ERR_CAPACITY, "%d walks, at most %d per call", n, WALK_CAP);
+  for (int i = 0; i < n; i++) {
+    const sift_walk &w = walks[i];
+    if (w.octave < 0 || w.octave >= ctx->n_oct || w.scaleLevel < 1 || w.scaleLevel >= ctx->nlev - 2 || w.iteration < 0 ||
+        w.x < 1 || w.x >= ctx->L->octs[w.octave].w - 1 || w.y < 1 || w.y >= ctx->L->octs[w.octave].gh - 1)
+      return fail(ctx, SIFT_ERR_BAD_ARGS, "walk %d is outside the DoG volume", i);
+  }
+  CK(cudaSetDevice(ctx->device));
+  ctx->L = &ctx->lanes[0];
+  const int64_t l0 = ctx->launches;
+  int rc;
+  Counters c;
+  memset(&c, 0, sizeof c);
+  sift_keypoint *kps = nullptr;
+  *n_out = 0;
+  ctx->escaped.clear();
+  if (n > 0) {
+    if ((rc = grow(ctx, ctx->L->walks, 2 * (size_t)WALK_CAP * sizeof(sift_walk)))) return rc;
+    sift_walk *d_in = (sift_walk *)ctx->L->walks.p + WALK_CAP;
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
+    CK(cudaMemcpyAsync(d_in, walks, (size_t)n * sizeof(sift_walk), cudaMemcpyHostToDevice, ctx->L->stream));
+    launch_refine_resume(ctx->L->stream, ctx->L->d_octs, d_in, n, refine_params(ctx, nullptr), dev_keypoints(ctx),
+                         ctx->L->kp_cap, dev_counters(ctx), (sift_walk *)ctx->L->walks.p, WALK_CAP);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if ((rc = download_keypoints(ctx, &c, &kps))) return rc;
+    if ((rc = fetch_escaped(ctx, c))) return rc;
+    *n_out = c.n_kp;
+    sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
+  }
+  fill_stats(stats, c, 0, 0.f, (int)(ctx->launches - l0));
   if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
   return SIFT_OK;
 }

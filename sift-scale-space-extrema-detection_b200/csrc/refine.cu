@@ -78,82 +78,121 @@ __device__ __forceinline__ bool inverse3x3(const double m[3][3], double inv[3][3
   return true;
 }
 
+// One walk of the loop at background.js:480-668, from any iteration (a fresh candidate starts at it = 0 on its
+// own pixel; a walk handed over by another strip resumes where it left).  m is a row of the whole image; the
+// strip holds rows [ytop, ytop + oc.h).
+__device__ __forceinline__ void refine_walk(const OctaveDev *__restrict__ octs, const sift_walk w0, const RefineParams &rp,
+                                            sift_keypoint *__restrict__ out, int cap, Counters *ctr,
+                                            sift_walk *__restrict__ walks, int walk_cap)
+{
+  const OctaveDev &oc = octs[w0.octave];
+  DogView<float> D;
+#pragma unroll
+  for (int i = 0; i < SIFT_MAX_LEVELS; i++) D.pl[i] = oc.dog[i];
+  D.pitch = oc.pitch;
+  const int rows = oc.gh, cols = oc.w, ytop = oc.y_top;
+  int s = w0.scaleLevel, m = w0.y, nn = w0.x, it = w0.iteration;
+  const double value = (double)w0.value;
+  int outcome = REFINE_NO_CONVERGENCE;
+  // the 3x3x3 neighbourhood of the sample must lie in rows that hold the whole image's values
+  bool left_strip = m - ytop - 1 < oc.valid0 || m - ytop + 1 >= oc.valid1;     // (handed to the wrong strip)
+  sift_keypoint kp;
+  for (; !left_strip && it < rp.max_iter; it++) {                                // background.js:480
+    double g[3], h[3][3], inv[3][3];
+    grad_hess(D, s, m - ytop, nn, g, h);
+    if (!inverse3x3(h, inv)) { outcome = REFINE_SINGULAR; break; }               // matrix2d.js:482 (Q7)
+    double a[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {                                                // matrix2d.js:454, 527-537
+      double res = 0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) res += (inv[r][c] * -1) * g[c];
+      a[r] = res;
+    }
+    if (fabs(a[0]) < rp.offset_bound && fabs(a[1]) < rp.offset_bound && fabs(a[2]) < rp.offset_bound) {  // :558
+      const double omega = value + (((0.5 * a[0]) * g[0]) + ((0.5 * a[1]) * g[1]) + ((0.5 * a[2]) * g[2])); // :565
+      if (fabs(omega) < rp.contrast_thr) { outcome = REFINE_LOW_CONTRAST; break; }                          // :577
+      const double tr = 0 + h[1][1] + h[2][2];                                   // :592
+      const double det = (h[1][1] * h[2][2]) - (h[1][2] * h[2][1]);              // :593
+      const double edgeness = (tr * tr) / det;                                   // :594
+      if (edgeness > rp.edge_thr) { outcome = REFINE_EDGE; break; }              // :599 (NaN / negative pass, Q6)
+      const double delta = exp2((double)(w0.octave - 1));                        // :611 Math.pow(2, octave-1), exact
+      kp.octave = w0.octave; kp.scaleLevel = s; kp.localX = nn; kp.localY = m;
+      kp.absoluteY = delta * (a[1] + m);                                         // :612
+      kp.absoluteX = delta * (a[2] + nn);                                        // :613
+      kp.absoluteSigma = (delta / rp.min_interpixel) * rp.min_blur * pow(2.0, (a[0] + s) / rp.spo);         // :614
+      kp.interpolatedValue = omega;
+      kp.offset[0] = (float)a[0]; kp.offset[1] = (float)a[1]; kp.offset[2] = (float)a[2];
+      kp.dogValue = w0.value;
+      kp.candScale = w0.candScale; kp.candX = w0.candX; kp.candY = w0.candY; kp.iterations = it;
+      outcome = REFINE_ACCEPTED;
+      break;
+    }
+    s = (int)js_round(s + a[0]);                                                 // :638-640
+    m = (int)js_round(m + a[1]);
+    nn = (int)js_round(nn + a[2]);
+    if (s < 1 || s >= rp.ndog - 1) { outcome = REFINE_LEFT_SCALE; break; }       // :644
+    if (m < 1 || m >= rows - 1) { outcome = REFINE_LEFT_ROWS; break; }           // :651
+    if (nn < 1 || nn >= cols - 1) { outcome = REFINE_LEFT_COLS; break; }         // :658
+    if (m - ytop - 1 < oc.valid0 || m - ytop + 1 >= oc.valid1) { left_strip = true; it++; break; }   // inside the image, outside this strip's valid rows
+  }
+  if (left_strip && it < rp.max_iter) {
+    // undecided: the strip that owns row m continues at iteration `it` (sift_strip_resume)
+    const int slot = atomicAdd(&ctr->n_left_strip, 1);
+    if (walks && slot < walk_cap) {
+      sift_walk w = w0;
+      w.scaleLevel = s; w.y = m; w.x = nn; w.iteration = it;
+      walks[slot] = w;
+    }
+    return;
+  }
+  // (a walk that jumped out on its last iteration never looks at the new sample: background.js:480 ends the loop)
+  atomicAdd(&ctr->outcomes[outcome], 1);
+  if (outcome == REFINE_ACCEPTED) {
+    const int slot = atomicAdd(&ctr->n_kp, 1);
+    if (slot < cap) out[slot] = kp;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 refine_kernel(const OctaveDev *__restrict__ octs, const sift_candidate *__restrict__ cand,
               const int *__restrict__ d_ncand, int n_cand_host, int cand_cap, RefineParams rp,
-              sift_keypoint *__restrict__ out, int cap, Counters *ctr)
+              sift_keypoint *__restrict__ out, int cap, Counters *ctr, sift_walk *__restrict__ walks, int walk_cap)
 {
   int n = (n_cand_host >= 0) ? n_cand_host : *d_ncand;
   if (n > cand_cap) n = cand_cap;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const sift_candidate cd = cand[idx];
-    const OctaveDev &oc = octs[cd.octave];
-    DogView<float> D;
-#pragma unroll
-    for (int i = 0; i < SIFT_MAX_LEVELS; i++) D.pl[i] = oc.dog[i];
-    D.pitch = oc.pitch;
-    const int rows = oc.gh, cols = oc.w, ytop = oc.y_top;    // m is a row of the whole image; the strip holds rows [ytop, ytop + oc.h)
-    int s = cd.scaleLevel, m = cd.y, nn = cd.x;
-    const double value = (double)cd.value;
-    int outcome = REFINE_NO_CONVERGENCE;
-    bool left_strip = false;
-    sift_keypoint kp;
-    for (int it = 0; it < rp.max_iter; it++) {                                     // background.js:480
-      double g[3], h[3][3], inv[3][3];
-      grad_hess(D, s, m - ytop, nn, g, h);
-      if (!inverse3x3(h, inv)) { outcome = REFINE_SINGULAR; break; }               // matrix2d.js:482 (Q7)
-      double a[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {                                                // matrix2d.js:454, 527-537
-        double res = 0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) res += (inv[r][c] * -1) * g[c];
-        a[r] = res;
-      }
-      if (fabs(a[0]) < rp.offset_bound && fabs(a[1]) < rp.offset_bound && fabs(a[2]) < rp.offset_bound) {  // :558
-        const double omega = value + (((0.5 * a[0]) * g[0]) + ((0.5 * a[1]) * g[1]) + ((0.5 * a[2]) * g[2])); // :565
-        if (fabs(omega) < rp.contrast_thr) { outcome = REFINE_LOW_CONTRAST; break; }                          // :577
-        const double tr = 0 + h[1][1] + h[2][2];                                   // :592
-        const double det = (h[1][1] * h[2][2]) - (h[1][2] * h[2][1]);              // :593
-        const double edgeness = (tr * tr) / det;                                   // :594
-        if (edgeness > rp.edge_thr) { outcome = REFINE_EDGE; break; }              // :599 (NaN / negative pass, Q6)
-        const double delta = exp2((double)(cd.octave - 1));                        // :611 Math.pow(2, octave-1), exact
-        kp.octave = cd.octave; kp.scaleLevel = s; kp.localX = nn; kp.localY = m;
-        kp.absoluteY = delta * (a[1] + m);                                         // :612
-        kp.absoluteX = delta * (a[2] + nn);                                        // :613
-        kp.absoluteSigma = (delta / rp.min_interpixel) * rp.min_blur * pow(2.0, (a[0] + s) / rp.spo);         // :614
-        kp.interpolatedValue = omega;
-        kp.offset[0] = (float)a[0]; kp.offset[1] = (float)a[1]; kp.offset[2] = (float)a[2];
-        kp.dogValue = cd.value;
-        kp.candScale = cd.scaleLevel; kp.candX = cd.x; kp.candY = cd.y; kp.iterations = it;
-        outcome = REFINE_ACCEPTED;
-        break;
-      }
-      s = (int)js_round(s + a[0]);                                                 // :638-640
-      m = (int)js_round(m + a[1]);
-      nn = (int)js_round(nn + a[2]);
-      if (s < 1 || s >= rp.ndog - 1) { outcome = REFINE_LEFT_SCALE; break; }       // :644
-      if (m < 1 || m >= rows - 1) { outcome = REFINE_LEFT_ROWS; break; }           // :651
-      if (m - ytop < 1 || m - ytop >= oc.h - 1) { outcome = REFINE_LEFT_ROWS; left_strip = true; break; }   // walked out of the strip's halo
-      if (nn < 1 || nn >= cols - 1) { outcome = REFINE_LEFT_COLS; break; }         // :658
-    }
-    atomicAdd(&ctr->outcomes[outcome], 1);
-    if (left_strip) atomicAdd(&ctr->n_left_strip, 1);
-    if (outcome == REFINE_ACCEPTED) {
-      const int slot = atomicAdd(&ctr->n_kp, 1);
-      if (slot < cap) out[slot] = kp;
-    }
+    sift_walk w;
+    w.octave = cd.octave; w.scaleLevel = cd.scaleLevel; w.x = cd.x; w.y = cd.y; w.iteration = 0; w.value = cd.value;
+    w.candScale = cd.scaleLevel; w.candX = cd.x; w.candY = cd.y; w.reserved0 = 0;
+    refine_walk(octs, w, rp, out, cap, ctr, walks, walk_cap);
   }
+}
+
+__global__ void __launch_bounds__(128)
+refine_resume_kernel(const OctaveDev *__restrict__ octs, const sift_walk *__restrict__ in, int n, RefineParams rp,
+                     sift_keypoint *__restrict__ out, int cap, Counters *ctr, sift_walk *__restrict__ walks, int walk_cap)
+{
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+    refine_walk(octs, in[idx], rp, out, cap, ctr, walks, walk_cap);
 }
 
 void launch_refine(cudaStream_t st, const OctaveDev *d_octs, int n_octs, const sift_candidate *cand,
                    const int *d_ncand, int n_cand_host, int cand_cap, RefineParams rp, sift_keypoint *out, int cap,
-                   Counters *ctr)
+                   Counters *ctr, sift_walk *walks, int walk_cap)
 {
   (void)n_octs;
   int blocks = 148 * 4;
   if (n_cand_host >= 0) blocks = max(1, min(blocks, (n_cand_host + 127) / 128));
-  refine_kernel<<<blocks, 128, 0, st>>>(d_octs, cand, d_ncand, n_cand_host, cand_cap, rp, out, cap, ctr);
+  refine_kernel<<<blocks, 128, 0, st>>>(d_octs, cand, d_ncand, n_cand_host, cand_cap, rp, out, cap, ctr, walks, walk_cap);
+}
+
+void launch_refine_resume(cudaStream_t st, const OctaveDev *d_octs, const sift_walk *in, int n, RefineParams rp,
+                          sift_keypoint *out, int cap, Counters *ctr, sift_walk *walks, int walk_cap)
+{
+  if (n <= 0) return;
+  refine_resume_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_octs, in, n, rp, out, cap, ctr, walks, walk_cap);
 }
 
 // ---- step functions SIFT_generateGradientVector / SIFT_generateHessianMatrix on Matrix2D (fp64) ----

@@ -166,7 +166,7 @@ scan_all_kernel(const OctaveDev *__restrict__ octs, ScanAllArgs A, sift_candidat
   const int t = blockIdx.x - t0;
   const int ty = t / ntx, tx = t - ty * ntx;
   const OctaveDev &oc = octs[o];
-  const int w = oc.w, h = oc.h;
+  const int w = oc.w;
   const size_t pitch = oc.pitch;
   const int x0 = tx * SA_TW + threadIdx.x * SA_PX;
   const int y = ty * SA_TH + threadIdx.y;

@@ -181,11 +181,28 @@ class Engine:
             n = C.c_int()
             st = L.Stats()
             rc = self._lib.sift_strip_finish(self._h, out.ctypes.data, cap, C.byref(n), C.byref(st))
-            if rc == L.SIFT_ERR_CAPACITY:
+            if rc == L.SIFT_ERR_CAPACITY and n.value > cap:
                 cap = n.value
                 continue
             self._check(rc)
             return out[:n.value], st.as_dict()
+
+    def strip_escaped(self) -> np.ndarray:
+        """Refinement walks that left this strip's rows in the last strip_finish / strip_resume (WALK_DTYPE)."""
+        n = C.c_int()
+        out = np.zeros(1 << 16, dtype=L.WALK_DTYPE)
+        self._check(self._lib.sift_strip_escaped(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def strip_resume(self, walks: np.ndarray, capacity: int = 1 << 12):
+        """Continue walks (WALK_DTYPE) on this strip's pyramid; returns (keypoints, stats of the walks ended here)."""
+        w = np.ascontiguousarray(walks, dtype=L.WALK_DTYPE)
+        cap = max(capacity, len(w))
+        out = np.zeros(cap, dtype=L.KEYPOINT_DTYPE)
+        n = C.c_int()
+        st = L.Stats()
+        self._check(self._lib.sift_strip_resume(self._h, w.ctypes.data, len(w), out.ctypes.data, cap, C.byref(n), C.byref(st)))
+        return out[:n.value], st.as_dict()
 
     # -- stages
     def build_scale_space(self, image, params: L.Params, rgba: bool = False):

@@ -12,8 +12,10 @@ from each neighbour.  Each strip is one `Engine` on one GPU:
     keypoints = engine.strip_finish()                         # scan + refine of the owned rows, global coordinates
 
 Per-pixel arithmetic does not depend on the decomposition (same taps, same order), so the union of the
-strips' keypoints is bit-identical to the whole-image result (tests/test_mosaic.py), provided no refinement
-walk left a strip's halo (`stats["leftStrip"] == 0`; a larger `margin` fixes that).
+strips' keypoints is bit-identical to the whole-image result (tests/test_mosaic.py).  A refinement walk may
+jump to a row its strip does not hold (background.js:638-640 moves by Math.round(alpha), unbounded): the strip
+hands the walk's state out (`strip_escaped`), the strip that owns the new row continues it (`strip_resume`),
+until every walk has ended (`resolve_escaped_*`; at most maxIterations - 1 rounds).
 
 `detect_mosaic_local` drives several engines from one process (tests; or all GPUs of a box from one host
 thread); `detect_mosaic_distributed` is the one-process-per-GPU form on `torch.distributed` (NCCL over
@@ -109,12 +111,13 @@ def source_rows(image: np.ndarray, layout: L.StripLayout) -> np.ndarray:
     return np.ascontiguousarray(image[layout.top[0] // 2:(layout.bottom[0] + 1) // 2])
 
 
-def detect_mosaic_local(engines: list, image: np.ndarray, params: L.Params, margin: int = 16):
+def detect_mosaic_local(engines: list, image: np.ndarray, params: L.Params, margin: int = 16, layouts: list | None = None):
     """All strips from one process (engine i = strip i; the engines may sit on different GPUs or share one).
-    Halo rows move device to device with torch copies.  Returns (keypoints in reference order, per-strip stats)."""
+    Halo rows move device to device with torch copies.  `layouts`: explicit cuts (default: plan_strips).
+    Returns (keypoints in reference order, per-strip stats, layouts)."""
     import torch
     h, w = image.shape[:2]
-    layouts = plan_strips(params, w, h, len(engines), margin)
+    layouts = layouts or plan_strips(params, w, h, len(engines), margin)
     for eng, lay in zip(engines, layouts):
         eng.strip_begin(params, lay, source_rows(image, lay))
     for o in range(params.numberOfOctaves):
@@ -132,7 +135,72 @@ def detect_mosaic_local(engines: list, image: np.ndarray, params: L.Params, marg
         k, st = eng.strip_finish()
         parts.append(k)
         stats.append(st)
+    resolve_escaped_local(engines, layouts, parts, stats)
     return merge_keypoints(parts), stats, layouts
+
+
+_OUTCOMES = ("keypoints", "rejLowContrast", "rejEdge", "rejLeftScale", "rejLeftRows", "rejLeftCols", "rejNoConvergence",
+             "rejSingular")
+
+
+def owner_of(layouts: list, octave: int, row: int) -> int:
+    """The strip that owns global row `row` of `octave` (owned ranges tile the octave's rows)."""
+    for r, lay in enumerate(layouts):
+        if lay.own0[octave] <= row < lay.own1[octave]:
+            return r
+    raise ValueError(f"row {row} of octave {octave} is owned by no strip")
+
+
+def _add_outcomes(total: dict, part: dict):
+    for k in _OUTCOMES:
+        total[k] += part[k]
+    total["kernelLaunches"] += part["kernelLaunches"]
+
+
+def resolve_escaped_local(engines: list, layouts: list, parts: list, stats: list, max_rounds: int = 8):
+    """Continue, on the owning strips, the refinement walks that left a strip (all engines in this process).
+    parts[i] / stats[i] are extended in place with the keypoints / outcomes decided by strip i."""
+    pending = [e.strip_escaped() for e in engines]
+    for _ in range(max_rounds):
+        walks = np.concatenate(pending) if pending else np.zeros(0, dtype=L.WALK_DTYPE)
+        if len(walks) == 0:
+            return
+        owners = np.array([owner_of(layouts, int(w["octave"]), int(w["y"])) for w in walks])
+        pending = []
+        for r, eng in enumerate(engines):
+            mine = walks[owners == r]
+            if len(mine) == 0:
+                continue
+            k, st = eng.strip_resume(mine)
+            parts[r] = np.concatenate([parts[r], k])
+            _add_outcomes(stats[r], st)
+            pending.append(eng.strip_escaped())
+    raise RuntimeError("refinement walks still unresolved after %d rounds" % max_rounds)
+
+
+def resolve_escaped_distributed(engine, layouts: list, rank: int, kps: np.ndarray, stats: dict, dist=None,
+                                max_rounds: int = 8):
+    """One process per strip: every round all ranks share their escaped walks (a few 40-byte records), each
+    continues the ones whose row it owns.  Returns this rank's keypoints with the newly decided ones appended."""
+    import torch.distributed as tdist
+    dist = dist or tdist
+    world = dist.get_world_size()
+    mine_out = engine.strip_escaped()
+    for _ in range(max_rounds):
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine_out.tobytes())
+        walks = np.concatenate([np.frombuffer(b, dtype=L.WALK_DTYPE) for b in gathered])
+        if len(walks) == 0:
+            return kps
+        owners = np.array([owner_of(layouts, int(w["octave"]), int(w["y"])) for w in walks])
+        mine = walks[owners == rank]
+        mine_out = np.zeros(0, dtype=L.WALK_DTYPE)
+        if len(mine):
+            k, st = engine.strip_resume(mine)
+            kps = np.concatenate([kps, k])
+            _add_outcomes(stats, st)
+            mine_out = engine.strip_escaped()
+    raise RuntimeError("refinement walks still unresolved after %d rounds" % max_rounds)
 
 
 def detect_mosaic_distributed(engine, image_rows: np.ndarray, layouts: list, params: L.Params, rank: int):
@@ -145,7 +213,9 @@ def detect_mosaic_distributed(engine, image_rows: np.ndarray, layouts: list, par
         if o > 0:
             exchange_seed_halos(seed_tensor(engine, lay, o), layouts, o, rank)
         engine.strip_octave(o)
-    return engine.strip_finish()
+    kps, stats = engine.strip_finish()
+    kps = resolve_escaped_distributed(engine, layouts, rank, kps, stats)
+    return kps, stats
 
 
 def merge_keypoints(parts: list) -> np.ndarray:

@@ -76,6 +76,38 @@ def _gloo_worker(rank, world, port, q):
             seed[own0 - top:own1 - top] = rows[own0 - top:own1 - top]          # only the owned rows are known
             M.exchange_seed_halos(seed, lays, o, rank)
             ok = ok and bool(torch.equal(seed, rows))                            # halos now hold the neighbours' rows
+        # hand-over of refinement walks that left a strip: the protocol, with a stand-in for the GPU engine.  Every
+        # walk bounces to the other strip until its third iteration, then becomes a keypoint where it stands.
+        class FakeStrip:
+            def __init__(self, first):
+                self.out = first
+
+            def strip_escaped(self):
+                return self.out
+
+            def strip_resume(self, walks):
+                assert all(M.owner_of(lays, int(w["octave"]), int(w["y"])) == rank for w in walks)
+                go = walks[walks["iteration"] < 3].copy()
+                go["iteration"] += 1
+                go["y"] = [lays[1 - rank].own0[int(o)] + 3 for o in go["octave"]]          # a row the other strip owns
+                self.out = go
+                end = walks[walks["iteration"] >= 3]
+                k = np.zeros(len(end), dtype=L2.KEYPOINT_DTYPE)
+                k["octave"], k["candY"], k["localY"], k["iterations"] = end["octave"], end["candY"], end["y"], end["iteration"]
+                st = {n: 0 for n in M._OUTCOMES}
+                st.update(keypoints=len(k), kernelLaunches=1)
+                return k, st
+        first = np.zeros(3, dtype=L2.WALK_DTYPE)
+        first["octave"] = [0, 1, 2]
+        first["iteration"] = [1, 2, 3]
+        first["candY"] = 100 * (rank + 1) + np.arange(3)
+        first["y"] = [lays[1 - rank].own0[o] + 1 for o in (0, 1, 2)]                      # jumped into the other strip
+        stats = {n: 0 for n in M._OUTCOMES}
+        stats["kernelLaunches"] = 0
+        mine = M.resolve_escaped_distributed(FakeStrip(first), lays, rank, np.zeros(0, dtype=L2.KEYPOINT_DTYPE), stats)
+        # walks that started at iteration 1 / 2 / 3 end after 3 / 2 / 1 hops: on this / the other / this... strip
+        ok = ok and stats["keypoints"] == len(mine) == 3 and all(mine["iterations"] == 3)
+        ok = ok and all(M.owner_of(lays, int(k["octave"]), int(k["localY"])) == rank for k in mine)
         kp = np.zeros(2, dtype=L2.KEYPOINT_DTYPE)
         kp["octave"] = rank
         kp["candY"] = [5 + rank, 1 + rank]
@@ -115,16 +147,74 @@ def test_strips_are_bit_identical_to_the_whole_image(engine, world, w, h, n_oct)
     engines = [sift_b200.Engine(0) for _ in range(world)]
     try:
         got, stats, lays = mosaic.detect_mosaic_local(engines, u8, prm, margin=16)
-        assert sum(s["leftStrip"] for s in stats) == 0
         assert len(got) == len(whole) and len(whole) > 20
         assert got.tobytes() == whole.tobytes()
         assert sum(s["candidates"] for s in stats) == st_whole["candidates"]
+        for k in mosaic._OUTCOMES:                                   # every walk ended exactly once, the same way
+            assert sum(s[k] for s in stats) == st_whole[k], k
         for r, (eng, lay) in enumerate(zip(engines, lays)):
             for o in range(n_oct):
                 for s in range(5):
                     d = eng.get_level(L.SIFT_LEVEL_DOG, o, s)
                     a, b = lay.own0[o] - lay.top[o], lay.own1[o] - lay.top[o]
                     assert np.array_equal(d[a:b], levels[(o, s)][lay.own0[o]:lay.own1[o]]), (r, o, s)
+    finally:
+        for e in engines:
+            e.close()
+
+
+@pytest.mark.gpu
+def test_refinement_walks_that_leave_a_strip_are_continued_by_the_owner(engine):
+    """background.js:638-640 moves a sample by Math.round(alpha), unbounded: with a thin margin some walks jump to
+    rows their strip does not hold.  They are handed to the owning strip and end exactly as in the whole image."""
+    w, h, n_oct, world = 192, 1536, 3, 2
+    u8 = fixtures.synthetic_u8(w, h, 5, blobs=w * h // 64, sigma_lo=0.6, sigma_hi=2.0)
+    prm = _params(n_oct)
+    whole, st_whole = engine.detect(u8, prm)
+    # cut the image right behind the candidate of the longest vertical walk, so that the walk ends in the other strip
+    H0, cut0 = 2 * h, None
+    for kp in whole[np.argsort(-np.abs(whole["localY"] - whole["candY"]))][:8]:
+        o = int(kp["octave"])
+        ya, yb = sorted((int(kp["candY"]), int(kp["localY"])))
+        align = max(1, (1 << (n_oct - 1)) >> o)                  # octave-0 cuts are multiples of 2^(octaves-1)
+        c = (ya // align + 1) * align
+        if yb - c >= 5 and 300 <= (c << o) <= H0 - 300:
+            cut0 = c << o
+            break
+    assert cut0 is not None, "fixture has no refinement walk of 6+ rows: pick another seed"
+    lays = [mosaic.strip_layout(prm, w, h, 0, cut0, 2), mosaic.strip_layout(prm, w, h, cut0, H0, 2)]
+    engines = [sift_b200.Engine(0) for _ in range(world)]
+    try:
+        got, stats, lays = mosaic.detect_mosaic_local(engines, u8, prm, layouts=lays)
+        escaped = sum(s["leftStrip"] for s in stats)
+        assert escaped >= 1
+        assert got.tobytes() == whole.tobytes() and len(whole) > 1000
+        for k in mosaic._OUTCOMES:
+            assert sum(s[k] for s in stats) == st_whole[k], k
+        # the mechanism, directly: a fresh walk (iteration 0 on the candidate's pixel) resumed on the owner gives the
+        # whole-image record; on a strip that does not hold the row it comes straight back, untouched
+        moved = whole[(whole["iterations"] >= 1) & (whole["octave"] == 0)][:50]
+        assert len(moved) >= 10
+        walks = np.zeros(len(moved), dtype=L.WALK_DTYPE)
+        walks["octave"] = moved["octave"]; walks["scaleLevel"] = moved["candScale"]; walks["x"] = moved["candX"]
+        walks["y"] = moved["candY"]; walks["value"] = moved["dogValue"]; walks["candScale"] = moved["candScale"]
+        walks["candX"] = moved["candX"]; walks["candY"] = moved["candY"]
+        owners = np.array([mosaic.owner_of(lays, 0, int(y)) for y in walks["y"]])
+        for r in sorted(set(owners.tolist())):
+            k, st = engines[r].strip_resume(walks[owners == r])
+            later = engines[r].strip_escaped()
+            done = moved[owners == r]
+            keep = ~np.isin(done["candY"] * 100000 + done["candX"], later["candY"] * 100000 + later["candX"])
+            assert k.tobytes() == done[keep].tobytes() and st["keypoints"] == len(k)
+        far = 1 - int(owners[0])
+        sel = (owners == owners[0]) & (np.abs(walks["y"] - lays[far].own0[0]) > 100) & (np.abs(walks["y"] - lays[far].own1[0]) > 100)
+        k, st = engines[far].strip_resume(walks[sel])
+        back = engines[far].strip_escaped()
+        assert len(k) == 0 and st["leftStrip"] == len(back) == int(sel.sum()) > 0
+        assert back.tobytes() == np.sort(walks[sel], order=["octave", "candScale", "candY", "candX"]).tobytes()
+        with pytest.raises(sift_b200.SiftError):
+            bad = walks[:1].copy(); bad["y"] = 10 ** 6
+            engines[0].strip_resume(bad)
     finally:
         for e in engines:
             e.close()
@@ -141,3 +231,13 @@ def test_engine_returns_to_whole_images_after_a_strip(engine):
         engine.strip_octave(1)                                     # octaves run in order
     after, _ = engine.detect(u8, prm)
     assert before.tobytes() == after.tobytes()
+
+
+def test_strip_generator_equals_the_whole_image_rows():
+    """tools/mosaic_run.py: each rank generates only the source rows of its strip (counter-based PRNG)."""
+    from sift_b200 import fixtures
+    w, h = 211, 157
+    whole = fixtures.synthetic_u8(w, h, 4321, blobs=40)
+    for y0, y1 in ((0, 157), (0, 1), (30, 97), (150, 157), (-5, 20), (140, 400)):
+        got = fixtures.synthetic_u8_rows(w, h, y0, y1, 4321, blobs=40)
+        assert np.array_equal(got, whole[max(0, y0):min(h, y1)])

@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--octaves", type=int, default=4)
-    ap.add_argument("--margin", type=int, default=32)
+    ap.add_argument("--margin", type=int, default=64)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
@@ -35,9 +35,12 @@ def main():
     prm = L.default_params(numberOfOctaves=args.octaves, minBlurLevel=1.6)
     layouts = mosaic.plan_strips(prm, W, H, world, args.margin)
     lay = layouts[rank]
-    # every rank builds the same seeded mosaic and keeps its rows (the generator is cheap next to 32768^2 I/O)
-    img = fixtures.synthetic_u8(W, H, 4321, blobs=max(64, W * H // 16384))
-    rows = mosaic.source_rows(img, lay)
+    # every rank generates the source rows of its own strip (+ octave-0 halo) of the same seeded mosaic: the
+    # generator is counter-based, nobody holds the whole 32768^2 image
+    nblobs = max(64, W * H // 16384)
+    t_gen = time.perf_counter()
+    rows = fixtures.synthetic_u8_rows(W, H, lay.top[0] // 2, (lay.bottom[0] + 1) // 2, 4321, blobs=nblobs)
+    t_gen = time.perf_counter() - t_gen
     eng = sift_b200.Engine(local)
     times = []
     for _ in range(args.reps):
@@ -51,10 +54,12 @@ def main():
     dist.all_reduce(left)
     if rank == 0:
         line = {"mosaic": f"{W}x{H}", "octaves": args.octaves, "n_gpus": world, "strips": world, "margin": args.margin,
-                "keypoints": int(len(merged)), "left_strip": int(left.item()), "seconds": min(times),
+                "keypoints": int(len(merged)), "walks_handed_over": int(left.item()), "seconds": min(times),
                 "mpixel_per_s": W * H / 1e6 / min(times),
-                "halo_rows": [int(lay.halo[o]) for o in range(args.octaves)]}
+                "halo_rows": [int(lay.halo[o]) for o in range(args.octaves)], "strip_source_rows": int(rows.shape[0]),
+                "generate_s": round(t_gen, 2), "reps_s": [round(t, 4) for t in times]}
         if args.verify:
+            img = fixtures.synthetic_u8(W, H, 4321, blobs=nblobs)
             whole, _ = eng.detect(img, prm)
             line["identical_to_whole_image"] = bool(whole.tobytes() == merged.tobytes())
             line["whole_keypoints"] = int(len(whole))
