@@ -164,6 +164,8 @@ class Engine:
     # -- mosaic strips (see mosaic.py)
     def strip_begin(self, params: L.Params, layout: L.StripLayout, rows, rgba: bool = False):
         a, dt, w, h = _as_image(rows, rgba)
+        self._strip_cap = max(getattr(self, "_strip_cap", 0), 1 << 16,
+                              (layout.own1[0] - layout.own0[0]) * layout.width[0] // 64)
         self._check(self._lib.sift_strip_begin(self._h, C.byref(params), C.byref(layout), a.ctypes.data, dt, 0))
 
     def strip_seed(self, octave: int) -> int:
@@ -174,17 +176,20 @@ class Engine:
     def strip_octave(self, octave: int):
         self._check(self._lib.sift_strip_octave(self._h, octave))
 
-    def strip_finish(self, capacity: int = 1 << 16):
-        cap = capacity
+    def strip_finish(self, capacity: int | None = None):
+        """Scan + refine of the strip's owned rows.  The output capacity follows the strip's previous result (a
+        retry repeats the scan and the refinement), starting from one record per 64 owned octave-0 pixels."""
+        cap = capacity or getattr(self, "_strip_cap", 1 << 16)
         while True:
-            out = np.zeros(cap, dtype=L.KEYPOINT_DTYPE)
+            out = np.empty(cap, dtype=L.KEYPOINT_DTYPE)
             n = C.c_int()
             st = L.Stats()
             rc = self._lib.sift_strip_finish(self._h, out.ctypes.data, cap, C.byref(n), C.byref(st))
             if rc == L.SIFT_ERR_CAPACITY and n.value > cap:
-                cap = n.value
+                cap = n.value + n.value // 8
                 continue
             self._check(rc)
+            self._strip_cap = max(cap, n.value + n.value // 8)
             return out[:n.value], st.as_dict()
 
     def strip_escaped(self) -> np.ndarray:

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--margin", type=int, default=64)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--phases", action="store_true", help="time upload / octaves (exchange + blur) / scan+refine separately")
+    ap.add_argument("--pinned", action="store_true", help="keep the strip's source rows in pinned host memory")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -41,7 +43,28 @@ def main():
     t_gen = time.perf_counter()
     rows = fixtures.synthetic_u8_rows(W, H, lay.top[0] // 2, (lay.bottom[0] + 1) // 2, 4321, blobs=nblobs)
     t_gen = time.perf_counter() - t_gen
+    if args.pinned:
+        pin = torch.from_numpy(rows).pin_memory()
+        rows = pin.numpy()
     eng = sift_b200.Engine(local)
+    phases = {}
+    if args.phases:                                      # the same steps as mosaic.detect_mosaic_distributed, timed one by one
+        def tick(name, t0):
+            torch.cuda.synchronize(); dist.barrier()
+            phases[name] = round(time.perf_counter() - t0, 4)
+        for _ in range(2):
+            dist.barrier(); t0 = time.perf_counter()
+            eng.strip_begin(prm, lay, rows); tick("upload", t0)
+            for o in range(args.octaves):
+                t0 = time.perf_counter()
+                if o > 0:
+                    mosaic.exchange_seed_halos(mosaic.seed_tensor(eng, lay, o), layouts, o, rank)
+                    tick(f"exchange_{o}", t0); t0 = time.perf_counter()
+                eng.strip_octave(o); tick(f"octave_{o}", t0)
+            t0 = time.perf_counter()
+            k, st = eng.strip_finish(); tick("scan_refine_download_order", t0)
+            t0 = time.perf_counter()
+            mosaic.resolve_escaped_distributed(eng, layouts, rank, k, st); tick("walk_handover", t0)
     times = []
     for _ in range(args.reps):
         dist.barrier(); torch.cuda.synchronize()
@@ -58,6 +81,8 @@ def main():
                 "mpixel_per_s": W * H / 1e6 / min(times),
                 "halo_rows": [int(lay.halo[o]) for o in range(args.octaves)], "strip_source_rows": int(rows.shape[0]),
                 "generate_s": round(t_gen, 2), "reps_s": [round(t, 4) for t in times]}
+        if phases:
+            line["phases_s"] = phases
         if args.verify:
             img = fixtures.synthetic_u8(W, H, 4321, blobs=nblobs)
             whole, _ = eng.detect(img, prm)
