@@ -10,8 +10,8 @@ Workload (BASELINE.json configs[1]): 1920x1080 synthetic frames, 4 octaves x 3 s
 
 Own arm, one JSON line on rank 0:
   value    device-resident throughput (inputs already in HBM), CUDA events on the engine's stream, max over ranks
-  e2e      the same through sift_detect() (C ABI, HOST buffers): H2D of the u8 frame and D2H of the
-           keypoint records inside the timed region
+  e2e      the same through sift_detect_batch() (C ABI, HOST buffers): H2D of the u8 frames, D2H and ordering of
+           the keypoint records inside the timed region
   roofline dominant kernel class (octave-0 blur+DoG) against the measured HBM peak, plus the whole-path figure
   cpu_baseline  the float64 oracle (port of the reference's dense 2D algorithm) on one host core, bounded sample
 """

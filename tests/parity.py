@@ -43,7 +43,7 @@ def _cand_key(c):
     return (int(c["octave"]), int(c["scale"] if "scale" in c else c["scaleLevel"]), int(c["y"]), int(c["x"]))
 
 
-def check_candidates(cands, ora, near_tol=1e-5):
+def check_candidates(cands, ora, near_tol=1e-5, pix_thr=0.012):
     """cands: structured CANDIDATE_DTYPE in reference order. Mismatches must sit on the pre-filter threshold
     or be float32 ties of the 26-neighbourhood."""
     got = [(int(c["octave"]), int(c["scaleLevel"]), int(c["y"]), int(c["x"])) for c in cands]
@@ -54,7 +54,7 @@ def check_candidates(cands, ora, near_tol=1e-5):
     for k in sg ^ sw:
         o, s, y, x = k
         v = ora.dog[o][s][y, x]
-        near_thr = abs(abs(v) - 0.012) <= near_tol * 0.012 * 10
+        near_thr = abs(abs(v) - pix_thr) <= near_tol * pix_thr * 10
         nb = np.stack([ora.dog[o][s + d][y - 1:y + 2, x - 1:x + 2] for d in (-1, 0, 1)]).ravel()
         nb = np.delete(nb, 13)
         tie = np.min(np.abs(nb - v)) <= max(abs(v), DOG_FLOOR) * 1e-6   # closer than float32 can tell apart

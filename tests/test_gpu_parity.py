@@ -51,6 +51,48 @@ def test_reference_default_blur_level(engine):
     check_keypoints(kps, ora)
 
 
+@pytest.mark.parametrize("spo", [1, 2, 4, 5])
+def test_other_scales_per_octave(engine, spo):
+    """scalesPerOctave != 3: spo + 3 levels per octave, k = 2^(1/spo) (background.js:100, 157), pre-filter
+    0.8 * 0.015 * (2^(1/spo) - 1) / (2^(1/3) - 1) (sift.js:285-293); spo = 5 takes the non-TMA scan."""
+    u8 = fixtures.synthetic_u8(320, 240, 21)          # enough keypoints for the 99.5 % bar to allow one ill-conditioned walk
+    img = fixtures.to_float(u8)
+    ora = oracle.detect(img, numberOfOctaves=3, scalesPerOctave=spo, minBlurLevel=1.6, separable=True)
+    assert ora.outcomes["singular"] == 0
+    prm = L.default_params(numberOfOctaves=3, scalesPerOctave=spo, minBlurLevel=1.6)
+    engine.build_scale_space(u8, prm)
+    assert engine.pyramid_info() == (3, spo + 3)
+    check_levels(engine, ora, L)
+    cands, _ = engine.find_candidates()
+    thr = 0.8 * 0.015 * (2 ** (1 / spo) - 1) / (2 ** (1 / 3) - 1)
+    check_candidates(cands, ora, pix_thr=thr)
+    kps, stats = engine.detect(u8, prm)
+    check_keypoints(kps, ora)
+    assert stats["candidates"] == len(cands) and len(ora.candidates) > 10
+
+
+def test_f32_and_pitched_inputs(engine):
+    """SIFT_F32 pixels, and rows further apart than their length (pitch_bytes): same result as the dense u8 frame."""
+    import ctypes as C
+    w, h = 150, 90
+    u8 = fixtures.synthetic_u8(w, h, 17)
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    want, _ = engine.detect(u8, prm)
+    f32, _ = engine.detect((u8.astype(np.float64) / 255.0).astype(np.float32), prm)
+    # float32(v / 255) is not v / 255: positions agree to the float32 input rounding, the cells are the same
+    assert len(f32) == len(want) and np.array_equal(f32["localX"], want["localX"]) and np.array_equal(f32["localY"], want["localY"])
+    assert np.abs(f32["absoluteX"] - want["absoluteX"]).max() < 1e-2
+    padded = np.zeros((h, w + 37), np.uint8)
+    padded[:, :w] = u8
+    out = np.zeros(len(want) + 8, dtype=L.KEYPOINT_DTYPE)
+    n = C.c_int()
+    st = L.Stats()
+    rc = engine._lib.sift_detect(engine._h, padded.ctypes.data, L.SIFT_U8, w, h, padded.strides[0], C.byref(prm),
+                                 out.ctypes.data, len(out), C.byref(n), C.byref(st))
+    assert rc == L.SIFT_OK and n.value == len(want)
+    assert out[:n.value].tobytes() == want.tobytes()
+
+
 def test_f64_input_matches_u8(engine):
     ora, cands, kps, _ = _run_case(engine, 96, 80, 3, 43, True, dtype="f64")
     check_candidates(cands, ora)
