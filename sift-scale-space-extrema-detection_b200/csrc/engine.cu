@@ -1423,14 +1423,38 @@ SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *
   const int64_t l0 = ctx->launches;
   int rc;
   Counters c;
-  sift_keypoint *kps;
-  if ((rc = scan_refine_download(ctx, &c, &kps, 0))) return rc;
+  // a strip of a gigapixel mosaic yields 10^5..10^6 records: they are ordered on the device (order.cu) and
+  // downloaded once, in place, instead of being radix-sorted by the host
+  for (int attempt = 0;; attempt++) {
+    if (attempt == 3) return fail(ctx, SIFT_ERR_CAPACITY, "candidate buffer kept overflowing");
+    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
+    if ((rc = run_scan(ctx, 0))) return rc;
+    if ((rc = run_refine(ctx, -1, dev_keypoints(ctx), ctx->L->kp_cap))) return rc;
+    CK(cudaMemcpyAsync(&c, dev_counters(ctx), sizeof c, cudaMemcpyDeviceToHost, ctx->L->stream));
+    CK(cudaStreamSynchronize(ctx->L->stream));
+    if (c.n_cand <= ctx->L->cand_cap && c.n_kp <= ctx->L->kp_cap) break;
+    const int want = std::max(c.n_cand, c.n_kp) + std::max(c.n_cand, c.n_kp) / 8 + 1024;
+    if ((rc = grow(ctx, ctx->L->cand, (size_t)want * sizeof(sift_candidate)))) return rc;
+    ctx->L->cand_cap = want;
+    if ((rc = grow(ctx, ctx->L->outbuf, sizeof(Counters) + (size_t)want * sizeof(sift_keypoint)))) return rc;
+    ctx->L->kp_cap = want;
+  }
   ctx->last = c;
   if ((rc = fetch_escaped(ctx, c))) return rc;
   fill_stats(stats, c, 0, 0.f, (int)(ctx->launches - l0));
   *n_out = c.n_kp;
-  sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
   if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
+  if (c.n_kp > 0) {
+    const size_t sort_bytes = (order_scratch_bytes(c.n_kp) + 255) & ~(size_t)255;
+    if ((rc = grow(ctx, ctx->L->order, sort_bytes + (size_t)c.n_kp * sizeof(sift_keypoint)))) return rc;
+    sift_keypoint *d_sorted = (sift_keypoint *)((char *)ctx->L->order.p + sort_bytes);
+    ctx->launches += launch_order_keypoints(ctx->L->stream, dev_keypoints(ctx), dev_counters(ctx), c.n_kp, ctx->L->order.p,
+                                            sort_bytes, d_sorted, c.n_kp, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_sorted, (size_t)c.n_kp * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->L->stream));
+    CK(cudaStreamSynchronize(ctx->L->stream));
+    if (stats) stats->kernelLaunches = (int)(ctx->launches - l0);
+  }
   return SIFT_OK;
 }
 

@@ -184,9 +184,15 @@ def resolve_escaped_distributed(engine, layouts: list, rank: int, kps: np.ndarra
     continues the ones whose row it owns.  Returns this rank's keypoints with the newly decided ones appended."""
     import torch.distributed as tdist
     dist = dist or tdist
+    import torch
     world = dist.get_world_size()
     mine_out = engine.strip_escaped()
+    dev = torch.device("cuda", engine.device) if dist.get_backend() == "nccl" else torch.device("cpu")
     for _ in range(max_rounds):
+        pending = torch.tensor([len(mine_out)], dtype=torch.int64, device=dev)
+        dist.all_reduce(pending)                              # the common case: nobody has a walk to hand over
+        if int(pending.item()) == 0:
+            return kps
         gathered = [None] * world
         dist.all_gather_object(gathered, mine_out.tobytes())
         walks = np.concatenate([np.frombuffer(b, dtype=L.WALK_DTYPE) for b in gathered])
