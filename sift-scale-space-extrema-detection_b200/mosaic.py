@@ -180,30 +180,36 @@ def resolve_escaped_local(engines: list, layouts: list, parts: list, stats: list
 
 def resolve_escaped_distributed(engine, layouts: list, rank: int, kps: np.ndarray, stats: dict, dist=None,
                                 max_rounds: int = 8):
-    """One process per strip: every round all ranks share their escaped walks (a few 40-byte records), each
-    continues the ones whose row it owns.  Returns this rank's keypoints with the newly decided ones appended."""
+    """One process per strip: every round all ranks share their escaped walks (a few 40-byte records, padded
+    tensors over the process group), each continues the ones whose row it owns.  Returns this rank's keypoints
+    with the newly decided ones appended."""
+    import torch
     import torch.distributed as tdist
     dist = dist or tdist
-    import torch
     world = dist.get_world_size()
-    mine_out = engine.strip_escaped()
     dev = torch.device("cuda", engine.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    rec = L.WALK_DTYPE.itemsize
+    mine_out = engine.strip_escaped()
+    extra = []
     for _ in range(max_rounds):
-        pending = torch.tensor([len(mine_out)], dtype=torch.int64, device=dev)
-        dist.all_reduce(pending)                              # the common case: nobody has a walk to hand over
-        if int(pending.item()) == 0:
-            return kps
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine_out.tobytes())
-        walks = np.concatenate([np.frombuffer(b, dtype=L.WALK_DTYPE) for b in gathered])
-        if len(walks) == 0:
-            return kps
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([len(mine_out)], dtype=torch.int64, device=dev))
+        counts = [int(c.item()) for c in counts]
+        if sum(counts) == 0:                                  # the common case: nobody has a walk to hand over
+            return np.concatenate([kps] + extra) if extra else kps
+        width = max(counts) * rec
+        send = torch.zeros(width, dtype=torch.uint8)
+        send[:len(mine_out) * rec] = torch.from_numpy(np.frombuffer(mine_out.tobytes(), dtype=np.uint8).copy())
+        bufs = [torch.zeros(width, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(bufs, send.to(dev))
+        walks = np.concatenate([np.frombuffer(b.cpu().numpy().tobytes()[:n * rec], dtype=L.WALK_DTYPE)
+                                for b, n in zip(bufs, counts)])
         owners = np.array([owner_of(layouts, int(w["octave"]), int(w["y"])) for w in walks])
         mine = walks[owners == rank]
         mine_out = np.zeros(0, dtype=L.WALK_DTYPE)
         if len(mine):
             k, st = engine.strip_resume(mine)
-            kps = np.concatenate([kps, k])
+            extra.append(k)
             _add_outcomes(stats, st)
             mine_out = engine.strip_escaped()
     raise RuntimeError("refinement walks still unresolved after %d rounds" % max_rounds)

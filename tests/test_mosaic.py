@@ -38,6 +38,13 @@ def test_strip_layout_arithmetic():
     assert sorted(tr) == sorted([(1, 0, 160, a.halo[1]), (0, 1, 160 - b.halo[1], b.halo[1])])
 
 
+def test_mosaic_module_surface():
+    for name in ("strip_layout", "plan_strips", "halo_transfers", "exchange_seed_halos", "seed_tensor", "source_rows",
+                 "detect_mosaic_local", "detect_mosaic_distributed", "owner_of", "resolve_escaped_local",
+                 "resolve_escaped_distributed", "merge_keypoints", "gather_keypoints"):
+        assert callable(getattr(mosaic, name)), name
+
+
 def test_strip_layout_rejects_bad_cuts():
     prm = _params(4)
     with pytest.raises(sift_b200.SiftError):                     # boundary not a multiple of 2^(octaves-1)

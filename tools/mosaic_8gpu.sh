@@ -4,5 +4,5 @@
 N=${1:-8}
 run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 tools/mosaic_run.py "${@:2}" 2> gpurun_out/mosaic_err_$1.log | grep '^{' ; tail -3 gpurun_out/mosaic_err_$1.log | cut -c1-300; }
 nvidia-smi --query-gpu=index,name,memory.total --format=csv,noheader | head -8
-run 29531 --size 16384 --octaves 4 --verify --reps 2 | tee gpurun_out/mosaic_16384_${N}gpu.json
-run 29532 --size 32768 --octaves 4 --reps 2 | tee gpurun_out/mosaic_32768_${N}gpu.json
+run 29531 --size 16384 --octaves 4 --verify --reps 3 --pinned | tee gpurun_out/mosaic_16384_${N}gpu.json
+run 29532 --size 32768 --octaves 4 --reps 3 --pinned --phases | tee gpurun_out/mosaic_32768_${N}gpu.json
