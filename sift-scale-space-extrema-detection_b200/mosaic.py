@@ -172,7 +172,8 @@ def resolve_escaped_local(engines: list, layouts: list, parts: list, stats: list
             if len(mine) == 0:
                 continue
             k, st = eng.strip_resume(mine)
-            parts[r] = np.concatenate([parts[r], k])
+            if len(k):
+                parts[r] = np.concatenate([parts[r], k])
             _add_outcomes(stats[r], st)
             pending.append(eng.strip_escaped())
     raise RuntimeError("refinement walks still unresolved after %d rounds" % max_rounds)
@@ -209,7 +210,8 @@ def resolve_escaped_distributed(engine, layouts: list, rank: int, kps: np.ndarra
         mine_out = np.zeros(0, dtype=L.WALK_DTYPE)
         if len(mine):
             k, st = engine.strip_resume(mine)
-            extra.append(k)
+            if len(k):                                        # (appending copies the strip's whole record array)
+                extra.append(k)
             _add_outcomes(stats, st)
             mine_out = engine.strip_escaped()
     raise RuntimeError("refinement walks still unresolved after %d rounds" % max_rounds)
