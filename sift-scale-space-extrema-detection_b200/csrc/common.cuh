@@ -96,9 +96,6 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
                           const double *d_u8lut);
 
 // scan.cu
-void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int spo, double pix_threshold,
-                        int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,
-                        Counters *ctr);
 void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
                      double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,
                      int low_cap, Counters *ctr);

@@ -52,53 +52,6 @@ __device__ __forceinline__ int warp_append(bool hit, int *counter)
   return hit ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
-__global__ void __launch_bounds__(SC_BX *SC_BY)
-scan_octave_kernel(OctaveDev oct, int octave, int spo, double pix_threshold, int count_low,
-                   sift_candidate *__restrict__ cand, int cand_cap, sift_candidate *__restrict__ low, int low_cap,
-                   Counters *ctr)
-{
-  const int x = blockIdx.x * SC_BX + threadIdx.x;
-  const int y = blockIdx.y * SC_BY + threadIdx.y;
-  const int yg = y + oct.y_top;                                                       // row of the whole image
-  const bool inside = (x >= 1 && x < oct.w - 1 && yg >= 1 && yg < oct.gh - 1 && y >= oct.own0 && y < oct.own1);   // sift.js:221-222
-  const size_t pitch = oct.pitch;
-  for (int s = 1; s <= spo; s++) {                                                    // background.js:377
-    bool hit = false, hit_low = false;
-    float c = 0.f;
-    if (inside) {
-      c = oct.dog[s][(size_t)y * pitch + x];
-      const bool strong = (double)fabsf(c) >= pix_threshold;                          // sift.js:294
-      if (strong || count_low) {
-        if (is_extremum<float>(oct.dog[s - 1], oct.dog[s], oct.dog[s + 1], pitch, x, y, c)) {
-          hit = strong; hit_low = !strong;
-        }
-      }
-    }
-    int slot = warp_append(hit, &ctr->n_cand);
-    if (slot >= 0 && slot < cand_cap) {
-      sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = yg; r.value = c; r.reserved0 = 0;
-      cand[slot] = r;
-    }
-    if (count_low) {
-      slot = warp_append(hit_low, &ctr->n_low);
-      if (low && slot >= 0 && slot < low_cap) {
-        sift_candidate r; r.octave = octave; r.scaleLevel = s; r.x = x; r.y = yg; r.value = c; r.reserved0 = 0;
-        low[slot] = r;
-      }
-    }
-  }
-}
-
-void launch_scan_octave(cudaStream_t st, const OctaveDev &oct, int octave, int spo, double pix_threshold,
-                          int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low, int low_cap,
-                          Counters *ctr)
-{
-  if (oct.w < 3 || oct.h < 3) return;
-  dim3 block(SC_BX, SC_BY);
-  dim3 grid((oct.w + SC_BX - 1) / SC_BX, (oct.h + SC_BY - 1) / SC_BY);
-  scan_octave_kernel<<<grid, block, 0, st>>>(oct, octave, spo, pix_threshold, count_low, cand, cand_cap, low,
-                                             low_cap, ctr);
-}
 
 // ---- whole pyramid in one launch: 4 pixels per thread (one 16-byte load per scale), the 26
 // neighbours are only fetched for pixels that pass the pre-filter, in-plane ring first.
@@ -234,15 +187,14 @@ void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *
 }
 
 // ---- whole pyramid in one launch, TMA-tiled -------------------------------------------------------
-// One CTA = one 128 x 32 pixel tile of one octave.  An elected thread issues one TMA 2D tile load
-// (cp.async.bulk.tensor) per DoG level -- box 136 x 34 floats: the tile plus the one-pixel ring the
+// One CTA = one 128 x 16 pixel tile of one octave.  An elected thread issues one TMA 2D tile load
+// (cp.async.bulk.tensor) per DoG level -- box 136 x 18 floats: the tile plus the one-pixel ring the
 // 26-neighbour test needs, widened to keep 16-byte alignment -- and the CTA waits on an mbarrier; out-of-
 // range rows / columns are zero-filled by the TMA unit and never tested (sift.js:221-222 scans the
 // interior only).  Every DoG value is read from HBM once per tile (+ halo) and all tests run from shared
 // memory, branch-free: a thread owns 2 neighbouring pixels and marches down 8 rows keeping, per level, the
-// horizontal 3-max / 3-min of the two previous rows in registers; a pixel is a strict maximum iff it is
-// greater than max(3x3 block above, 3x3 block below, its 8 in-plane neighbours) (sift.js:261,266: ties
-// are never extrema).  Hits are compacted with ballot / popc and one atomic per warp.
+// horizontal 3-max / 3-min of the two previous rows in registers (see scan_tma_kernel for the test itself).
+// Hits are compacted with ballot / popc and one atomic per warp.
 #include <cuda.h>
 
 #ifndef ST_PX
