@@ -7,6 +7,7 @@ python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpuru
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; tail -c 400 gpurun_out/bench.log; echo
 fi
+[ "${1:-all}" = "tests" ] && exit 0          # tests + smoke + bench only (kernels unchanged since the last ncu pass)
 python tools/prof_detect.py > gpurun_out/plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -s 10 -c 10 --csv --log-file gpurun_out/launches.csv python tools/prof_detect.py > gpurun_out/ncu.log 2>&1
