@@ -37,7 +37,7 @@ W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
 FRAMES = 64                    # frames per GPU per step (distinct seeds)
 # dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0_1.txt), ncu --set full
-NCU_TRAFFIC_OCT0_BYTES = 345.5e6
+NCU_TRAFFIC_OCT0_BYTES = 344.4e6
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
 CPU_TILE = int(os.environ.get("SIFT_BENCH_CPU_TILE", "256"))   # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
