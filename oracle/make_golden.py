@@ -39,6 +39,8 @@ CASES = {   # tiny inputs (the interpreter runs ~60k dense-kernel taps per secon
     "g28x22_o2_b08": (28, 22, 30, 30, 2, 3, 0.8, 0.5, "matrix"),      # worker.js:35 default sigma0 = 0.8
     "g17x13_o3_b08_rgba": (17, 13, 23, 30, 3, 3, 0.8, 0.5, "rgba"),   # odd sizes (ceil halving) + ImageData ingest
     "g16x16_o2_s2_b10": (16, 16, 31, 30, 2, 2, 1.0, 0.5, "matrix"),   # scalesPerOctave = 2 (threshold formula)
+    "g16x14_o2_s4_b10": (16, 14, 73, 30, 2, 4, 1.0, 0.5, "matrix"),   # scalesPerOctave = 4: 7 levels, 6 DoG, scales 1..4
+    "g20x16_o2_s1_b12": (20, 16, 37, 30, 2, 1, 1.2, 0.5, "matrix"),   # scalesPerOctave = 1: one tested scale per octave
 }
 
 
