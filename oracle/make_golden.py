@@ -42,7 +42,9 @@ CASES = {   # tiny inputs (the interpreter runs ~60k dense-kernel taps per secon
     "g16x14_o2_s4_b10": (16, 14, 73, 30, 2, 4, 1.0, 0.5, "matrix"),   # scalesPerOctave = 4: 7 levels, 6 DoG, scales 1..4
     "g20x16_o2_s1_b12": (20, 16, 37, 30, 2, 1, 1.2, 0.5, "matrix"),   # scalesPerOctave = 1: one tested scale per octave
     "g30x24_o3_b16": (30, 24, 37, 30, 3, 3, 1.6, 0.5, "matrix"),      # BASELINE parameters over 3 octaves: radii up to 58
-}                                                                     # on a 15 x 12 octave (every tap clamps, sift.js:116-119)
+    # ^ on a 15 x 12 octave (every tap clamps, sift.js:116-119)
+    "g40x32_o4_b16": (40, 32, 21, 40, 4, 3, 1.6, 0.5, "matrix"),      # BASELINE configs' full parameter set: 4 octaves, radii
+}                                                                     # up to 116 (a 233 x 233 kernel on a 10 x 8 octave)
 
 
 class _Canvas:
