@@ -240,6 +240,24 @@ def preview_vectors(ref_root):
     return out
 
 
+def chunking_vectors(ref_root):
+    """The reference blurs in chunk_size x chunk_size tiles for its progressive repaint (background.js:147-203) but
+    reads the whole base image for every tile's halo (sift.js:109-125): run it with two chunk sizes on the same
+    input and keep both results, so a test can hold the claim that chunk_size does not change any output."""
+    sys.path.insert(0, ROOT)
+    from sift_b200 import fixtures
+    u8 = fixtures.synthetic_u8(14, 12, 15, blobs=30, sigma_lo=0.6, sigma_hi=2.2)
+    out = {"input_u8": u8}
+    for chunk in (32, 5):
+        res = run_reference(ref_root, u8, 2, 3, 1.0, 0.5, "matrix", chunk=chunk)
+        out[f"c{chunk}_keypoints"] = res["keypoints"]
+        out[f"c{chunk}_candidates"] = res["candidates"]
+        out[f"c{chunk}_levels"] = np.stack([res[f"gauss_0_{s}"] for s in range(6)])
+        out[f"c{chunk}_dog1"] = np.stack([res[f"dog_1_{s}"] for s in range(5)])
+        out[f"c{chunk}_chunk_messages"] = int(res["messages_scale_space"].get("received-gaussian-blurred-chunk", 0))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -256,6 +274,9 @@ def main():
         sv = step_function_vectors(args.ref)
         np.savez_compressed(os.path.join(args.out, "ref_steps.npz"), **sv)
         print(f"ref_steps.npz {time.time() - t0:.1f}s", flush=True)
+    if args.only in (None, "chunking"):
+        np.savez_compressed(os.path.join(args.out, "ref_chunking.npz"), **chunking_vectors(args.ref))
+        print("ref_chunking.npz", flush=True)
     if args.only in (None, "preview"):
         np.savez_compressed(os.path.join(args.out, "ref_preview.npz"), **preview_vectors(args.ref))
         print("ref_preview.npz", flush=True)

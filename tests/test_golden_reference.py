@@ -56,6 +56,19 @@ def test_oracle_reproduces_the_reference_bit_for_bit(name):
     assert np.allclose(kp[:, 4], ref_kp[:, 4], rtol=4e-16, atol=0)
 
 
+def test_reference_results_do_not_depend_on_chunk_size():
+    """background.js:147-203 blurs in chunk_size tiles only to repaint progressively; every tile reads the whole base
+    image (sift.js:109-125).  The unmodified reference, run with chunk sizes 32 and 5 (11 vs 225 chunk messages),
+    produced identical levels, DoG, candidates and keypoints -- which is why the C ABI has no chunk parameter."""
+    g = np.load(os.path.join(GOLDEN, "ref_chunking.npz"))
+    assert int(g["c5_chunk_messages"]) > 10 * int(g["c32_chunk_messages"]) > 0
+    for key in ("levels", "dog1", "candidates", "keypoints"):
+        assert np.array_equal(g[f"c32_{key}"], g[f"c5_{key}"]), key
+    r = oracle.detect(g["input_u8"].astype(np.float64) / 255.0, numberOfOctaves=2, scalesPerOctave=3, minBlurLevel=1.0,
+                      assumedBlur=0.5, separable=False)
+    assert np.array_equal(np.stack(r.gauss[0]), g["c5_levels"]) and np.array_equal(np.stack(r.dog[1]), g["c5_dog1"])
+
+
 def test_rgba_ingest_matches_image_utils():
     """image-utils.js:107-114: grey = (0.299R + 0.587G + 0.114B) / 255, which is NOT v/255 for grey bytes."""
     g = _load("g17x13_o3_b08_rgba")
