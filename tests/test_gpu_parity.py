@@ -201,6 +201,33 @@ def test_full_hd_properties(engine):
     assert len(ka & kb) >= 0.995 * max(len(ka), len(kb))
 
 
+def test_full_hd_pyramid_is_affine_in_the_image(engine):
+    """BASELINE configs[1] at full size, every level of every octave, no oracle needed: the kernels are normalised
+    (sift.js:48-63) and everything up to the DoG is linear, so for y = a*x + b every Gaussian level obeys
+    G(y) = a*G(x) + b and every DoG level D(y) = a*D(x) -- to the 1e-5 of the level contract."""
+    w, h = 1920, 1080
+    x = fixtures.to_float(fixtures.synthetic_u8(w, h, 1234))
+    a_, b_ = 0.5, 0.25
+    y = a_ * x + b_
+    prm = L.default_params(numberOfOctaves=4, minBlurLevel=1.6)
+    worst_g = worst_d = 0.0
+    for o in range(4):                                   # one octave at a time keeps the host copies small
+        engine.build_scale_space(x, prm)
+        gx = [engine.get_level(L.SIFT_LEVEL_GAUSSIAN, o, s).astype(np.float64) for s in range(6)]
+        dx = [engine.get_level(L.SIFT_LEVEL_DOG, o, s).astype(np.float64) for s in range(5)]
+        engine.build_scale_space(y, prm)
+        for s in range(6):
+            gy = engine.get_level(L.SIFT_LEVEL_GAUSSIAN, o, s).astype(np.float64)
+            want = a_ * gx[s] + b_
+            worst_g = max(worst_g, float((np.abs(gy - want) / np.maximum(np.abs(want), 1e-3)).max()))
+        for s in range(5):
+            dy = engine.get_level(L.SIFT_LEVEL_DOG, o, s).astype(np.float64)
+            want = a_ * dx[s]
+            worst_d = max(worst_d, float((np.abs(dy - want) / np.maximum(np.abs(want), 0.012)).max()))
+    assert worst_g <= 1e-5 and worst_d <= 1e-5, (worst_g, worst_d)
+    assert worst_g > 0.0                                 # (the two runs are not trivially the same numbers)
+
+
 def test_device_resident_frames_in_flight_equal_single(engine):
     """sift_detect_device deals frames to lanes (frames in flight); results must equal the host call, per frame."""
     import torch
