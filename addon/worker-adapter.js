@@ -20,34 +20,39 @@ export const WorkerMessageTypes = {
   RECEIVED_REFINED_KEYPOINTS: 'received-refined-keypoints',
 };
 
-export class SiftWorker {
-  onmessage = null;
-  // previews: also post the per-level images the reference's canvas consumes (main.js:150-165), before the
-  // stage reply as the reference does.  The per-chunk repaint messages (RECEIVED_*_CHUNK) and the candidate
-  // markers are progressive-display only and are not emitted.
-  constructor({ previews = false } = {}) { this.previews = previews; }
-  postMessage(message) {
-    const T = WorkerMessageTypes;
-    let reply;
-    const extra = [];
-    switch (message.type) {                                            // background.js:18-49
-      case T.COMPUTE_GAUSSIAN_SCALE_SPACE:
-        reply = { type: T.RECEIVED_GAUSSIAN_SCALE_SPACE, scaleSpace: computeGaussianScaleSpace(message) };
-        if (this.previews) for (const p of levelPreviews(LEVEL.GAUSSIAN)) extra.push({ type: T.RECEIVED_GAUSSIAN_BLURRED_IMAGE, ...p });
-        break;
-      case T.COMPUTE_DIFFERENCE_OF_GAUSSIANS:
-        reply = { type: T.RECEIVED_DIFFERENCE_OF_GAUSSIANS, differenceOfGaussians: computeDifferenceOfGaussians(message.scaleSpace) };
-        if (this.previews) for (const p of levelPreviews(LEVEL.DOG)) extra.push({ type: T.RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE, ...p });
-        break;
-      case T.FIND_CANDIDATE_KEYPOINTS:
-        reply = { type: T.RECEIVED_CANDIDATE_KEYPOINTS, candidateKeypoints: findCandidateKeypoints(message) };
-        break;
-      case T.REFINE_CANDIDATE_KEYPOINTS:
-        reply = { type: T.RECEIVED_REFINED_KEYPOINTS, refinedKeypoints: refineCandidateKeypoints(message) };
-        break;
-      default:
-        return;
-    }
-    queueMicrotask(() => { if (this.onmessage) for (const m of [...extra, reply]) this.onmessage({ data: m }); });
-  }
+/** `new SiftWorker()` / `SiftWorker()`: an object with the two members the reference uses of its Worker --
+ *  `postMessage(message)` and an assignable `onmessage` (main.js:46-47, src/worker.js:29-98).
+ *  previews: also post the per-level images the reference's canvas consumes (main.js:150-165), before the stage
+ *  reply as the reference does.  The per-chunk repaint messages (RECEIVED_*_CHUNK) and the candidate markers are
+ *  progressive-display only and are not emitted. */
+export function SiftWorker({ previews = false } = {}) {
+  const T = WorkerMessageTypes;
+  const worker = {
+    onmessage: null,
+    previews,
+    postMessage: (message) => {
+      let reply;
+      const extra = [];
+      switch (message.type) {                                          // background.js:18-49
+        case T.COMPUTE_GAUSSIAN_SCALE_SPACE:
+          reply = { type: T.RECEIVED_GAUSSIAN_SCALE_SPACE, scaleSpace: computeGaussianScaleSpace(message) };
+          if (worker.previews) for (const p of levelPreviews(LEVEL.GAUSSIAN)) extra.push({ type: T.RECEIVED_GAUSSIAN_BLURRED_IMAGE, ...p });
+          break;
+        case T.COMPUTE_DIFFERENCE_OF_GAUSSIANS:
+          reply = { type: T.RECEIVED_DIFFERENCE_OF_GAUSSIANS, differenceOfGaussians: computeDifferenceOfGaussians(message.scaleSpace) };
+          if (worker.previews) for (const p of levelPreviews(LEVEL.DOG)) extra.push({ type: T.RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE, ...p });
+          break;
+        case T.FIND_CANDIDATE_KEYPOINTS:
+          reply = { type: T.RECEIVED_CANDIDATE_KEYPOINTS, candidateKeypoints: findCandidateKeypoints(message) };
+          break;
+        case T.REFINE_CANDIDATE_KEYPOINTS:
+          reply = { type: T.RECEIVED_REFINED_KEYPOINTS, refinedKeypoints: refineCandidateKeypoints(message) };
+          break;
+        default:
+          return;
+      }
+      queueMicrotask(() => { if (worker.onmessage) for (const m of [...extra, reply]) worker.onmessage({ data: m }); });
+    },
+  };
+  return worker;
 }

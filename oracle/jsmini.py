@@ -734,6 +734,9 @@ class Parser:
                 name = self.eat("id")[1] if self.at("id") else None
                 ps, body = self.func_rest()
                 return ("func", name, ps, body)
+            if t[1] == "import" and self.atp(".", 1) and self.peek(2)[1] == "meta":
+                self.i += 3                                   # import.meta (ES modules): an object with `url`
+                return ("importmeta",)
         if k == "p":
             if t[1] == "(":
                 self.i += 1
@@ -1174,6 +1177,9 @@ class Compiler:
             return ev
         if k == "call":
             return self.call(node)
+        if k == "importmeta":
+            interp = self.interp
+            return lambda scope: JSObject(url="file://" + interp._dir_stack[-1] + "/")
         if k == "new":
             callee = self.expr(node[1])
             args = self.args(node[2])
@@ -1289,6 +1295,15 @@ class Compiler:
                 v = a(scope)
                 return b(scope) if v is None or v is UNDEF else v
             return ev
+        if op == "instanceof":
+            def ev(scope):
+                x, c = a(scope), b(scope)
+                if isinstance(c, type):                         # host constructors are Python classes
+                    return isinstance(x, c)
+                if isinstance(c, _ArrayCtor):
+                    return type(x) is list
+                return False
+            return ev
         if op == "===":
             return lambda scope: strict_eq(a(scope), b(scope))
         if op == "!==":
@@ -1372,6 +1387,8 @@ def _contains_func(node) -> bool:
 def get_index(o, i):
     if isinstance(o, Uint8ClampedArray):
         return o.get(i)
+    if hasattr(o, "js_get"):                                 # host objects with indexed elements (typed arrays)
+        return o.js_get(i)
     if isinstance(o, str):
         i = int(i)
         return o[i] if 0 <= i < len(o) else UNDEF
@@ -1394,6 +1411,9 @@ def set_index(o, i, v):
         raise JSError("unsupported array property write")
     if isinstance(o, Uint8ClampedArray):
         o.set(i, v)
+        return
+    if hasattr(o, "js_set"):
+        o.js_set(i, v)
         return
     if isinstance(o, dict):
         o[i if isinstance(i, str) else to_str(i)] = v
@@ -1488,6 +1508,36 @@ def call_method(o, name, args):
 # ------------------------------------------------------------------ host globals
 
 
+class _ArrayCtor:
+    """The global Array: `new Array(n)`, Array.isArray, Array.from(iterable | {length}, mapFn)."""
+
+    def __call__(self, *a):
+        if len(a) == 1 and isinstance(a[0], (int, float)):
+            return [UNDEF] * int(a[0])
+        return list(a)
+
+    @staticmethod
+    def isArray(v=UNDEF):
+        return type(v) is list
+
+    def __getattr__(self, name):
+        if name == "from":
+            return self._from
+        raise AttributeError(name)
+
+    @staticmethod
+    def _from(src, fn=None):
+        if type(src) is list:
+            items = list(src)
+        elif isinstance(src, dict):
+            items = [UNDEF] * int(to_num(src.get("length", 0)))
+        elif hasattr(src, "js_get"):
+            items = [src.js_get(i) for i in range(int(src.length))]
+        else:
+            items = list(src)
+        return [fn(v, i) for i, v in enumerate(items)] if fn is not None and fn is not UNDEF else items
+
+
 class _Number:
     EPSILON = 2.220446049250313e-16
     MAX_SAFE_INTEGER = 9007199254740991
@@ -1541,16 +1591,19 @@ class Interpreter:
         g = self.global_scope.vars
         g.update({"Math": _math(), "Number": _Number(), "Infinity": math.inf, "NaN": math.nan,
                   "Uint8ClampedArray": Uint8ClampedArray,
-                  "Array": JSObject(isArray=lambda v: isinstance(v, list)),
+                  "Array": _ArrayCtor(),
                   "parseFloat": to_num, "isNaN": lambda v: to_num(v) != to_num(v)})
         if globals_:
             g.update(globals_)
         self.modules = {}
+        self.virtual_modules = {}        # specifier -> exports, for host-provided modules ('node:module', ...)
         self.current_exports = None
         self._dir_stack = [self.root]
         self.compiler = Compiler(self)
 
     def load_module(self, path: str) -> dict:
+        if path in self.virtual_modules:
+            return self.virtual_modules[path]
         full = os.path.normpath(os.path.join(self._dir_stack[-1], path))
         if full in self.modules:
             return self.modules[full]

@@ -1,0 +1,236 @@
+"""addon/*.js executed.  Node.js is absent from this image, so the ES modules a Node host would import -- native.js,
+sift.js, background.js, worker-adapter.js -- run under oracle/jsmini.py (the interpreter that runs the reference) with
+`require('./sift_b200.node')` answered by a Python stand-in for the N-API addon:
+  * stage calls answer from the reference's own outputs (tests/golden/ref_g22x18_o2_b16.npz), as fp32 planes and packed
+    24 / 80-byte records exactly as sift_addon.c hands them over, so the replies the glue assembles can be compared
+    with the replies the reference produced;
+  * step calls are computed by the float64 oracle, so SIFT_blurMatrix2DChunk & co. can be compared with the reference's
+    step vectors (tests/golden/ref_steps.npz).
+What this covers is the glue: record decoding / encoding, typed-array plumbing, in-place semantics, reply schemas and
+the worker message protocol.  The arithmetic behind the addon is covered by the GPU tests."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import jsmini
+from sift_b200 import _lib as L
+
+import js_host as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ADDON = os.path.join(ROOT, "addon")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+J = jsmini.JSObject
+
+
+class FakeAddon:
+    """Same entry points and value shapes as addon/sift_addon.c."""
+
+    def __init__(self, g):
+        self.g = g
+        self.n_oct, self.nlev = int(g["n_octaves"]), int(g["n_levels"])
+        self.calls = []
+
+    # -- context / fused
+    def create(self, device=0):
+        self.calls.append("create")
+        return J(handle=1)
+
+    def _records(self, rows):
+        out = np.zeros(len(rows), dtype=L.KEYPOINT_DTYPE)
+        for i, r in enumerate(rows):
+            out[i]["octave"], out[i]["scaleLevel"], out[i]["localX"], out[i]["localY"] = (int(v) for v in r[:4])
+            out[i]["absoluteSigma"], out[i]["absoluteX"], out[i]["absoluteY"], out[i]["interpolatedValue"] = r[4:8]
+            out[i]["offset"] = (0.25, -0.5, 0.125)
+            out[i]["dogValue"] = 0.0625
+        return H.ArrayBuffer(np.frombuffer(out.tobytes(), dtype=np.uint8).copy())
+
+    def detect(self, ctx, data, w, h, dtype, prm):
+        self.calls.append(("detect", w, h, dtype, prm["numberOfOctaves"], prm["minBlurLevel"]))
+        k = self.g["keypoints"]
+        return J(records=self._records(k), count=len(k), stats=J(keypoints=len(k), candidates=len(self.g["candidates"])))
+
+    # -- stages
+    def buildScaleSpace(self, ctx, data, w, h, dtype, prm):
+        assert isinstance(data, H.Float64Array) and dtype == 2                       # a Matrix2D arrives as F64
+        assert np.array_equal(data.a.reshape(h, w), self.g["input_matrix"])
+        assert (prm["numberOfOctaves"], prm["scalesPerOctave"], prm["minBlurLevel"], prm["assumedBlur"]) == tuple(self.g["params"])
+        assert prm["contrastThreshold"] == 0.015 and prm["edgeRatio"] == 10 and prm["maxIterations"] == 5
+        self.calls.append("buildScaleSpace")
+
+    def pyramidInfo(self, ctx):
+        return J(octaves=self.n_oct, levels=self.nlev)
+
+    def _level(self, kind, o, s):
+        return self.g[("gauss_%d_%d" if kind == 0 else "dog_%d_%d") % (o, s)]
+
+    def getLevel(self, ctx, kind, o, s):
+        m = self._level(kind, o, s)
+        blur = float(self.g[("gauss_blur_%d_%d" if kind == 0 else "dog_blur_%d_%d") % (o, s)])
+        return J(blurLevel=blur, width=m.shape[1], height=m.shape[0], data=H.Float32Array.of_numpy(m.astype(np.float32).ravel()))
+
+    def levelPreview(self, ctx, kind, o, s, mode, coefficient):
+        rgba, mm = oracle.preview(self._level(kind, o, s), int(mode), float(coefficient))
+        return J(width=rgba.shape[1], height=rgba.shape[0], min=mm[0], max=mm[1], data=H.Uint8ClampedArray.of_numpy(rgba.ravel()))
+
+    def findCandidates(self, ctx, prm, want_low):
+        c = self.g["candidates"]
+        rec = np.zeros(len(c), dtype=L.CANDIDATE_DTYPE)
+        rec["octave"], rec["scaleLevel"], rec["x"], rec["y"], rec["value"] = c[:, 0], c[:, 1], c[:, 2], c[:, 3], c[:, 4]
+        return J(count=len(c), records=H.ArrayBuffer(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()))
+
+    def refine(self, ctx, prm, buffer, count):
+        got = np.frombuffer(buffer.data.tobytes(), dtype=L.CANDIDATE_DTYPE)[:int(count)]    # what encodeCandidates packed
+        c = self.g["candidates"]
+        assert int(count) == len(c)
+        assert np.array_equal(np.stack([got["octave"], got["scaleLevel"], got["x"], got["y"]], axis=1), c[:, :4].astype(int))
+        assert np.array_equal(got["value"], c[:, 4].astype(np.float32))
+        self.calls.append("refine")
+        k = self.g["keypoints"]
+        return J(count=len(k), records=self._records(k))
+
+    # -- steps, computed by the oracle on the Float64Arrays the glue passes
+    def blurChunk(self, ctx, src, rows, cols, dst, sigma, x1, y1, x2, y2):
+        out = dst.a.reshape(rows, cols).copy()
+        oracle.blur_chunk(src.a.reshape(rows, cols), out, sigma, x1, y1, x2, y2)
+        dst.a[:] = out.ravel()
+
+    def subtractChunk(self, ctx, a, b, rows, cols, dst, x1, y1, x2, y2):
+        out = dst.a.reshape(rows, cols).copy()
+        oracle.subtract_chunk(a.a.reshape(rows, cols), b.a.reshape(rows, cols), out, x1, y1, x2, y2)
+        dst.a[:] = out.ravel()
+
+    def findExtremas(self, ctx, d0, d1, d2, rows, cols, spo, contrast, prefactor):
+        r = oracle.find_extremas([d.a.reshape(rows, cols) for d in (d0, d1, d2)], int(spo), contrast, prefactor)
+        cand, low = r["candidateKeypoints"], r["lowContrastKeypoints"]
+
+        def pack(lst):
+            return (H.Int32Array.of_numpy(np.array([(e["x"], e["y"]) for e in lst], dtype=np.int32).ravel()),
+                    H.Float64Array.of_numpy(np.array([e["value"] for e in lst], dtype=np.float64)))
+        cxy, cv = pack(cand)
+        lxy, lv = pack(low)
+        return J(nCand=len(cand), candXY=cxy, candValue=cv, nLow=len(low), lowXY=lxy, lowValue=lv)
+
+    def gradientHessian(self, ctx, dm, dc, dp, rows, cols, m, n):
+        trio = [d.a.reshape(rows, cols) for d in (dm, dc, dp)]
+        g, h = oracle.gradient(trio, 1, int(m), int(n)), oracle.hessian(trio, 1, int(m), int(n))
+        return H.Float64Array.of_numpy(np.concatenate([g, h.ravel()]))
+
+
+@pytest.fixture()
+def golden():
+    return np.load(os.path.join(GOLDEN, "ref_g22x18_o2_b16.npz"), allow_pickle=True)
+
+
+def test_worker_adapter_speaks_the_reference_protocol(golden):
+    fake = FakeAddon(golden)
+    interp, drain = H.make_interpreter(ADDON, fake)
+    mod = interp.load_module("worker-adapter.js")
+    T = mod["WorkerMessageTypes"]
+    n_oct, spo, min_blur, assumed = (float(v) for v in golden["params"])
+    inbox = []
+    worker = mod["SiftWorker"](J(previews=True))
+    worker["onmessage"] = lambda e: inbox.append(e["data"])
+
+    def post(**m):
+        worker["postMessage"](J(**m))
+        assert inbox == [] or inbox[-1]["type"] != m["type"]      # replies are asynchronous, like a Worker's
+        drain()
+        out = list(inbox)
+        inbox.clear()
+        return out
+
+    # main.js:111-117 -> background.js:71
+    msgs = post(type=T["COMPUTE_GAUSSIAN_SCALE_SPACE"], inputImage=golden["input_matrix"].tolist(), numberOfOctaves=n_oct,
+                scalesPerOctave=spo, minBlurLevel=min_blur, assumedBlur=assumed, chunkSize=32)
+    assert [m["type"] for m in msgs] == [T["RECEIVED_GAUSSIAN_BLURRED_IMAGE"]] * 12 + [T["RECEIVED_GAUSSIAN_SCALE_SPACE"]]
+    ss = msgs[-1]["scaleSpace"]
+    assert len(ss) == 2 and all(len(o) == 6 for o in ss)
+    for o in range(2):
+        for s in range(6):
+            ref = golden[f"gauss_{o}_{s}"]
+            assert ss[o][s]["blurLevel"] == float(golden[f"gauss_blur_{o}_{s}"])
+            assert np.array_equal(np.array(ss[o][s]["image"]), ref.astype(np.float32).astype(np.float64))   # Matrix2D rows
+    img = msgs[0]["imageData"]
+    want, _ = oracle.preview(golden["gauss_0_0"], oracle.PREVIEW_GRAY)
+    assert (img["width"], img["height"]) == (44, 36) and msgs[0]["octave"] == 0 and msgs[11]["octave"] == 1
+    assert isinstance(img["data"], H.Uint8ClampedArray) and np.array_equal(img["data"].a, want.ravel())
+
+    # main.js:239 -> background.js:258
+    msgs = post(type=T["COMPUTE_DIFFERENCE_OF_GAUSSIANS"], scaleSpace=ss)
+    assert [m["type"] for m in msgs] == [T["RECEIVED_DIFFERENCE_OF_GAUSSIAN_IMAGE"]] * 10 + [T["RECEIVED_DIFFERENCE_OF_GAUSSIANS"]]
+    dog = msgs[-1]["differenceOfGaussians"]
+    assert [len(o) for o in dog] == [5, 5]
+    assert dog[1][2]["blurLevel"] == float(golden["dog_blur_1_2"])
+    want, _ = oracle.preview(golden["dog_1_4"], oracle.PREVIEW_MINMAX)
+    assert np.array_equal(msgs[9]["imageData"]["data"].a, want.ravel())
+
+    # main.js:274-280 -> background.js:359: candidateKeypoints[o][i] = {scaleLevel, localExtremas:[{x, y, value}]}
+    msgs = post(type=T["FIND_CANDIDATE_KEYPOINTS"], differenceOfGaussians=dog, octaveBaseImages=[], scalesPerOctave=spo)
+    cands = msgs[-1]["candidateKeypoints"]
+    assert [m["type"] for m in msgs] == [T["RECEIVED_CANDIDATE_KEYPOINTS"]]
+    assert [[e["scaleLevel"] for e in o] for o in cands] == [[1, 2, 3], [1, 2, 3]]
+    flat = [(o, e["scaleLevel"], x["x"], x["y"], x["value"]) for o, oc in enumerate(cands) for e in oc for x in e["localExtremas"]]
+    ref = golden["candidates"]
+    assert len(flat) == len(ref) > 0
+    assert np.array_equal(np.array(flat)[:, :4], ref[:, :4]) and np.array_equal(np.array(flat)[:, 4], ref[:, 4].astype(np.float32))
+
+    # main.js:325-332 -> background.js:455: the eight fields of background.js:619-628 (+ offset, dogValue)
+    msgs = post(type=T["REFINE_CANDIDATE_KEYPOINTS"], differenceOfGaussians=dog, candidateKeypoints=cands, scalesPerOctave=spo,
+                numberOfOctaves=n_oct, minBlurLevel=min_blur)
+    kps = msgs[-1]["refinedKeypoints"]
+    ref = golden["keypoints"]
+    assert msgs[-1]["type"] == T["RECEIVED_REFINED_KEYPOINTS"] and len(kps) == len(ref) > 0
+    fields = ("octave", "scaleLevel", "localX", "localY", "absoluteSigma", "absoluteX", "absoluteY", "interpolatedValue")
+    assert np.array_equal(np.array([[k[f] for f in fields] for k in kps]), ref)
+    assert kps[0]["offset"] == [0.25, -0.5, 0.125] and kps[0]["dogValue"] == 0.0625
+    assert fake.calls.count("create") == 1 and "refine" in fake.calls          # one context, like the reference's one worker
+    worker["postMessage"](J(type="no-such-request"))                              # background.js:18-49: unknown types are ignored
+    drain()
+    assert inbox == []
+
+
+def test_fused_detect_and_pixel_type_dispatch(golden):
+    fake = FakeAddon(golden)
+    interp, _ = H.make_interpreter(ADDON, fake)
+    bg = interp.load_module("background.js")
+    nat = interp.load_module("native.js")
+    u8 = H.Uint8Array.of_numpy(golden["input_u8"].ravel())
+    r = bg["detect"](J(data=u8, width=22, height=18), J(numberOfOctaves=2, minBlurLevel=1.6))
+    assert len(r["keypoints"]) == len(golden["keypoints"]) and r["stats"]["keypoints"] == len(golden["keypoints"])
+    assert fake.calls[-1] == ("detect", 22, 18, nat["DTYPE"]["U8"], 2, 1.6)
+    rgba = H.Uint8ClampedArray(22 * 18 * 4)
+    assert nat["toPixels"](J(data=rgba, width=22, height=18))["dtype"] == nat["DTYPE"]["RGBA8"]     # ImageData
+    assert nat["toPixels"](J(data=H.Float32Array(22 * 18), width=22, height=18))["dtype"] == nat["DTYPE"]["F32"]
+    assert nat["toPixels"]([[0.0, 1.0], [0.5, 0.25]])["dtype"] == nat["DTYPE"]["F64"]
+    with pytest.raises(Exception):
+        nat["toPixels"](J(data=[1, 2, 3], width=3, height=1))
+
+
+def test_step_functions_keep_the_reference_semantics(golden):
+    """src/sift.js:72-149: `output` is mutated in place inside the chunk only and the chunk comes back as a matrix."""
+    s = np.load(os.path.join(GOLDEN, "ref_steps.npz"), allow_pickle=True)
+    interp, _ = H.make_interpreter(ADDON, FakeAddon(golden))
+    sift = interp.load_module("sift.js")
+    out = [[0.0] * 9 for _ in range(11)]
+    chunk = sift["SIFT_blurMatrix2DChunk"](s["blur_in"].tolist(), out, float(s["blur_sigma"]), J(x1=2, y1=1, x2=8, y2=10))
+    assert np.array_equal(np.array(chunk), s["blur_chunk"]) and np.array_equal(np.array(out), s["blur_output"])
+    out = [[0.0] * 7 for _ in range(6)]
+    chunk = sift["SIFT_subtractMatrix2DChunk"]([s["sub_a"].tolist(), s["sub_b"].tolist()], out, J(x1=1, y1=0, x2=7, y2=5))
+    assert np.array_equal(np.array(chunk), s["sub_chunk"]) and np.array_equal(np.array(out), s["sub_output"])
+    # the fast shape: {data: Float64Array, width, height} in, written in place, chunk back in the same shape
+    src = J(data=H.Float64Array.of_numpy(s["sub_a"].ravel()), width=7, height=6)
+    src2 = J(data=H.Float64Array.of_numpy(s["sub_b"].ravel()), width=7, height=6)
+    dst = J(data=H.Float64Array(42), width=7, height=6)
+    chunk = sift["SIFT_subtractMatrix2DChunk"]([src, src2], dst, J(x1=1, y1=0, x2=7, y2=5))
+    assert np.array_equal(dst["data"].a.reshape(6, 7), s["sub_output"]) and (chunk["width"], chunk["height"]) == (6, 5)
+    assert np.array_equal(chunk["data"].a.reshape(5, 6), s["sub_chunk"])
+    r = sift["SIFT_findExtremas"]([t.tolist() for t in s["ext_trio"]], 3)
+    got = np.array([(e["x"], e["y"], e["value"]) for e in r["candidateKeypoints"]]).reshape(-1, 3)
+    low = np.array([(e["x"], e["y"], e["value"]) for e in r["lowContrastKeypoints"]]).reshape(-1, 3)
+    assert np.array_equal(got, s["ext_cand"]) and np.array_equal(low, s["ext_low"])
+    dog = [[J(image=t.tolist()) for t in s["ext_trio"]]]
+    assert np.array_equal(np.array(sift["SIFT_generateGradientVector"](0, 1, 4, 5, dog)), s["grad"])
+    assert np.array_equal(np.array(sift["SIFT_generateHessianMatrix"](0, 1, 4, 5, dog)), s["hess"])
