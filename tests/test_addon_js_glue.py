@@ -192,6 +192,39 @@ def test_worker_adapter_speaks_the_reference_protocol(golden):
     assert inbox == []
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_the_references_own_senders_drive_the_adapter(golden):
+    """the reference's src/worker.js sender functions (what main.js calls, worker.js:29-98), unmodified,
+    post their requests to a SiftWorker instead of a Worker; the message types of both files agree."""
+    fake = FakeAddon(golden)
+    interp, drain = H.make_interpreter(ADDON, fake)
+    ours = interp.load_module("worker-adapter.js")
+    ref = interp.load_module("/root/reference/src/worker.js")
+    for name, value in ours["WorkerMessageTypes"].items():
+        assert ref["WorkerMessageTypes"][name] == value, name
+    n_oct, spo, min_blur, assumed = (float(v) for v in golden["params"])
+    inbox = []
+    worker = ours["SiftWorker"]()
+    worker["onmessage"] = lambda e: inbox.append(e["data"])
+    ref["workerComputeGaussianScaleSpace"](worker, J(input_image=golden["input_matrix"].tolist(), min_blur_level=min_blur,
+                                                     chunk_size=32, number_of_octaves=n_oct, scales_per_octave=spo,
+                                                     assumed_blur=assumed))                        # main.js:111-117
+    drain()
+    ss = inbox.pop()["scaleSpace"]
+    ref["workerComputeDifferenceOfGaussians"](worker, ss)                                          # main.js:239
+    drain()
+    dog = inbox.pop()["differenceOfGaussians"]
+    ref["workerFindCandidateKeypoints"](worker, dog, [o[0]["image"] for o in ss], spo)             # main.js:274-280
+    drain()
+    cands = inbox.pop()["candidateKeypoints"]
+    ref["workerRefineCandidateKeypoints"](worker, dog, cands, spo, n_oct, min_blur)                # main.js:325-332
+    drain()
+    msg = inbox.pop()
+    assert inbox == [] and msg["type"] == ref["WorkerMessageTypes"]["RECEIVED_REFINED_KEYPOINTS"]
+    fields = ("octave", "scaleLevel", "localX", "localY", "absoluteSigma", "absoluteX", "absoluteY", "interpolatedValue")
+    assert np.array_equal(np.array([[k[f] for f in fields] for k in msg["refinedKeypoints"]]), golden["keypoints"])
+
+
 def test_fused_detect_and_pixel_type_dispatch(golden):
     fake = FakeAddon(golden)
     interp, _ = H.make_interpreter(ADDON, fake)
