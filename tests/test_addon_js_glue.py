@@ -267,3 +267,85 @@ def test_step_functions_keep_the_reference_semantics(golden):
     dog = [[J(image=t.tolist()) for t in s["ext_trio"]]]
     assert np.array_equal(np.array(sift["SIFT_generateGradientVector"](0, 1, 4, 5, dog)), s["grad"])
     assert np.array_equal(np.array(sift["SIFT_generateHessianMatrix"](0, 1, 4, 5, dog)), s["hess"])
+
+
+class EngineAddon:
+    """The stage entry points of sift_addon.c over the real engine (ctypes): what a Node host would get from the GPU."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def create(self, device=0):
+        return J(handle=1)
+
+    @staticmethod
+    def _params(p):
+        return L.default_params(numberOfOctaves=int(p["numberOfOctaves"]), scalesPerOctave=int(p["scalesPerOctave"]),
+                                minBlurLevel=float(p["minBlurLevel"]), assumedBlur=float(p["assumedBlur"]))
+
+    def buildScaleSpace(self, ctx, data, w, h, dtype, prm):
+        self.prm = self._params(prm)
+        self.e.build_scale_space(np.ascontiguousarray(data.a.reshape(int(h), int(w))), self.prm)
+        self.e.build_dog()
+
+    def pyramidInfo(self, ctx):
+        n_oct, nlev = self.e.pyramid_info()
+        return J(octaves=n_oct, levels=nlev)
+
+    def getLevel(self, ctx, kind, o, s):
+        m = self.e.get_level(int(kind), int(o), int(s))
+        return J(blurLevel=self.e.blur_level(int(kind), int(o), int(s)), width=m.shape[1], height=m.shape[0],
+                 data=H.Float32Array.of_numpy(m.ravel()))
+
+    def levelPreview(self, ctx, kind, o, s, mode, coefficient):
+        rgba, mm = self.e.level_preview(int(kind), int(o), int(s), int(mode), float(coefficient))
+        return J(width=rgba.shape[1], height=rgba.shape[0], min=mm[0], max=mm[1], data=H.Uint8ClampedArray.of_numpy(rgba.ravel()))
+
+    def findCandidates(self, ctx, prm, want_low):
+        c, _ = self.e.find_candidates()
+        return J(count=len(c), records=H.ArrayBuffer(np.frombuffer(c.tobytes(), dtype=np.uint8).copy()))
+
+    def refine(self, ctx, prm, buffer, count):
+        c = np.frombuffer(buffer.data.tobytes(), dtype=L.CANDIDATE_DTYPE)[:int(count)]
+        k, _ = self.e.refine(c, self.prm)
+        return J(count=len(k), records=H.ArrayBuffer(np.frombuffer(k.tobytes(), dtype=np.uint8).copy()))
+
+
+@pytest.mark.gpu
+def test_worker_protocol_over_the_real_engine_reproduces_the_reference(engine, golden):
+    """main.js's four requests -> addon/worker-adapter.js -> addon/background.js -> (stand-in for the N-API layer) ->
+    libsift_b200.so on the GPU: the refined keypoints are the reference's (same cells, positions to 1e-3 px)."""
+    interp, drain = H.make_interpreter(ADDON, EngineAddon(engine))
+    mod = interp.load_module("worker-adapter.js")
+    T = mod["WorkerMessageTypes"]
+    n_oct, spo, min_blur, assumed = (float(v) for v in golden["params"])
+    inbox = []
+    worker = mod["SiftWorker"](J(previews=True))
+    worker["onmessage"] = lambda e: inbox.append(e["data"])
+
+    def post(**m):
+        worker["postMessage"](J(**m))
+        drain()
+        out = list(inbox)
+        inbox.clear()
+        return out
+
+    msgs = post(type=T["COMPUTE_GAUSSIAN_SCALE_SPACE"], inputImage=golden["input_matrix"].tolist(), numberOfOctaves=n_oct,
+                scalesPerOctave=spo, minBlurLevel=min_blur, assumedBlur=assumed, chunkSize=32)
+    assert len(msgs) == 13
+    ss = msgs[-1]["scaleSpace"]
+    for o in range(2):
+        for s in range(6):
+            ref = golden[f"gauss_{o}_{s}"]
+            assert np.abs(np.array(ss[o][s]["image"]) - ref).max() <= 1e-5 * np.abs(ref).max()
+    dog = post(type=T["COMPUTE_DIFFERENCE_OF_GAUSSIANS"], scaleSpace=ss)[-1]["differenceOfGaussians"]
+    cands = post(type=T["FIND_CANDIDATE_KEYPOINTS"], differenceOfGaussians=dog, octaveBaseImages=[], scalesPerOctave=spo)[-1]["candidateKeypoints"]
+    flat = [(o, e["scaleLevel"], x["x"], x["y"]) for o, oc in enumerate(cands) for e in oc for x in e["localExtremas"]]
+    assert np.array_equal(np.array(flat), golden["candidates"][:, :4])
+    kps = post(type=T["REFINE_CANDIDATE_KEYPOINTS"], differenceOfGaussians=dog, candidateKeypoints=cands, scalesPerOctave=spo,
+               numberOfOctaves=n_oct, minBlurLevel=min_blur)[-1]["refinedKeypoints"]
+    ref = golden["keypoints"]
+    got = np.array([[k[f] for f in ("octave", "scaleLevel", "localX", "localY", "absoluteSigma", "absoluteX", "absoluteY",
+                                    "interpolatedValue")] for k in kps])
+    assert got.shape == ref.shape and np.array_equal(got[:, :4], ref[:, :4])
+    assert np.abs(got[:, 5:7] - ref[:, 5:7]).max() <= 1e-3 and np.allclose(got[:, 4], ref[:, 4], rtol=1e-3)
