@@ -225,6 +225,52 @@ def test_the_references_own_senders_drive_the_adapter(golden):
     assert np.array_equal(np.array([[k[f] for f in fields] for k in msg["refinedKeypoints"]]), golden["keypoints"])
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_option_a_the_references_driver_with_our_step_functions():
+    """INTEGRATION.md option A, executed: the reference's UNMODIFIED background.js with its `./src/sift.js` import
+    answered by addon/sift.js (arithmetic behind it: the float64 oracle standing in for the addon).  Driven like the
+    page drives its worker, the four replies equal the reference's own run on the same input, bit for bit."""
+    from oracle import make_golden
+    g = np.load(os.path.join(GOLDEN, "ref_g16x16_o2_s2_b10.npz"), allow_pickle=True)
+    outbox = []
+    interp, _ = H.make_interpreter(ADDON, FakeAddon(g))
+    interp.global_scope.vars.update({"onmessage": None, "postMessage": lambda m, *r: outbox.append(m),
+                                     "console": J(log=lambda *a: None), "OffscreenCanvas": make_golden._Canvas})
+    interp.virtual_modules["./src/sift.js"] = interp.load_module("sift.js")        # the swap of background.js:6
+    interp.load_module("/root/reference/background.js")
+    send = interp.load_module("/root/reference/src/worker.js")
+    T = send["WorkerMessageTypes"]
+    handle = J(postMessage=lambda m, *r: interp.get_global("onmessage")(J(data=m)))
+    n_oct, spo, min_blur, assumed = (float(v) for v in g["params"])
+
+    def reply(kind):
+        hits = [m for m in outbox if m.get("type") == T[kind]]
+        outbox.clear()
+        assert len(hits) == 1
+        return hits[0]
+
+    send["workerComputeGaussianScaleSpace"](handle, J(input_image=g["input_matrix"].tolist(), min_blur_level=min_blur,
+                                                      chunk_size=32, number_of_octaves=n_oct, scales_per_octave=spo,
+                                                      assumed_blur=assumed))
+    ss = reply("RECEIVED_GAUSSIAN_SCALE_SPACE")["scaleSpace"]
+    for o in range(int(n_oct)):
+        for s in range(int(spo) + 3):
+            assert np.array_equal(np.array(ss[o][s]["image"]), g[f"gauss_{o}_{s}"]), (o, s)
+    send["workerComputeDifferenceOfGaussians"](handle, ss)
+    dog = reply("RECEIVED_DIFFERENCE_OF_GAUSSIANS")["differenceOfGaussians"]
+    assert np.array_equal(np.array(dog[1][2]["image"]), g["dog_1_2"])
+    send["workerFindCandidateKeypoints"](handle, dog, [o[0]["image"] for o in ss], spo)
+    cands = reply("RECEIVED_CANDIDATE_KEYPOINTS")["candidateKeypoints"]
+    flat = [(o, e["scaleLevel"], x["x"], x["y"], x["value"]) for o, oc in enumerate(cands) for e in oc for x in e["localExtremas"]]
+    assert np.array_equal(np.array(flat), g["candidates"])
+    send["workerRefineCandidateKeypoints"](handle, dog, cands, spo, n_oct, min_blur)
+    kps = reply("RECEIVED_REFINED_KEYPOINTS")["refinedKeypoints"]
+    fields = ("octave", "scaleLevel", "localX", "localY", "absoluteSigma", "absoluteX", "absoluteY", "interpolatedValue")
+    got = np.array([[k[f] for f in fields] for k in kps])
+    assert got.shape == g["keypoints"].shape and np.array_equal(got[:, :4], g["keypoints"][:, :4])
+    assert np.array_equal(got[:, 5:], g["keypoints"][:, 5:]) and np.allclose(got[:, 4], g["keypoints"][:, 4], rtol=4e-16, atol=0)
+
+
 def test_fused_detect_and_pixel_type_dispatch(golden):
     fake = FakeAddon(golden)
     interp, _ = H.make_interpreter(ADDON, fake)
