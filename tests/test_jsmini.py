@@ -105,6 +105,33 @@ def test_modules_and_exports(tmp_path):
     assert js.get_global("result") == "42a"
 
 
+def test_array_constructor_instanceof_and_host_modules(tmp_path):
+    """What addon/*.js needs beyond the reference's subset (tests/test_addon_js_glue.py runs those files)."""
+    class Box:                                            # a host class: `new Box(v)`, `x instanceof Box`, indexed reads
+        def __init__(self, v=0):
+            self.v = v
+
+        def js_get(self, i):
+            return self.v + i
+
+        def js_set(self, i, v):
+            self.v = v - i
+
+    js = jsmini.Interpreter(str(tmp_path), {"Box": Box})
+    assert js.eval("new Array(3).length") == 3 and js.eval("Array.isArray(new Array(2))") is True
+    assert js.eval("Array.from([1, 2, 3], (v, i) => v * 10 + i)") == [10, 21, 32]
+    assert js.eval("Array.from({ length: 3 }, (_, i) => i * i)") == [0, 1, 4]
+    assert js.eval("new Box(5) instanceof Box") is True and js.eval("[] instanceof Box") is False
+    assert js.eval("[1] instanceof Array") is True and js.eval("({}) instanceof Array") is False
+    assert js.eval("(() => { const b = new Box(5); b[2] = 10; return b[1]; })()") == 9
+    assert js.eval("null ?? 7") == 7 and js.eval("0 ?? 7") == 0
+    assert js.eval("({ a: 1, ...{ b: 2, a: 3 } }).a") == 3
+    js.virtual_modules["host:thing"] = {"answer": lambda: 42}
+    (tmp_path / "m.js").write_text("import { answer } from 'host:thing';\nexport const where = import.meta.url;\nexport const v = answer();\n")
+    m = js.load_module("m.js")
+    assert m["v"] == 42 and m["where"].startswith("file://") and str(tmp_path) in m["where"]
+
+
 def test_undeclared_assignment_throws_in_strict_modules(tmp_path):
     (tmp_path / "bad.js").write_text("undeclared_global = 1;\n")
     js = jsmini.Interpreter(str(tmp_path))
