@@ -52,6 +52,14 @@ class FakeAddon:
         k = self.g["keypoints"]
         return J(records=self._records(k), count=len(k), stats=J(keypoints=len(k), candidates=len(self.g["candidates"])))
 
+    def detectBatch(self, ctx, frames, w, h, n_images, dtype, prm, capacity):
+        assert frames.length == w * h * n_images
+        k = self.g["keypoints"]
+        counts = [len(k) if i % 2 == 0 else 0 for i in range(int(n_images))]          # odd frames: no keypoints
+        rows = np.concatenate([k] * sum(1 for c in counts if c)) if any(counts) else k[:0]
+        offs = H.Int32Array.of_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+        return J(records=self._records(rows), offsets=offs, stats=J(keypoints=len(rows)))
+
     # -- stages
     def buildScaleSpace(self, ctx, data, w, h, dtype, prm):
         assert isinstance(data, H.Float64Array) and dtype == 2                       # a Matrix2D arrives as F64
@@ -280,6 +288,11 @@ def test_fused_detect_and_pixel_type_dispatch(golden):
     r = bg["detect"](J(data=u8, width=22, height=18), J(numberOfOctaves=2, minBlurLevel=1.6))
     assert len(r["keypoints"]) == len(golden["keypoints"]) and r["stats"]["keypoints"] == len(golden["keypoints"])
     assert fake.calls[-1] == ("detect", 22, 18, nat["DTYPE"]["U8"], 2, 1.6)
+    frames = H.Uint8Array(22 * 18 * 3)
+    b = bg["detectBatch"](frames, 22, 18, 3, nat["DTYPE"]["U8"], J(numberOfOctaves=2))
+    nk = len(golden["keypoints"])
+    assert [len(f) for f in b["keypoints"]] == [nk, 0, nk] and b["stats"]["keypoints"] == 2 * nk
+    assert b["keypoints"][2][0]["absoluteX"] == float(golden["keypoints"][0][5])
     rgba = H.Uint8ClampedArray(22 * 18 * 4)
     assert nat["toPixels"](J(data=rgba, width=22, height=18))["dtype"] == nat["DTYPE"]["RGBA8"]     # ImageData
     assert nat["toPixels"](J(data=H.Float32Array(22 * 18), width=22, height=18))["dtype"] == nat["DTYPE"]["F32"]
