@@ -5,7 +5,15 @@
 // of background.js:233-236, 350-353, 446-449, 681-684 -- plus one fused detect() that keeps the pyramid
 // on the GPU.  The postMessage transport is gone; addon/worker-adapter.js puts it back for callers that
 // still speak WorkerMessageTypes.
-import { native, context, toPixels, toMatrix2D, decodeKeypoints, decodeCandidates, encodeCandidates, LEVEL } from './native.js';
+import { native, context, toPixels, toF64, toMatrix2D, decodeKeypoints, decodeCandidates, encodeCandidates, LEVEL } from './native.js';
+
+// Which replies does the device still hold?  The reference consumes the pyramid IN each request (background.js:258,
+// 359, 455); here the context keeps it on the GPU, so a stage may only skip the upload when the payload is the very
+// reply object this module produced AND nothing has rebuilt the context's pyramid since (native.pyramidSerial changes
+// on every build / detect / setLevel).  Anything else -- another image in between, a cloned or edited payload -- is
+// uploaded (DoG) or recomputed from the payload (scale space), exactly as the reference would have used it.
+const resident = { gaussian: null, dog: null, serial: -1 };
+const holds = (kind, payload) => payload != null && resident[kind] === payload && native.pyramidSerial(context()) === resident.serial;
 
 const paramsOf = (o = {}) => ({
   numberOfOctaves: o.numberOfOctaves ?? 5, scalesPerOctave: o.scalesPerOctave ?? 3,         // worker.js:33-34
@@ -62,16 +70,49 @@ export function dogChunkPreview(octave, scale, chunk) {
 export function computeGaussianScaleSpace(request, { matrices = Array.isArray(request.inputImage) } = {}) {
   const px = toPixels(request.inputImage);
   native.buildScaleSpace(context(), px.data, px.width, px.height, px.dtype, paramsOf(request));
-  return readLevels(LEVEL.GAUSSIAN, matrices);
+  const reply = readLevels(LEVEL.GAUSSIAN, matrices);
+  resident.gaussian = reply; resident.dog = null; resident.serial = native.pyramidSerial(context());
+  return reply;
 }
 
 /** background.js:258 -- the DoG of the pyramid the context holds (formed by the blur kernels). */
-export function computeDifferenceOfGaussians(_scaleSpace, { matrices = true } = {}) {
-  return readLevels(LEVEL.DOG, matrices);
+export function computeDifferenceOfGaussians(scaleSpace, { matrices = true } = {}) {
+  if (scaleSpace == null || holds('gaussian', scaleSpace)) {       // the blur kernels already formed it, unrounded
+    const reply = readLevels(LEVEL.DOG, matrices);
+    if (scaleSpace != null) resident.dog = reply;
+    return reply;
+  }
+  // a scale space this context does not hold: D[o][s-1] = S[o][s-1] - S[o][s] from the payload (background.js:269-330)
+  const reply = [];
+  for (const octave of scaleSpace) {
+    const levels = [];
+    for (let s = 1; s < octave.length; s++) {
+      const a = toF64(octave[s - 1].image), b = toF64(octave[s].image);
+      const out = new Float64Array(a.rows * a.cols);
+      native.subtractChunk(context(), a.data, b.data, a.rows, a.cols, out, 0, 0, a.cols, a.rows);
+      levels.push({ blurLevel: octave[s - 1].blurLevel,
+                    image: matrices ? toMatrix2D(out, a.rows, a.cols) : { data: out, width: a.cols, height: a.rows } });
+    }
+    reply.push(levels);
+  }
+  return reply;
+}
+
+/** Make the context hold the DoG pyramid of a request (upload unless it is the resident one). */
+function ensureDogResident(dog, request) {
+  if (dog == null || holds('dog', dog)) return;
+  const first = toF64(dog[0][0].image);
+  const prm = paramsOf(request);
+  prm.numberOfOctaves = dog.length; prm.scalesPerOctave = dog[0].length - 2;
+  native.setPyramidShape(context(), first.cols, first.rows, prm);
+  for (let o = 0; o < dog.length; o++)
+    for (let s = 0; s < dog[o].length; s++) native.setLevel(context(), LEVEL.DOG, o, s, Float32Array.from(toF64(dog[o][s].image).data));
+  resident.gaussian = null; resident.dog = dog; resident.serial = native.pyramidSerial(context());
 }
 
 /** background.js:359 -- request {differenceOfGaussians, octaveBaseImages (unused), scalesPerOctave}. */
 export function findCandidateKeypoints(request) {
+  ensureDogResident(request.differenceOfGaussians, request);
   const r = native.findCandidates(context(), null, false);
   const info = native.pyramidInfo(context());
   const reply = [];
@@ -86,6 +127,7 @@ export function findCandidateKeypoints(request) {
 /** background.js:455 -- request {differenceOfGaussians, scalesPerOctave, numberOfOctaves, candidateKeypoints,
  *  minBlurLevel, minInterpixelDistance}. */
 export function refineCandidateKeypoints(request) {
+  ensureDogResident(request.differenceOfGaussians, request);
   const flat = [];
   for (let octave = 0; octave < request.numberOfOctaves; octave++)                     // background.js:468-471
     for (let scale_i = 0; scale_i < request.scalesPerOctave; scale_i++) {

@@ -85,7 +85,8 @@ static void *get_bytes(napi_env env, napi_value v, size_t *bytes)
     size_t len = 0, off = 0;
     napi_value ab;
     if (napi_get_typedarray_info(env, v, &t, &len, &data, &ab, &off) != napi_ok) return NULL;
-    static const size_t es[] = { 1, 1, 1, 2, 2, 4, 4, 4, 8, 8, 8 };
+    static const size_t es[] = { 1, 1, 1, 2, 2, 4, 4, 4, 8, 8, 8 };     /* napi_int8_array .. napi_biguint64_array */
+    if ((size_t)t >= sizeof es / sizeof es[0]) return NULL;             /* element types newer than this table */
     *bytes = len * es[t];
     return data;
   }
@@ -182,7 +183,8 @@ static napi_value Detect(napi_env env, napi_callback_info info)
     int n = 0;
     sift_stats st;
     const int rc = sift_detect(ctx, px, dtype, w, h, 0, &prm, (sift_keypoint *)rec, cap, &n, &st);
-    if (rc == SIFT_ERR_CAPACITY) { cap = n; continue; }            /* n holds the required count */
+    if (rc == SIFT_ERR_CAPACITY && n > cap) { cap = n; continue; }  /* n holds the required count; any other capacity
+                                                                     * failure (device buffers kept overflowing) throws */
     if (rc != SIFT_OK) return throw_status(env, ctx, rc);
     napi_value out;
     napi_create_object(env, &out);
@@ -232,11 +234,26 @@ static napi_value BuildScaleSpace(napi_env env, napi_callback_info info)
   size_t bytes = 0;
   void *px = get_bytes(env, argv[1], &bytes);
   if (!ctx || !px) return throw_msg(env, "SIFT_ERR_BAD_ARGS", "context / pixel buffer expected");
+  const int w = get_i32(env, argv[2]), h = get_i32(env, argv[3]), dtype = get_i32(env, argv[4]);
+  static const size_t px_bytes[] = { 1, 4, 8, 4 };                      /* SIFT_U8, SIFT_F32, SIFT_F64, SIFT_RGBA8 */
+  if (w < 1 || h < 1 || dtype < 0 || dtype > 3 || bytes < (size_t)w * h * px_bytes[dtype])
+    return throw_msg(env, "SIFT_ERR_BAD_ARGS", "pixel buffer smaller than width * height of the given dtype");
   sift_params prm;
   get_params(env, argv[5], &prm);
-  const int rc = sift_build_scale_space(ctx, px, get_i32(env, argv[4]), get_i32(env, argv[2]), get_i32(env, argv[3]), 0, &prm);
+  const int rc = sift_build_scale_space(ctx, px, dtype, w, h, 0, &prm);
   if (rc != SIFT_OK) return throw_status(env, ctx, rc);
   return NULL;
+}
+
+/* pyramidSerial(ctx) -> generation of the pyramid the stage calls read (sift_pyramid_serial) */
+static napi_value PyramidSerial(napi_env env, napi_callback_info info)
+{
+  ARGS(1);
+  sift_ctx *ctx = get_ctx(env, argv[0]);
+  if (!ctx) return throw_msg(env, "SIFT_ERR_BAD_ARGS", "context expected");
+  napi_value n;
+  napi_create_double(env, (double)sift_pyramid_serial(ctx), &n);
+  return n;
 }
 
 /* pyramidInfo(ctx) -> {octaves, levels, sizes:[w0,h0,w1,h1,...] as Int32Array} */
@@ -359,7 +376,7 @@ static napi_value FindCandidates(napi_env env, napi_callback_info info)
     int n = 0, nl = 0;
     const int rc = sift_find_candidates(ctx, pp, (sift_candidate *)rec, cap, &n, want_low ? (sift_candidate *)lrec : NULL,
                                         want_low ? cap : 0, want_low ? &nl : NULL);
-    if (rc == SIFT_ERR_CAPACITY) { cap = (n > nl ? n : nl); continue; }
+    if (rc == SIFT_ERR_CAPACITY && (n > cap || nl > cap)) { cap = (n > nl ? n : nl); continue; }
     if (rc != SIFT_OK) return throw_status(env, ctx, rc);
     napi_value out;
     napi_create_object(env, &out);
@@ -522,7 +539,7 @@ NAPI_EXTERN napi_value napi_register_module_v1(napi_env env, napi_value exports)
 {
   static const struct { const char *name; napi_callback fn; } table[] = {
     { "create", Create }, { "version", Version }, { "detect", Detect }, { "detectBatch", DetectBatch },
-    { "buildScaleSpace", BuildScaleSpace }, { "pyramidInfo", PyramidInfo }, { "getLevel", GetLevel }, { "levelPreview", LevelPreview },
+    { "buildScaleSpace", BuildScaleSpace }, { "pyramidInfo", PyramidInfo }, { "pyramidSerial", PyramidSerial }, { "getLevel", GetLevel }, { "levelPreview", LevelPreview },
     { "setPyramidShape", SetPyramidShape }, { "setLevel", SetLevel }, { "findCandidates", FindCandidates },
     { "refine", Refine }, { "blurChunk", BlurChunk }, { "subtractChunk", SubtractChunk },
     { "findExtremas", FindExtremas }, { "gradientHessian", GradientHessian }, { "linearResize", LinearResize },

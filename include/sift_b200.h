@@ -135,8 +135,9 @@ typedef struct sift_stats {
   int32_t rejSingular;      /* abs(det) < Number.EPSILON (matrix2d.js:482): the reference throws, we discard */
   float msDevice;           /* CUDA-event time of the device work of this call */
   int32_t kernelLaunches;   /* kernels launched by this call */
-  int32_t leftStrip;        /* mosaic strips only: walks (counted in rejLeftRows) that left the strip's halo, not the
-                             * image -- 0 means the strip result equals the whole-image result */
+  int32_t leftStrip;        /* mosaic strips only: walks that jumped to a row this strip does not hold (not out of the
+                             * image).  They are NOT counted in any rej* field here: each is handed out as a sift_walk
+                             * (sift_strip_escaped) and its outcome is counted by the strip that ends it */
 } sift_stats;
 
 typedef struct sift_ctx sift_ctx;
@@ -161,6 +162,11 @@ SIFT_API int sift_set_keep_gaussian(sift_ctx *ctx, int keep);
 /* Frames in flight for sift_detect_device / sift_detect_batch (1..4, default 3, env SIFT_B200_LANES). */
 SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes);
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for the context */
+/* Generation of the pyramid the stage calls read (sift_get_level, sift_find_candidates, sift_refine ...): changes
+ * whenever any call rebuilds, replaces or invalidates it (sift_build_scale_space, sift_detect*, sift_set_level,
+ * sift_strip_begin, a plan change).  A host that caches "the context still holds the pyramid of reply X" -- as the
+ * reference's main thread holds gaussian_scale_space / difference_of_gaussians (main.js:31-32) -- compares this. */
+SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx);
 
 /* Per-kernel-class device timing (CUDA events around each launch group on sift_stream).
  * Off by default; bench.py turns it on for a separate instrumented pass. */
@@ -186,7 +192,11 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
 
 /* Same, image already in device memory; keypoints stay in device memory
  * (d_out; in the reference's order when `ordered` != 0, which adds a device-side radix sort, else in
- * completion order) and *d_count (device int) receives the count (which may exceed cap: only cap are written).  Asynchronous: ordered after what is already queued on sift_stream(ctx);
+ * completion order) and *d_count (device int) receives the count.  Overflow is reported on the device, never
+ * silently truncated: when the context's candidate list or `cap` (ordered: min(cap, the lane's record buffer))
+ * was too small, *d_count = -(capacity that would have sufficed) and the records written are an arbitrary
+ * subset that must not be used -- call again with a larger cap / through sift_detect, which grows the buffers.
+ * Asynchronous: ordered after what is already queued on sift_stream(ctx);
  * sift_flush() / sift_synchronize() order the results before later work on that stream. */
 SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
                                 size_t pitch_bytes, const sift_params *params,

@@ -115,6 +115,9 @@ def lib():
         L.oracle_refine_one.argtypes = [C.POINTER(Pyramid), C.POINTER(Candidate),
                                         C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
                                         C.POINTER(Keypoint)]
+        L.oracle_refine_margin.restype = C.c_double
+        L.oracle_refine_margin.argtypes = [C.POINTER(Pyramid), C.POINTER(Candidate), C.c_double, C.c_double, C.c_int,
+                                           C.c_double]
         L.oracle_detect.argtypes = [_DP, C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.POINTER(Pyramid),
                                     C.POINTER(Keypoint), C.c_int, C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -254,7 +257,8 @@ def _kp_dict(k: Keypoint) -> dict:
 
 
 class Result:
-    """Everything the four stages produce for one image (numpy copies)."""
+    """Everything the four stages produce for one image.  The level arrays are views of the C pyramid, which is
+    released with the Result (close() / garbage collection)."""
 
     def __init__(self):
         self.gauss = []        # [o][s] float64 arrays
@@ -263,8 +267,23 @@ class Result:
         self.dog = []          # [o][s]
         self.candidates = []   # dicts octave, scale, x, y, value (reference order)
         self.n_low_contrast = 0
+        self.low_contrast = [] # dicts like candidates: extrema below the pre-filter (sift.js:301-306), reference order
+        self.margins = {}      # (octave, scale, y, x) -> oracle_refine_margin of that candidate (test diagnostic)
         self.keypoints = []    # dicts (reference order)
         self.outcomes = {}
+        self._pyr = None
+
+    def close(self):
+        if self._pyr is not None:
+            self.gauss, self.dog = [], []
+            lib().oracle_pyramid_free(C.byref(self._pyr))
+            self._pyr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def detect(image, params: Params | None = None, separable: bool = False, keep_levels: bool = True,
@@ -279,28 +298,30 @@ def detect(image, params: Params | None = None, separable: bool = False, keep_le
                                                1 if separable else 0, C.byref(pyr))
     if rc:
         raise RuntimeError(f"oracle scale space failed rc={rc}")
+    res = Result()
+    res._pyr = pyr
     try:
         L.oracle_compute_dog(C.byref(pyr))
         nc, nl = C.c_int(), C.c_int()
         L.oracle_find_candidates(C.byref(pyr), prm.contrastThreshold, prm.preFilterFactor,
                                  None, 0, C.byref(nc), None, 0, C.byref(nl))
         cand = (Candidate * max(1, nc.value))()
+        low = (Candidate * max(1, nl.value))()
         L.oracle_find_candidates(C.byref(pyr), prm.contrastThreshold, prm.preFilterFactor,
-                                 cand, nc.value, C.byref(nc), None, 0, C.byref(nl))
+                                 cand, nc.value, C.byref(nc), low, nl.value, C.byref(nl))
         kps = (Keypoint * max(1, nc.value))()
         nk = C.c_int()
         outc = (C.c_int * len(OUTCOMES))()
         L.oracle_refine(C.byref(pyr), cand, nc.value, prm.contrastThreshold, prm.edgeRatio, prm.maxIterations,
                         prm.offsetBound, prm.minBlurLevel, prm.minInterpixelDistance,
                         kps, nc.value, C.byref(nk), outc)
-        res = Result()
         for o in range(pyr.octaves):
             shape = (pyr.rows[o], pyr.cols[o])
             n = shape[0] * shape[1]
             if keep_levels:
-                res.gauss.append([np.ctypeslib.as_array(pyr.gauss[o][s], shape=(n,)).reshape(shape).copy()
+                res.gauss.append([np.ctypeslib.as_array(pyr.gauss[o][s], shape=(n,)).reshape(shape)
                                   for s in range(pyr.levels)])
-                res.dog.append([np.ctypeslib.as_array(pyr.dog[o][s], shape=(n,)).reshape(shape).copy()
+                res.dog.append([np.ctypeslib.as_array(pyr.dog[o][s], shape=(n,)).reshape(shape)
                                 for s in range(pyr.levels - 1)])
             res.blur.append([pyr.blur[o][s] for s in range(pyr.levels)])
             res.offset_sigma.append([pyr.offset_sigma[o][s] for s in range(pyr.levels)])
@@ -308,8 +329,17 @@ def detect(image, params: Params | None = None, separable: bool = False, keep_le
         res.candidates = [{"octave": cand[i].octave, "scale": cand[i].scale, "x": cand[i].x, "y": cand[i].y,
                            "value": cand[i].value} for i in range(nc.value)]
         res.n_low_contrast = nl.value
+        res.low_contrast = [{"octave": low[i].octave, "scale": low[i].scale, "x": low[i].x, "y": low[i].y,
+                             "value": low[i].value} for i in range(nl.value)]
+        for i in range(nc.value):
+            res.margins[(cand[i].octave, cand[i].scale, cand[i].y, cand[i].x)] = L.oracle_refine_margin(
+                C.byref(pyr), C.byref(cand[i]), prm.contrastThreshold, prm.edgeRatio, prm.maxIterations,
+                prm.offsetBound)
         res.keypoints = [_kp_dict(kps[i]) for i in range(nk.value)]
         res.outcomes = {OUTCOMES[i]: outc[i] for i in range(len(OUTCOMES))}
+        if not keep_levels:
+            res.close()
         return res
-    finally:
-        L.oracle_pyramid_free(C.byref(pyr))
+    except Exception:
+        res.close()
+        raise

@@ -27,6 +27,8 @@
  * Images are row-major double[rows*cols]; "Matrix2D m[i][j]" == m[i*cols+j]
  * (matrix2d.js:5-31).
  */
+#include <pthread.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -186,6 +188,72 @@ int oracle_blur_image(const double *input, int rows, int cols, double *output, d
  * NOT line-by-line: mathematically the 2D kernel is the outer product of the
  * normalised 1D kernel (g(i,j) = g1(i) g1(j), sum = (sum g1)^2); results agree
  * with oracle_blur_image to ~1e-15 relative (tests/test_oracle.py checks). */
+/* Row bands of the two separable passes.  Every output is an independent sum taken in ascending tap order, so
+ * bands can run on separate threads (pthreads; ORACLE_THREADS, default = online cores, at most 32) and the
+ * vertical pass can run tap-outer / column-inner (contiguous reads) without changing a single bit of the result. */
+typedef struct {
+  const double *in; double *out; const double *k1;
+  int rows, cols, R, y0, y1, vertical;
+} sep_band;
+
+static void *sep_band_run(void *arg)
+{
+  const sep_band *b = (const sep_band *)arg;
+  const int size = 2 * b->R + 1, R = b->R, rows = b->rows, cols = b->cols;
+  if (!b->vertical) {
+    for (int y = b->y0; y < b->y1; y++)
+      for (int x = 0; x < cols; x++) {
+        double acc = 0;
+        for (int i = 0; i < size; i++) {
+          int _x = x + i - R; if (_x < 0) _x = 0; else if (_x >= cols) _x = cols - 1;
+          acc += b->in[(size_t)y * cols + _x] * b->k1[i];
+        }
+        b->out[(size_t)y * cols + x] = acc;
+      }
+  } else {
+    for (int y = b->y0; y < b->y1; y++) {
+      double *out = b->out + (size_t)y * cols;
+      for (int x = 0; x < cols; x++) out[x] = 0;
+      for (int j = 0; j < size; j++) {
+        int _y = y + j - R; if (_y < 0) _y = 0; else if (_y >= rows) _y = rows - 1;
+        const double *t = b->in + (size_t)_y * cols;
+        const double w = b->k1[j];
+        for (int x = 0; x < cols; x++) out[x] += t[x] * w;
+      }
+    }
+  }
+  return NULL;
+}
+
+static int sep_threads(int rows)
+{
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  const char *e = getenv("ORACLE_THREADS");
+  if (e && atoi(e) > 0) n = atoi(e);
+  if (n > 32) n = 32;
+  if (n > rows / 16) n = rows / 16;
+  return n < 1 ? 1 : (int)n;
+}
+
+static void sep_pass(const double *in, double *out, const double *k1, int rows, int cols, int R, int vertical)
+{
+  const int nt = sep_threads(rows);
+  pthread_t th[32];
+  sep_band band[32];
+  for (int t = 0; t < nt; t++) {
+    sep_band b = { in, out, k1, rows, cols, R, (int)((long long)rows * t / nt), (int)((long long)rows * (t + 1) / nt), vertical };
+    band[t] = b;
+  }
+  int started = 0;
+  for (int t = 1; t < nt; t++) {
+    if (pthread_create(&th[t], NULL, sep_band_run, &band[t]) != 0) break;
+    started = t;
+  }
+  sep_band_run(&band[0]);
+  for (int t = started + 1; t < nt; t++) sep_band_run(&band[t]);      /* threads that could not be created */
+  for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+}
+
 int oracle_blur_image_separable(const double *input, int rows, int cols, double *output, double sigma)
 {
   const int R = oracle_kernel_radius(sigma);
@@ -196,24 +264,8 @@ int oracle_blur_image_separable(const double *input, int rows, int cols, double 
   double s = 0;
   for (int i = 0; i < size; i++) { k1[i] = exp(-0.5 * (double)((i - R) * (i - R)) / (sigma * sigma)); s += k1[i]; }
   for (int i = 0; i < size; i++) k1[i] /= s;
-  for (int y = 0; y < rows; y++)
-    for (int x = 0; x < cols; x++) {
-      double acc = 0;
-      for (int i = 0; i < size; i++) {
-        int _x = x + i - R; if (_x < 0) _x = 0; else if (_x >= cols) _x = cols - 1;
-        acc += input[(size_t)y * cols + _x] * k1[i];
-      }
-      tmp[(size_t)y * cols + x] = acc;
-    }
-  for (int y = 0; y < rows; y++)
-    for (int x = 0; x < cols; x++) {
-      double acc = 0;
-      for (int j = 0; j < size; j++) {
-        int _y = y + j - R; if (_y < 0) _y = 0; else if (_y >= rows) _y = rows - 1;
-        acc += tmp[(size_t)_y * cols + x] * k1[j];
-      }
-      output[(size_t)y * cols + x] = acc;
-    }
+  sep_pass(input, tmp, k1, rows, cols, R, 0);
+  sep_pass(tmp, output, k1, rows, cols, R, 1);
   free(k1); free(tmp);
   return 0;
 }
@@ -513,6 +565,57 @@ int oracle_refine_one(const oracle_pyramid *p, const oracle_candidate *cnd,
     if (n < 1 || n >= cols - 1) return ORACLE_REFINE_LEFT_COLS;     /* :658 */
   }
   return ORACLE_REFINE_NO_CONVERGENCE;
+}
+
+/* TEST DIAGNOSTIC (no reference counterpart): walks a candidate exactly as oracle_refine_one does and returns how
+ * close the walk came to flipping a decision -- the smallest relative distance to a comparison threshold it met
+ * (offset bound :558, contrast :577, edge :599) or absolute distance of a moved coordinate to a Math.round boundary
+ * (:638-640).  A mismatch between two implementations is "explained" when this margin is within the stated
+ * tolerance (north_star: 1e-5 of a threshold). */
+double oracle_refine_margin(const oracle_pyramid *p, const oracle_candidate *cnd,
+                            double contrast, double edge_ratio, int max_iterations, double offset_bound)
+{
+  const int octave = cnd->octave;
+  const int rows = p->rows[octave], cols = p->cols[octave];
+  const int ndog = p->levels - 1;
+  const double *const *dog = (const double *const *)p->dog[octave];
+  int s = cnd->scale, m = cnd->y, n = cnd->x;
+  double margin = INFINITY;
+#define MARGIN_(d) do { const double d_ = (d); if (d_ < margin) margin = d_; } while (0)
+  for (int i = 0; i < max_iterations; i++) {
+    double g[3], h[3][3], inv[3][3];
+    oracle_gradient(dog, cols, s, m, n, g);
+    oracle_hessian(dog, cols, s, m, n, h);
+    if (!oracle_inverse3x3(h, inv)) return 0.0;
+    double alpha[3];
+    for (int r = 0; r < 3; r++) {
+      double result = 0;
+      for (int c = 0; c < 3; c++) result += (inv[r][c] * -1) * g[c];
+      alpha[r] = result;
+    }
+    for (int r = 0; r < 3; r++) MARGIN_(fabs(fabs(alpha[r]) - offset_bound) / offset_bound);
+    if (fabs(alpha[0]) < offset_bound && fabs(alpha[1]) < offset_bound && fabs(alpha[2]) < offset_bound) {
+      const double v = cnd->value + (((0.5 * alpha[0]) * g[0]) + ((0.5 * alpha[1]) * g[1]) + ((0.5 * alpha[2]) * g[2]));
+      const double threshold = oracle_contrast_threshold(p->spo, contrast);
+      MARGIN_(fabs(fabs(v) - threshold) / threshold);
+      if (fabs(v) < threshold) return margin;
+      const double tr = 0 + h[1][1] + h[2][2];
+      const double det = (h[1][1] * h[2][2]) - (h[1][2] * h[2][1]);
+      const double edgeness = (tr * tr) / det;
+      const double edge_threshold = ((edge_ratio + 1) * (edge_ratio + 1)) / edge_ratio;
+      if (edgeness == edgeness) MARGIN_(fabs(edgeness - edge_threshold) / edge_threshold);
+      return margin;
+    }
+    const double moved[3] = { s + alpha[0], m + alpha[1], n + alpha[2] };
+    for (int r = 0; r < 3; r++) {
+      const double f = (moved[r] + 0.5) - floor(moved[r] + 0.5);      /* 0 on a rounding boundary */
+      MARGIN_(f < 1 - f ? f : 1 - f);
+    }
+    s = (int)oracle_js_round(moved[0]); m = (int)oracle_js_round(moved[1]); n = (int)oracle_js_round(moved[2]);
+    if (s < 1 || s >= ndog - 1 || m < 1 || m >= rows - 1 || n < 1 || n >= cols - 1) return margin;
+  }
+#undef MARGIN_
+  return margin;
 }
 
 /* background.js:455-685 over the candidate list in reference order. */

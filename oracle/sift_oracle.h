@@ -90,6 +90,9 @@ int oracle_refine_one(const oracle_pyramid *p, const oracle_candidate *cnd,
                       double contrast, double edge_ratio, int max_iterations, double offset_bound,
                       double min_blur_level, double min_interpixel_distance,
                       oracle_keypoint *kp);
+/* test diagnostic: distance of a candidate's refinement walk to the nearest decision flip (see sift_oracle.c) */
+double oracle_refine_margin(const oracle_pyramid *p, const oracle_candidate *cnd,
+                            double contrast, double edge_ratio, int max_iterations, double offset_bound);
 int oracle_refine(const oracle_pyramid *p, const oracle_candidate *cand, int n_cand,
                   double contrast, double edge_ratio, int max_iterations, double offset_bound,
                   double min_blur_level, double min_interpixel_distance,

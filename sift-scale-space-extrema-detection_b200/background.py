@@ -17,14 +17,12 @@ from .engine import Engine, default_engine
 
 
 class _Resident(list):
-    """A reply (nested lists, like the reference's) that also remembers which engine still
-    holds the same pyramid on the device, so the next stage does not re-upload it."""
+    """A reply (nested lists, like the reference's) that also remembers which engine built it and the engine's
+    pyramid generation at that moment (sift_pyramid_serial), so the next stage does not re-upload a pyramid the
+    device still holds -- and DOES re-upload it when anything (another image, detect(), a strip) replaced it."""
     engine: Engine | None = None
     params: L.Params | None = None
     serial: int = -1
-
-
-_serial = [0]
 
 
 def _params(number_of_octaves=5, scales_per_octave=3, min_blur_level=0.8, assumed_blur=0.5, **extra) -> L.Params:
@@ -74,16 +72,14 @@ def computeGaussianScaleSpace(input_image, number_of_octaves=5, scales_per_octav
     for o in range(n_oct):
         reply.append([{"blurLevel": eng.blur_level(L.SIFT_LEVEL_GAUSSIAN, o, s),
                        "image": eng.get_level(L.SIFT_LEVEL_GAUSSIAN, o, s)} for s in range(nlev)])
-    _serial[0] += 1
-    reply.engine, reply.params, reply.serial = eng, prm, _serial[0]
-    eng._resident_serial = _serial[0]
+    reply.engine, reply.params, reply.serial = eng, prm, eng.pyramid_serial
     if post_message is not None:
         _post_level_images(eng, L.SIFT_LEVEL_GAUSSIAN, post_message)
     return reply
 
 
 def _is_resident(obj, eng) -> bool:
-    return isinstance(obj, _Resident) and obj.engine is eng and getattr(eng, "_resident_serial", None) == obj.serial
+    return isinstance(obj, _Resident) and obj.engine is eng and obj.serial >= 0 and eng.pyramid_serial == obj.serial
 
 
 def computeDifferenceOfGaussians(scale_space, chunk_size=32, engine: Engine | None = None, post_message=None):
@@ -127,7 +123,10 @@ def _ensure_dog_resident(difference_of_gaussians, eng: Engine, scales_per_octave
     for o, octave in enumerate(difference_of_gaussians):
         for s, lvl in enumerate(octave):
             eng.set_level(L.SIFT_LEVEL_DOG, o, s, lvl["image"])
-    eng._resident_serial = None
+    if isinstance(difference_of_gaussians, _Resident):
+        # adopted: the device now holds exactly these levels (fp32, as they were read back)
+        difference_of_gaussians.engine, difference_of_gaussians.params = eng, prm
+        difference_of_gaussians.serial = eng.pyramid_serial
     return prm
 
 

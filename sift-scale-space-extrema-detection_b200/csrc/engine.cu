@@ -96,6 +96,7 @@ struct sift_ctx {
   size_t h_cand_cap = 0;
 
   bool pyramid_built = false;
+  uint64_t pyramid_serial = 0;          // bumped whenever the pyramid the stage API reads is rebuilt, replaced or invalidated
   int keep_gauss = 1;
   Counters last;
 };
@@ -283,6 +284,7 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p, const 
   }
   ctx->plan_valid = false;
   ctx->pyramid_built = false;
+  ctx->pyramid_serial++;
   const int spo = p->scalesPerOctave, nlev = spo + 3, n_oct = p->numberOfOctaves;
   (void)spo;
 
@@ -504,6 +506,7 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
 // Gaussian scale space + DoG + seeds for every octave, from an image already on the device.
 static int run_pyramid(sift_ctx *ctx, const void *d_image, int dtype, size_t pitch_bytes)
 {
+  ctx->pyramid_serial++;
   for (int o = 0; o < ctx->n_oct; o++) run_octave(ctx, o, d_image, dtype, pitch_bytes);
   CK(cudaGetLastError());
   ctx->pyramid_built = true;
@@ -847,6 +850,7 @@ SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
 
 SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->main_stream : nullptr; }
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx) { return ctx ? ctx->launches : 0; }
+SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx) { return ctx ? ctx->pyramid_serial : 0; }
 
 SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled)
 {
@@ -901,7 +905,13 @@ SIFT_API int sift_detect(sift_ctx *ctx, const void *image, int dtype, int width,
   return SIFT_OK;
 }
 
-__global__ void copy_count_kernel(const Counters *c, int *dst) { *dst = c->n_kp; }
+// *dst = number of keypoints, or -(capacity that would have been enough) when the candidate list or the output
+// overflowed: which records were dropped then depends on the append order, so the caller must not use them.
+__global__ void copy_count_kernel(const Counters *c, int cand_cap, int cap, int *dst)
+{
+  const bool overflow = c->n_cand > cand_cap || c->n_kp > cap;
+  *dst = overflow ? -max(c->n_cand, c->n_kp) : c->n_kp;
+}
 
 SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, int width, int height,
                                 size_t pitch_bytes, const sift_params *params, sift_keypoint *d_out, int cap,
@@ -928,7 +938,7 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
   if (!ordered) {
     if (!rc) rc = run_refine(ctx, -1, d_out, cap);
     if (!rc) {
-      copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), d_count);
+      copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), ln->cand_cap, cap, d_count);
       ctx->launches += 1;
       if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "copy_count launch failed");
     }
@@ -940,7 +950,9 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
     if (!rc) rc = run_refine(ctx, -1, dev_keypoints(ctx), n_sort);
     if (!rc) {
       ctx->launches += launch_order_keypoints(ln->stream, dev_keypoints(ctx), dev_counters(ctx), n_sort, ln->order.p, ln->order.cap,
-                                              d_out, cap, d_count);
+                                              d_out, cap, nullptr);
+      copy_count_kernel<<<1, 1, 0, ln->stream>>>(dev_counters(ctx), ln->cand_cap, n_sort, d_count);
+      ctx->launches += 1;
       if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, SIFT_ERR_CUDA, "ordering launch failed");
     }
   }
@@ -1334,6 +1346,7 @@ SIFT_API int sift_set_pyramid_shape(sift_ctx *ctx, int width0, int height0, cons
   int rc;
   if ((rc = ensure_plan0(ctx, width0 / 2, height0 / 2, params))) return rc;
   ctx->pyramid_built = true;
+  ctx->pyramid_serial++;
   return SIFT_OK;
 }
 
@@ -1348,6 +1361,7 @@ SIFT_API int sift_set_level(sift_ctx *ctx, int kind, int octave, int level, cons
   CK(cudaMemcpy2DAsync(p, (size_t)od.pitch * 4, src, (size_t)od.w * 4, (size_t)od.w * 4, od.h,
                        cudaMemcpyHostToDevice, ctx->L->stream));
   CK(cudaStreamSynchronize(ctx->L->stream));
+  ctx->pyramid_serial++;
   return SIFT_OK;
 }
 
@@ -1377,6 +1391,7 @@ SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const si
   ctx->strip_dtype = dtype; ctx->strip_pitch = dpitch;
   ctx->strip_next_octave = 0;
   ctx->pyramid_built = false;
+  ctx->pyramid_serial++;
   CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
@@ -1509,6 +1524,10 @@ SIFT_API int sift_strip_resume(sift_ctx *ctx, const sift_walk *walks, int n, sif
   ctx->escaped.clear();
   if (n > 0) {
     if ((rc = grow(ctx, ctx->L->walks, 2 * (size_t)WALK_CAP * sizeof(sift_walk)))) return rc;
+    if (n > ctx->L->kp_cap) {                                  // every walk may end as a record
+      if ((rc = grow(ctx, ctx->L->outbuf, sizeof(Counters) + (size_t)n * sizeof(sift_keypoint)))) return rc;
+      ctx->L->kp_cap = n;
+    }
     sift_walk *d_in = (sift_walk *)ctx->L->walks.p + WALK_CAP;
     CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ctx->L->stream));
     CK(cudaMemcpyAsync(d_in, walks, (size_t)n * sizeof(sift_walk), cudaMemcpyHostToDevice, ctx->L->stream));
@@ -1519,7 +1538,7 @@ SIFT_API int sift_strip_resume(sift_ctx *ctx, const sift_walk *walks, int n, sif
     if ((rc = download_keypoints(ctx, &c, &kps))) return rc;
     if ((rc = fetch_escaped(ctx, c))) return rc;
     *n_out = c.n_kp;
-    sort_keypoints_into(ctx, kps, c.n_kp, out, cap);
+    sort_keypoints_into(ctx, kps, std::min(c.n_kp, ctx->L->kp_cap), out, cap);
   }
   fill_stats(stats, c, 0, 0.f, (int)(ctx->launches - l0));
   if (c.n_kp > cap) return fail(ctx, SIFT_ERR_CAPACITY, "%d keypoints, capacity %d", c.n_kp, cap);
@@ -1536,6 +1555,7 @@ SIFT_API int sift_blur_chunk(sift_ctx *ctx, const double *input, int rows, int c
   if (!(sigma > 0) || !std::isfinite(sigma)) return fail(ctx, SIFT_ERR_BAD_ARGS, "sigma %g", sigma);
   if (x1 >= x2 || y1 >= y2) return SIFT_OK;                      // empty chunk: the loops do not run (sift.js:96-99)
   CK(cudaSetDevice(ctx->device));
+  if (!(3 * sigma <= 4096.0)) return fail(ctx, SIFT_ERR_UNSUPPORTED, "kernel radius round(3 * %g) too large (max 4096)", sigma);
   const int R = (int)js_round(3 * sigma);                        // sift.js:38
   std::vector<double> w((size_t)2 * R + 1);
   gaussian_taps(sigma, R, w.data());
@@ -1679,10 +1699,20 @@ SIFT_API int sift_gradient_hessian(sift_ctx *ctx, const double *dm, const double
 
 SIFT_API int sift_resize_dims(int rows, int cols, double rate, int *out_rows, int *out_cols)
 {
-  if (rows < 0 || cols < 0 || !(rate > 0) || !out_rows || !out_cols) return SIFT_ERR_BAD_ARGS;
+  if (rows < 0 || cols < 0 || !(rate > 0) || !std::isfinite(rate) || !out_rows || !out_cols) return SIFT_ERR_BAD_ARGS;
+  // matrix2d.js:119,124 count `for (i = 0; i < rows; i += rate)`.  For a power-of-two rate every partial sum is
+  // exact, so the count is ceil(rows / rate) in closed form; other rates follow the reference's accumulation,
+  // bounded so that a tiny rate cannot spin (or overflow int) here.
+  if ((double)std::max(rows, cols) / rate > (double)(1 << 30)) return SIFT_ERR_UNSUPPORTED;
+  int e;
+  if (std::frexp(rate, &e) == 0.5) {
+    *out_rows = (int)std::ceil((double)rows / rate);
+    *out_cols = (int)std::ceil((double)cols / rate);
+    return SIFT_OK;
+  }
   int r = 0, c = 0;
-  for (double i = 0; i < rows; i += rate) r++;                    // matrix2d.js:119
-  for (double j = 0; j < cols; j += rate) c++;                    // matrix2d.js:124
+  for (double i = 0; i < rows; i += rate) r++;
+  for (double j = 0; j < cols; j += rate) c++;
   *out_rows = r; *out_cols = c;
   return SIFT_OK;
 }
@@ -1696,7 +1726,7 @@ SIFT_API int sift_linear_resize(sift_ctx *ctx, const double *input, int rows, in
   if (mant != 0.5) return fail(ctx, SIFT_ERR_UNSUPPORTED, "sampling rate %g is not a power of two", rate);
   CK(cudaSetDevice(ctx->device));
   int orows, ocols;
-  sift_resize_dims(rows, cols, rate, &orows, &ocols);
+  if (sift_resize_dims(rows, cols, rate, &orows, &ocols) != SIFT_OK) return fail(ctx, SIFT_ERR_UNSUPPORTED, "sampling rate %g too small", rate);
   int rc;
   const size_t nin = (size_t)rows * cols * 8, nout = (size_t)orows * ocols * 8;
   if ((rc = grow(ctx, ctx->misc[0], nin)) || (rc = grow(ctx, ctx->misc[1], nout))) return rc;

@@ -78,6 +78,11 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.sift_kernel_launches(self._h))
 
+    @property
+    def pyramid_serial(self) -> int:
+        """Generation of the pyramid the stage calls read; changes whenever any call rebuilds or invalidates it."""
+        return int(self._lib.sift_pyramid_serial(self._h))
+
     def synchronize(self):
         self._check(self._lib.sift_synchronize(self._h))
 
@@ -117,8 +122,8 @@ class Engine:
             st = L.Stats()
             rc = self._lib.sift_detect(self._h, a.ctypes.data, dt, w, h, 0, C.byref(prm), out.ctypes.data, cap,
                                        C.byref(n), C.byref(st))
-            if rc == L.SIFT_ERR_CAPACITY and capacity is None:
-                cap = n.value
+            if rc == L.SIFT_ERR_CAPACITY and capacity is None and n.value > cap:
+                cap = n.value            # the required count; any other capacity failure raises below
                 continue
             self._check(rc)
             return out[:n.value], st.as_dict()
@@ -268,7 +273,7 @@ class Engine:
                                                 low.ctypes.data if want_low_contrast else None,
                                                 cap if want_low_contrast else 0,
                                                 C.byref(nl) if want_low_contrast else None)
-            if rc == L.SIFT_ERR_CAPACITY and capacity is None:
+            if rc == L.SIFT_ERR_CAPACITY and capacity is None and max(n.value, nl.value) > cap:
                 cap = max(n.value, nl.value)
                 continue
             self._check(rc)

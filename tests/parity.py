@@ -15,6 +15,7 @@ import numpy as np
 LEVEL_RTOL = 1e-5
 DOG_FLOOR = 0.012
 POS_TOL = 1e-3
+NEAR_TOL = 1e-5      # north_star: a mismatch must lie within 1e-5 (relative) of a threshold, or be an exact tie
 
 
 def check_levels(eng, ora, L):
@@ -43,41 +44,65 @@ def _cand_key(c):
     return (int(c["octave"]), int(c["scale"] if "scale" in c else c["scaleLevel"]), int(c["y"]), int(c["x"]))
 
 
-def check_candidates(cands, ora, near_tol=1e-5, pix_thr=0.012):
-    """cands: structured CANDIDATE_DTYPE in reference order. Mismatches must sit on the pre-filter threshold
-    or be float32 ties of the 26-neighbourhood."""
+def _explain_candidate(key, ora, pix_thr, near_tol):
+    """Why may an extremum be on one list and not the other?  Only because abs(value) sits on the pre-filter
+    threshold (sift.js:293) or because two of its 27 voxels are closer than float32 storage can tell apart
+    (sift.js:261,266 ties).  Returns the reason or None."""
+    o, s, y, x = key
+    v = ora.dog[o][s][y, x]
+    if abs(abs(v) - pix_thr) <= near_tol * pix_thr:
+        return "threshold"
+    nb = np.stack([ora.dog[o][s + d][y - 1:y + 2, x - 1:x + 2] for d in (-1, 0, 1)]).ravel()
+    nb = np.delete(nb, 13)
+    if np.min(np.abs(nb - v)) <= max(abs(v), DOG_FLOOR) * 1e-6:       # closer than float32 can tell apart
+        return "tie"
+    return None
+
+
+def check_candidates(cands, ora, near_tol=NEAR_TOL, pix_thr=0.012, low=False):
+    """cands: structured CANDIDATE_DTYPE in reference order, compared with the oracle's candidate list (or, with
+    low=True, its low-contrast list).  Every mismatch must be explained by _explain_candidate."""
     got = [(int(c["octave"]), int(c["scaleLevel"]), int(c["y"]), int(c["x"])) for c in cands]
-    want = [_cand_key(c) for c in ora.candidates]
+    want = [_cand_key(c) for c in (ora.low_contrast if low else ora.candidates)]
     assert got == sorted(got), "candidates not in reference order"
     sg, sw = set(got), set(want)
-    bad = []
-    for k in sg ^ sw:
-        o, s, y, x = k
-        v = ora.dog[o][s][y, x]
-        near_thr = abs(abs(v) - pix_thr) <= near_tol * pix_thr * 10
-        nb = np.stack([ora.dog[o][s + d][y - 1:y + 2, x - 1:x + 2] for d in (-1, 0, 1)]).ravel()
-        nb = np.delete(nb, 13)
-        tie = np.min(np.abs(nb - v)) <= max(abs(v), DOG_FLOOR) * 1e-6   # closer than float32 can tell apart
-        if not (near_thr or tie):
-            bad.append((k, v))
+    assert len(sg) == len(got), "duplicate candidates"
+    bad = [(k, float(ora.dog[k[0]][k[1]][k[2], k[3]])) for k in sg ^ sw
+           if _explain_candidate(k, ora, pix_thr, near_tol) is None]
     assert not bad, f"unexplained candidate mismatches: {bad[:5]}"
+    # values are the float32 DoG samples themselves
+    by_key = {_cand_key(c): c["value"] for c in (ora.low_contrast if low else ora.candidates)}
+    for c, k in zip(cands, got):
+        if k in by_key:
+            assert abs(float(c["value"]) - by_key[k]) <= LEVEL_RTOL * max(abs(by_key[k]), DOG_FLOOR)
     return len(sg & sw), len(sg ^ sw)
 
 
-def check_keypoints(kps, ora, min_match=0.995):
+def _kp_key(k):
+    return (int(k["octave"]), int(k["candScale"]), int(k["candY"]), int(k["candX"]))
+
+
+def check_keypoints(kps, ora, min_match=0.995, near_tol=NEAR_TOL, pix_thr=0.012):
+    """>= 99.5 % of the keypoints on the same cell within 1e-3 px -- and EVERY record that is not matched must be
+    explained: its candidate sits on the pre-filter threshold / a tie (so the candidate lists differ), or the
+    oracle's refinement walk of that candidate came within near_tol of flipping a decision
+    (oracle_refine_margin: offset bound 0.6, contrast 0.015, edge 12.1, Math.round boundary)."""
     want = {}
     for k in ora.keypoints:
         want.setdefault((k["octave"], k["candScale"], k["candY"], k["candX"]), k)
     got = {}
     for k in kps:
-        got.setdefault((int(k["octave"]), int(k["candScale"]), int(k["candY"]), int(k["candX"])), k)
-    keys_got = [(int(k["octave"]), int(k["candScale"]), int(k["candY"]), int(k["candX"])) for k in kps]
+        got.setdefault(_kp_key(k), k)
+    keys_got = [_kp_key(k) for k in kps]
     assert keys_got == sorted(keys_got), "keypoints not in reference (candidate) order"
+    assert len(want) == len(ora.keypoints) and len(got) == len(kps), "two records from one candidate"
     matched = 0
     worst = 0.0
+    unmatched = []
     for key, w in want.items():
         g = got.get(key)
         if g is None:
+            unmatched.append(key)
             continue
         same_cell = (int(g["scaleLevel"]) == w["scaleLevel"] and int(g["localX"]) == w["localX"]
                      and int(g["localY"]) == w["localY"])
@@ -88,6 +113,20 @@ def check_keypoints(kps, ora, min_match=0.995):
             worst = max(worst, dx, dy)
             assert abs(float(g["absoluteSigma"]) - w["absoluteSigma"]) <= 1e-3 * w["absoluteSigma"]
             assert abs(float(g["interpolatedValue"]) - w["interpolatedValue"]) <= 1e-5 * max(abs(w["interpolatedValue"]), DOG_FLOOR)
+        else:
+            unmatched.append(key)
+    unmatched += [k for k in got if k not in want]
+    unexplained = []
+    for key in unmatched:
+        o, s, y, x = key
+        margin = ora.margins.get(key)
+        if margin is None:
+            # the oracle never refined this candidate: the candidate lists differ -> must be a threshold / tie case
+            if ora.dog and _explain_candidate(key, ora, pix_thr, near_tol) is None:
+                unexplained.append((key, "candidate only on the device"))
+        elif not (margin <= near_tol):
+            unexplained.append((key, f"walk margin {margin:.3g}"))
+    assert not unexplained, f"unexplained keypoint mismatches: {unexplained[:5]}"
     total = max(len(want), len(got), 1)
     frac = matched / total
     assert frac >= min_match, f"only {matched}/{total} keypoints matched ({frac:.4f})"

@@ -32,6 +32,8 @@ class FakeAddon:
         self.g = g
         self.n_oct, self.nlev = int(g["n_octaves"]), int(g["n_levels"])
         self.calls = []
+        self.serial = 0                    # sift_pyramid_serial: every build / detect / setLevel bumps it
+        self.uploaded = {}                 # (kind, o, s) -> plane set through setLevel
 
     # -- context / fused
     def create(self, device=0):
@@ -49,6 +51,7 @@ class FakeAddon:
 
     def detect(self, ctx, data, w, h, dtype, prm):
         self.calls.append(("detect", w, h, dtype, prm["numberOfOctaves"], prm["minBlurLevel"]))
+        self.serial += 1
         k = self.g["keypoints"]
         return J(records=self._records(k), count=len(k), stats=J(keypoints=len(k), candidates=len(self.g["candidates"])))
 
@@ -67,6 +70,19 @@ class FakeAddon:
         assert (prm["numberOfOctaves"], prm["scalesPerOctave"], prm["minBlurLevel"], prm["assumedBlur"]) == tuple(self.g["params"])
         assert prm["contrastThreshold"] == 0.015 and prm["edgeRatio"] == 10 and prm["maxIterations"] == 5
         self.calls.append("buildScaleSpace")
+        self.serial += 1
+
+    def pyramidSerial(self, ctx):
+        return self.serial
+
+    def setPyramidShape(self, ctx, w0, h0, prm):
+        self.calls.append(("setPyramidShape", int(w0), int(h0), int(prm["numberOfOctaves"]), int(prm["scalesPerOctave"])))
+        self.serial += 1
+
+    def setLevel(self, ctx, kind, o, s, data):
+        assert isinstance(data, H.Float32Array)
+        self.uploaded[(int(kind), int(o), int(s))] = data.a.copy()
+        self.serial += 1
 
     def pyramidInfo(self, ctx):
         return J(octaves=self.n_oct, levels=self.nlev)
@@ -125,6 +141,42 @@ class FakeAddon:
         trio = [d.a.reshape(rows, cols) for d in (dm, dc, dp)]
         g, h = oracle.gradient(trio, 1, int(m), int(n)), oracle.hessian(trio, 1, int(m), int(n))
         return H.Float64Array.of_numpy(np.concatenate([g, h.ravel()]))
+
+
+def test_stage_requests_are_consumed_not_the_contexts_last_pyramid(golden):
+    """the reference consumes the pyramid IN each request (background.js:258, 359, 455).  The glue may
+    skip the upload only for the reply it produced itself while nothing rebuilt the context's pyramid; after an
+    intervening detect() of another image the scale space is re-subtracted from the payload and the DoG uploaded."""
+    fake = FakeAddon(golden)
+    interp, _ = H.make_interpreter(ADDON, fake)
+    bg = interp.load_module("background.js")
+    n_oct, spo, min_blur, assumed = (float(v) for v in golden["params"])
+    req = J(inputImage=[list(map(float, r)) for r in golden["input_matrix"]], numberOfOctaves=n_oct, scalesPerOctave=spo,
+            minBlurLevel=min_blur, assumedBlur=assumed, chunkSize=32.0)
+    ss = bg["computeGaussianScaleSpace"](req)
+    dog = bg["computeDifferenceOfGaussians"](ss)                      # resident: read back, no subtraction call
+    bg["findCandidateKeypoints"](J(differenceOfGaussians=dog, scalesPerOctave=spo))
+    assert not fake.uploaded and not any(isinstance(c, tuple) and c[0] == "setPyramidShape" for c in fake.calls)
+    # another image goes through the context
+    bg["detect"](J(data=H.Uint8Array(16 * 12), width=16.0, height=12.0), J(numberOfOctaves=2.0))
+    dog2 = bg["computeDifferenceOfGaussians"](ss)                     # recomputed from the payload, pair by pair
+    for o in range(fake.n_oct):
+        for s in range(fake.nlev - 1):
+            want = golden["gauss_%d_%d" % (o, s)].astype(np.float32).astype(np.float64) - \
+                golden["gauss_%d_%d" % (o, s + 1)].astype(np.float32).astype(np.float64)
+            assert np.array_equal(np.array(dog2[o][s]["image"]), want)
+            assert dog2[o][s]["blurLevel"] == ss[o][s]["blurLevel"]
+    bg["findCandidateKeypoints"](J(differenceOfGaussians=dog, scalesPerOctave=spo))     # uploaded: all DoG levels
+    shape = [c for c in fake.calls if isinstance(c, tuple) and c[0] == "setPyramidShape"]
+    h0, w0 = golden["dog_0_0"].shape
+    assert shape == [("setPyramidShape", w0, h0, fake.n_oct, int(spo))]
+    assert set(fake.uploaded) == {(1, o, s) for o in range(fake.n_oct) for s in range(fake.nlev - 1)}
+    assert np.array_equal(fake.uploaded[(1, 0, 1)], golden["dog_0_1"].astype(np.float32).ravel())
+    n_up = len(fake.uploaded); fake.uploaded.clear()
+    bg["refineCandidateKeypoints"](J(differenceOfGaussians=dog, scalesPerOctave=spo, numberOfOctaves=n_oct,
+                                     candidateKeypoints=bg["findCandidateKeypoints"](J(differenceOfGaussians=dog, scalesPerOctave=spo)),
+                                     minBlurLevel=min_blur))
+    assert not fake.uploaded and n_up > 0                            # the uploaded pyramid is now the resident one
 
 
 @pytest.fixture()

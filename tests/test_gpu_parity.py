@@ -67,7 +67,7 @@ def test_other_scales_per_octave(engine, spo):
     thr = 0.8 * 0.015 * (2 ** (1 / spo) - 1) / (2 ** (1 / 3) - 1)
     check_candidates(cands, ora, pix_thr=thr)
     kps, stats = engine.detect(u8, prm)
-    check_keypoints(kps, ora)
+    check_keypoints(kps, ora, pix_thr=thr)
     assert stats["candidates"] == len(cands) and len(ora.candidates) > 10
 
 
@@ -277,12 +277,70 @@ def test_device_resident_ordered_output(engine):
             assert k == len(want) and k > 40
             assert got[:k].tobytes() == want.tobytes()
         else:
-            # truncated: count reports what was found (>= cap); the cap records written are valid keypoints in order
-            assert k >= cap
+            # overflow is reported on the device, never silently truncated: the count is -(capacity that would have
+            # sufficed); the cap records that were written are still genuine keypoints, in order
+            assert k < 0 and -k >= len(want)
             keys = [(int(r["octave"]), int(r["candScale"]), int(r["candY"]), int(r["candX"])) for r in got[:cap]]
             assert keys == sorted(keys)
             wk = {(int(r["octave"]), int(r["candScale"]), int(r["candY"]), int(r["candX"])) for r in want}
             assert set(keys) <= wk
+
+
+def test_device_resident_overflow_is_reported_on_the_device(engine):
+    """sift_detect_device must not truncate silently.  A `cap` smaller than the number of keypoints (or a
+    candidate list larger than the lane's buffer) sets *d_count to -(capacity that would have sufficed)."""
+    import torch
+    w, h = 320, 240
+    prm = L.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    u8 = fixtures.synthetic_u8(w, h, 61, blobs=300)
+    want, st = engine.detect(u8, prm)
+    d = torch.from_numpy(u8).cuda()
+    rec = L.KEYPOINT_DTYPE.itemsize
+    for ordered in (False, True):
+        for cap in (len(want), len(want) - 1, 5):
+            out = torch.zeros(max(cap, 1) * rec, dtype=torch.uint8, device="cuda")
+            cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            engine.detect_device(d.data_ptr(), L.SIFT_U8, w, h, 0, prm, out.data_ptr(), cap, cnt.data_ptr(), ordered=ordered)
+            engine.synchronize()
+            k = int(cnt.item())
+            if cap >= len(want):
+                assert k == len(want)
+            else:
+                assert k == -max(st["candidates"], len(want))
+
+
+def test_stage_replies_follow_the_pyramid_generation(engine):
+    """`ss = computeGaussianScaleSpace(A); detect(B); computeDifferenceOfGaussians(ss)` must give A's DoG.
+    The reply remembers sift_pyramid_serial(); any call that rebuilds the context's pyramid changes it, and the next
+    stage then works from the payload (background.js:258, 359, 455 consume the request) instead of the device."""
+    from sift_b200 import background as bg
+    a = fixtures.synthetic_u8(96, 80, 5)
+    b = fixtures.synthetic_u8(96, 80, 6)
+    s0 = engine.pyramid_serial
+    ss = bg.computeGaussianScaleSpace(a, 3, 3, 1.6, 0.5, engine=engine)
+    assert engine.pyramid_serial != s0 and ss.serial == engine.pyramid_serial
+    dog_direct = bg.computeDifferenceOfGaussians(ss, engine=engine)
+    cands_direct = bg.findCandidateKeypoints(dog_direct, None, 3, engine=engine)
+    kp_direct = bg.refineCandidateKeypoints(dog_direct, 3, 3, cands_direct, 1.6, engine=engine)
+    # another image through the same engine, by three different doors
+    for other in (lambda: engine.detect(b, L.default_params(numberOfOctaves=3, minBlurLevel=1.6)),
+                  lambda: engine.detect_batch(np.stack([b, b]), L.default_params(numberOfOctaves=3, minBlurLevel=1.6)),
+                  lambda: bg.computeGaussianScaleSpace(b, 3, 3, 1.6, 0.5, engine=engine)):
+        before = engine.pyramid_serial
+        other()
+        assert engine.pyramid_serial != before
+        dog = bg.computeDifferenceOfGaussians(ss, engine=engine)          # from the payload: fp32 levels subtracted
+        for o in range(3):
+            for s in range(5):
+                want = ss[o][s]["image"].astype(np.float64) - ss[o][s + 1]["image"].astype(np.float64)
+                assert np.array_equal(np.asarray(dog[o][s]["image"], dtype=np.float64), want)
+        other()
+        cands = bg.findCandidateKeypoints(dog_direct, None, 3, engine=engine)   # A's DoG is uploaded again
+        assert cands == cands_direct
+        other()
+        kps = bg.refineCandidateKeypoints(dog_direct, 3, 3, cands_direct, 1.6, engine=engine)
+        assert kps == kp_direct and len(kps) > 10
 
 
 def test_batch_overflow_falls_back_and_stays_correct(engine):

@@ -23,7 +23,7 @@ def _run(*args):
 def test_addon_registers_and_reports_its_version():
     r = _run("version")
     assert r.returncode == 0, r.stderr
-    assert "exports 17" in r.stdout and "version sift_b200" in r.stdout
+    assert "exports 18" in r.stdout and "version sift_b200" in r.stdout
 
 
 def test_addon_create_throws_without_a_gpu():

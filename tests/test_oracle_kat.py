@@ -250,6 +250,40 @@ def test_separable_oracle_equals_dense_oracle():
     assert [key(k) for k in a.keypoints] == [key(k) for k in b.keypoints]
 
 
+def test_separable_oracle_equals_dense_oracle_128x96():
+    """before the separable variant stands in for the dense kernel at 1080p / 4K, it must equal it
+    to ~1e-14 on a case both can run -- levels, DoG, the candidate and low-contrast lists, and the keypoints."""
+    img = fixtures.to_float(fixtures.synthetic_u8(128, 96, 1234))
+    a = oracle.detect(img, numberOfOctaves=3, minBlurLevel=1.6, separable=False)
+    b = oracle.detect(img, numberOfOctaves=3, minBlurLevel=1.6, separable=True)
+    for o in range(3):
+        for s in range(6):
+            assert np.abs(a.gauss[o][s] - b.gauss[o][s]).max() < 1e-14
+        for s in range(5):
+            assert np.abs(a.dog[o][s] - b.dog[o][s]).max() < 1e-14
+    ck = lambda c: (c["octave"], c["scale"], c["y"], c["x"])
+    assert [ck(c) for c in a.candidates] == [ck(c) for c in b.candidates] and len(a.candidates) > 50
+    assert [ck(c) for c in a.low_contrast] == [ck(c) for c in b.low_contrast] and a.n_low_contrast == len(a.low_contrast) > 20
+    key = lambda k: (k["octave"], k["candScale"], k["candY"], k["candX"], k["scaleLevel"], k["localX"], k["localY"])
+    assert [key(k) for k in a.keypoints] == [key(k) for k in b.keypoints]
+    for ka, kb in zip(a.keypoints, b.keypoints):
+        assert abs(ka["absoluteX"] - kb["absoluteX"]) < 1e-9 and abs(ka["absoluteY"] - kb["absoluteY"]) < 1e-9
+
+
+def test_refine_margin_diagnostic():
+    """oracle_refine_margin (test diagnostic used by tests/parity.py): zero-ish only for walks that sit on a decision."""
+    img = fixtures.to_float(fixtures.synthetic_u8(128, 96, 1234))
+    r = oracle.detect(img, numberOfOctaves=3, minBlurLevel=1.6, separable=True)
+    assert set(r.margins) == {(c["octave"], c["scale"], c["y"], c["x"]) for c in r.candidates}
+    assert all(m >= 0 for m in r.margins.values()) and min(r.margins.values()) > 1e-7
+    # moving the contrast threshold onto a keypoint's interpolated value puts its margin at ~0
+    k = r.keypoints[0]
+    c = abs(k["interpolatedValue"])
+    r2 = oracle.detect(img, numberOfOctaves=3, minBlurLevel=1.6, separable=True, contrastThreshold=c * (1 + 1e-9),
+                       preFilterFactor=0.8 * 0.015 / c)
+    assert r2.margins[(k["octave"], k["candScale"], k["candY"], k["candX"])] < 1e-8
+
+
 def test_refine_uses_original_value_and_keeps_duplicates():
     """Q5 (background.js:565): omega = extrema.value + 0.5 alpha.g with the ORIGINAL candidate value."""
     img = fixtures.to_float(fixtures.synthetic_u8(96, 80, 42))
