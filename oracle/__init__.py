@@ -256,6 +256,25 @@ def _kp_dict(k: Keypoint) -> dict:
             "iterations": k.iterations}
 
 
+def refine_on_dog(dog_levels, octave: int, candidate: dict, params: Params | None = None, **kw):
+    """oracle_refine_one (background.js:455-685) on caller-supplied DoG levels of one octave (float64 arrays, all the
+    same shape) -- e.g. the float32 levels a device stores, to tell its arithmetic from its storage precision.
+    Returns (outcome name, keypoint dict or None)."""
+    prm = params if params is not None else default_params(**kw)
+    keep = [_img(d) for d in dog_levels]
+    pyr = Pyramid()
+    pyr.octaves, pyr.levels, pyr.spo = octave + 1, len(keep) + 1, prm.scalesPerOctave
+    pyr.rows[octave], pyr.cols[octave] = keep[0].shape
+    for s, k in enumerate(keep):
+        pyr.dog[octave][s] = _dp(k)
+    c = Candidate(octave, int(candidate["scale"] if "scale" in candidate else candidate["scaleLevel"]),
+                  int(candidate["x"]), int(candidate["y"]), float(candidate["value"]))
+    kp = Keypoint()
+    rc = lib().oracle_refine_one(C.byref(pyr), C.byref(c), prm.contrastThreshold, prm.edgeRatio, prm.maxIterations,
+                                 prm.offsetBound, prm.minBlurLevel, prm.minInterpixelDistance, C.byref(kp))
+    return OUTCOMES[rc], (_kp_dict(kp) if rc == 0 else None)
+
+
 class Result:
     """Everything the four stages produce for one image.  The level arrays are views of the C pyramid, which is
     released with the Result (close() / garbage collection)."""

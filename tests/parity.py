@@ -82,11 +82,17 @@ def _kp_key(k):
     return (int(k["octave"]), int(k["candScale"]), int(k["candY"]), int(k["candX"]))
 
 
-def check_keypoints(kps, ora, min_match=0.995, near_tol=NEAR_TOL, pix_thr=0.012):
+def check_keypoints(kps, ora, min_match=0.995, near_tol=NEAR_TOL, pix_thr=0.012, device_dog=None, params=None):
     """>= 99.5 % of the keypoints on the same cell within 1e-3 px -- and EVERY record that is not matched must be
-    explained: its candidate sits on the pre-filter threshold / a tie (so the candidate lists differ), or the
-    oracle's refinement walk of that candidate came within near_tol of flipping a decision
-    (oracle_refine_margin: offset bound 0.6, contrast 0.015, edge 12.1, Math.round boundary)."""
+    explained, by one of:
+      threshold  its candidate sits on the pre-filter threshold / a tie (so the candidate lists differ), or the
+                 oracle's refinement walk of that candidate came within near_tol (1e-5) of flipping a decision
+                 (oracle_refine_margin: offset bound 0.6, contrast 0.015, edge 12.1, Math.round boundary);
+      storage    the quadratic fit at that sample is so ill-conditioned that rounding the DoG levels to the float32
+                 the device stores (6e-8 relative, 170x inside the 1e-5 level tolerance) moves the walk: shown by
+                 running the ORACLE's float64 refinement (background.js:455-685) on the device's own stored DoG
+                 levels (`device_dog(octave) -> levels`) and getting exactly the device's record / rejection.
+    Returns (matched, total, worst position error); the explanation counts are attached as check_keypoints.last."""
     want = {}
     for k in ora.keypoints:
         want.setdefault((k["octave"], k["candScale"], k["candY"], k["candX"]), k)
@@ -117,6 +123,9 @@ def check_keypoints(kps, ora, min_match=0.995, near_tol=NEAR_TOL, pix_thr=0.012)
             unmatched.append(key)
     unmatched += [k for k in got if k not in want]
     unexplained = []
+    reasons = {"threshold": 0, "storage": 0}
+    dog_cache = {}
+    import oracle as _oracle
     for key in unmatched:
         o, s, y, x = key
         margin = ora.margins.get(key)
@@ -124,8 +133,31 @@ def check_keypoints(kps, ora, min_match=0.995, near_tol=NEAR_TOL, pix_thr=0.012)
             # the oracle never refined this candidate: the candidate lists differ -> must be a threshold / tie case
             if ora.dog and _explain_candidate(key, ora, pix_thr, near_tol) is None:
                 unexplained.append((key, "candidate only on the device"))
-        elif not (margin <= near_tol):
-            unexplained.append((key, f"walk margin {margin:.3g}"))
+            else:
+                reasons["threshold"] += 1
+        elif margin <= near_tol:
+            reasons["threshold"] += 1
+        else:
+            why = f"walk margin {margin:.3g}"
+            if device_dog is not None:
+                if o not in dog_cache:
+                    dog_cache[o] = [np.asarray(d, dtype=np.float64) for d in device_dog(o)]
+                g = got.get(key)
+                cand = {"scale": s, "x": x, "y": y, "value": float(dog_cache[o][s][y, x])}
+                outcome, rec = _oracle.refine_on_dog(dog_cache[o], o, cand, params)
+                if g is None:
+                    same = outcome != "accepted"
+                else:
+                    same = (rec is not None and rec["scaleLevel"] == int(g["scaleLevel"]) and rec["localX"] == int(g["localX"])
+                            and rec["localY"] == int(g["localY"])
+                            and abs(rec["absoluteX"] - float(g["absoluteX"])) <= 1e-9 * max(1.0, abs(rec["absoluteX"]))
+                            and abs(rec["absoluteY"] - float(g["absoluteY"])) <= 1e-9 * max(1.0, abs(rec["absoluteY"])))
+                if same:
+                    reasons["storage"] += 1
+                    continue
+                why += f"; oracle refinement of the device's stored levels gives {outcome}, the device {'a record' if g is not None else 'none'}"
+            unexplained.append((key, why))
+    check_keypoints.last = dict(reasons, unmatched=len(unmatched))
     assert not unexplained, f"unexplained keypoint mismatches: {unexplained[:5]}"
     total = max(len(want), len(got), 1)
     frac = matched / total

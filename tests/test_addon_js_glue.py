@@ -403,6 +403,22 @@ class EngineAddon:
         n_oct, nlev = self.e.pyramid_info()
         return J(octaves=n_oct, levels=nlev)
 
+    def pyramidSerial(self, ctx):
+        return self.e.pyramid_serial
+
+    def setPyramidShape(self, ctx, w0, h0, prm):
+        self.prm = self._params(prm)
+        self.e.set_pyramid_shape(int(w0), int(h0), self.prm)
+
+    def setLevel(self, ctx, kind, o, s, data):
+        w, h = self.e.octave_size(int(o))
+        self.e.set_level(int(kind), int(o), int(s), data.a.reshape(h, w))
+
+    def subtractChunk(self, ctx, a, b, rows, cols, dst, x1, y1, x2, y2):
+        out = dst.a.reshape(int(rows), int(cols))
+        self.e.subtract_chunk(np.ascontiguousarray(a.a.reshape(int(rows), int(cols))),
+                              np.ascontiguousarray(b.a.reshape(int(rows), int(cols))), out, int(x1), int(y1), int(x2), int(y2))
+
     def getLevel(self, ctx, kind, o, s):
         m = self.e.get_level(int(kind), int(o), int(s))
         return J(blurLevel=self.e.blur_level(int(kind), int(o), int(s)), width=m.shape[1], height=m.shape[0],

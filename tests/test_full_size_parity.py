@@ -31,9 +31,16 @@ def _full_check(engine, w, h, n_oct, seed, levels=True):
         same_low, diff_low = check_candidates(low, ora, low=True)
         assert same + diff >= len(ora.candidates) and same_low + diff_low >= ora.n_low_contrast
         kps, stats = engine.detect(u8, prm)
-        matched, total, worst_pos = check_keypoints(kps, ora)
+        # (sift_detect leaves its pyramid in the context: the stored DoG levels can be read back for explanations)
+        oprm = oracle.default_params(numberOfOctaves=n_oct, minBlurLevel=1.6)
+        matched, total, worst_pos = check_keypoints(
+            kps, ora, params=oprm,
+            device_dog=lambda o: [engine.get_level(L.SIFT_LEVEL_DOG, o, s) for s in range(5)])
         assert stats["rejSingular"] == 0
-        return {"levels": worst, "cands": (same, diff), "low": (same_low, diff_low), "kps": (matched, total, worst_pos)}
+        r = {"levels": worst, "cands": (same, diff), "low": (same_low, diff_low), "kps": (matched, total, worst_pos),
+             "explained": dict(check_keypoints.last)}
+        print(f"{w}x{h}/{n_oct} oct seed {seed}: {r}")
+        return r
     finally:
         ora.close()
 

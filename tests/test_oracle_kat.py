@@ -284,6 +284,26 @@ def test_refine_margin_diagnostic():
     assert r2.margins[(k["octave"], k["candScale"], k["candY"], k["candX"])] < 1e-8
 
 
+def test_refine_on_supplied_dog_levels():
+    """oracle.refine_on_dog (used by tests/parity.py to tell a device's arithmetic from its float32 level storage):
+    on the oracle's own DoG it reproduces the oracle's records bit for bit; on float32-rounded levels the records
+    stay on the same cells with positions within the storage error."""
+    img = fixtures.to_float(fixtures.synthetic_u8(128, 96, 1234))
+    prm = oracle.default_params(numberOfOctaves=3, minBlurLevel=1.6)
+    r = oracle.detect(img, prm, separable=True)
+    assert len(r.keypoints) > 30
+    for k in r.keypoints:
+        o = k["octave"]
+        cand = {"scale": k["candScale"], "x": k["candX"], "y": k["candY"], "value": k["dogValue"]}
+        out, rec = oracle.refine_on_dog(r.dog[o], o, cand, prm)
+        assert out == "accepted" and rec == k
+        f32 = [d.astype(np.float32).astype(np.float64) for d in r.dog[o]]
+        if r.margins[(o, k["candScale"], k["candY"], k["candX"])] > 1e-3:
+            out32, rec32 = oracle.refine_on_dog(f32, o, dict(cand, value=float(np.float32(k["dogValue"]))), prm)
+            assert out32 == "accepted" and (rec32["localX"], rec32["localY"]) == (k["localX"], k["localY"])
+            assert abs(rec32["absoluteX"] - k["absoluteX"]) < 1e-3
+
+
 def test_refine_uses_original_value_and_keeps_duplicates():
     """Q5 (background.js:565): omega = extrema.value + 0.5 alpha.g with the ORIGINAL candidate value."""
     img = fixtures.to_float(fixtures.synthetic_u8(96, 80, 42))
