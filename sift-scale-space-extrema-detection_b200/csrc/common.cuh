@@ -95,6 +95,14 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
                           const LevelPlan *plans, int poly_woff, int nlev, int spo, int keep_gauss,
                           const double *d_u8lut);
 
+// blur_oct0.cu: octave 0, second generation (column pass first, row pass last; TMA source tile)
+bool oct0_v2_supported(const LevelPlan *plans, int nlev);
+size_t oct0_out_map_bytes(int nlev);
+bool oct0_build_out_maps(const OctaveDev &oct, int nlev, void *h_maps /* oct0_out_map_bytes(nlev) */);
+void launch_oct0_v2(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                    const OctaveDev &oct, const OctaveDev *next, const double *d_weights, const LevelPlan *plans,
+                    int poly_woff, int nlev, int spo, int keep_gauss, const void *d_out_maps);
+
 // scan.cu
 void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
                      double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,

@@ -33,7 +33,8 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, order, walks;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, tmaps_o0, order, walks;
+  bool oct0_maps = false;      // tmaps_o0 holds the TMA-store descriptors of octave 0's planes (blur_oct0.cu)
   bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
   int tma_blur[SIFT_MAX_OCTAVES];   // per octave: maps of its T^T planes start at tmaps_t[tma_blur[o]] (-1: none)
   int cand_cap = 0, kp_cap = 0;
@@ -410,6 +411,20 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
         ln->tma_scan = true;
       }
     }
+    // TMA-store descriptors of octave 0's Gaussian / DoG planes (blur_oct0.cu)
+    ln->oct0_maps = false;
+    if (ctx->fused0 && oct0_v2_supported(ctx->plans[0], nlev)) {
+      std::vector<char> hm(oct0_out_map_bytes(nlev));
+      if (oct0_build_out_maps(ln->octs[0], nlev, hm.data())) {
+        if ((rc = grow(ctx, ln->tmaps_o0, hm.size()))) break;
+        if (cudaMemcpyAsync(ln->tmaps_o0.p, hm.data(), hm.size(), cudaMemcpyHostToDevice, ln->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ln->stream) != cudaSuccess) {
+          rc = fail(ctx, SIFT_ERR_CUDA, "upload of the octave-0 TMA descriptors failed");
+          break;
+        }
+        ln->oct0_maps = true;
+      }
+    }
     // TMA descriptors of the fp64 T^T planes (pass B of octaves >= 1); the planes of every octave alias tbuf
     for (int o = 0; o < SIFT_MAX_OCTAVES; o++) ln->tma_blur[o] = -1;
     if (!ctx->no_tma) {
@@ -468,8 +483,12 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
   if (o == 0 && ctx->fused0) {
     prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
-    launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
-                         ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
+    if (ctx->L->oct0_maps)
+      launch_oct0_v2(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
+                     ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->L->tmaps_o0.p);
+    else
+      launch_fused_octave0(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
+                           ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->d_weights);
     ctx->launches += 1;
     prof_end(ctx);
     return;
@@ -776,7 +795,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.order, &ln.walks };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.tmaps_o0, &ln.order, &ln.walks };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);

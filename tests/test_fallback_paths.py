@@ -32,8 +32,10 @@ for (w, h, n_oct, seed) in ((208, 144, 3, 3), (1200, 900, 2, 8)):     # the seco
     print("OK", w, h, matched, total, st["kernelLaunches"])
 """
 
+# SIFT_B200_OCT0_WS: the persistent warp-specialised octave-0 kernel of blur_oct0.cu (TMA source boxes, TMA stores);
+# "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR": the same kernel with the source tile loaded by plain loads
 KNOBS = ["", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD", "SIFT_B200_NO_TMA", "SIFT_B200_NO_TMA_BLUR",
-         "SIFT_B200_FUSED0_LO", "SIFT_B200_FIR_NO8"]
+         "SIFT_B200_FUSED0_LO", "SIFT_B200_FIR_NO8", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR"]
 
 
 @pytest.mark.gpu
@@ -41,9 +43,11 @@ KNOBS = ["", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD", "SIFT_B200_NO_TMA
 def test_forced_kernel_variant_meets_the_parity_bars(knob):
     env = dict(os.environ)
     for k in KNOBS:
-        env.pop(k, None)
-    if knob:
-        env[knob] = "1"
+        for part in k.split("+"):
+            env.pop(part, None)
+    for part in knob.split("+"):
+        if part:
+            env[part] = "1"
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (knob, r.stdout[-2000:], r.stderr[-3000:])
     assert r.stdout.count("OK ") == 2
