@@ -36,8 +36,10 @@ METRIC = "Mpixel/s full SIFT detect (pyramid+DoG+extrema+refine) at 1/2/4/8 B200
 W, H = 1920, 1080
 N_OCT, SPO, MIN_BLUR, ASSUMED = 4, 3, 1.6, 0.5
 FRAMES = 64                    # frames per GPU per step (distinct seeds)
-# dram bytes of one launch of the dominant kernel (profiles/r01_ncu_fused_octave0_1.txt), ncu --set full
-NCU_TRAFFIC_OCT0_BYTES = 344.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, written by tools/ncu_traffic.py from the
+# `ncu --set full` captures of this round (roofline.traffic is read from this file by kernel name, null if absent)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")
+DOMINANT_KERNEL = "fused_octave0_hi_kernel"
 LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
 CPU_TILE = int(os.environ.get("SIFT_BENCH_CPU_TILE", "256"))   # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
@@ -119,6 +121,188 @@ def make_frames(n: int, first_seed: int):
     return np.stack([fixtures.synthetic_u8(W, H, first_seed + i) for i in range(n)])
 
 
+def ncu_traffic(kernel: str):
+    """(bytes per launch, source) of `kernel` from profiles/dram_traffic.json, or (None, why)."""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+        e = d["kernels"][kernel]
+        return float(e["dram_bytes"]), f"{e['source']} ({d.get('how', 'ncu --set full')})"
+    except Exception as ex:
+        return None, f"no ncu capture on file for {kernel}: {ex}"
+
+
+def bench_frames(eng, L, torch, frames_np, prm, n_frames, steps, warmup, cap, dist=None):
+    """Device-resident and host-to-host throughput of `n_frames` frames per step drawn (cyclically) from frames_np
+    [k, h, w] u8.  Returns a dict; times are max over ranks when dist is given."""
+    k, h, w = frames_np.shape
+    h_frames = torch.from_numpy(frames_np).pin_memory()
+    d_frames = h_frames.cuda()
+    ring = min(n_frames, 64)
+    d_out = torch.zeros(ring, cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(n_frames, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        for f in range(n_frames):
+            eng.detect_device(d_frames[f % k].data_ptr(), L.SIFT_U8, w, h, 0, prm, d_out[f % ring].data_ptr(), cap,
+                              d_cnt[f].data_ptr())
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step_device()
+    eng.flush()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    n_kp = int(d_cnt.clamp(min=0).sum().item())
+    overflow = int((d_cnt < 0).sum().item())
+    # host to host through sift_detect_batch: the k distinct frames repeated to n_frames
+    reps = (n_frames + k - 1) // k
+    h_out = torch.zeros(min(n_frames, k) * cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_offs = torch.zeros(k + 1, dtype=torch.int32)
+
+    def step_e2e():
+        left = n_frames
+        for _ in range(reps):
+            m = min(left, k)
+            eng.detect_batch_raw(h_frames.data_ptr(), L.SIFT_U8, w, h, 0, w * h, m, prm, h_out.data_ptr(), m * cap,
+                                 h_offs.data_ptr())
+            left -= m
+
+    for _ in range(max(1, warmup - 1)):
+        step_e2e()
+    barrier()
+    b0 = eng.transfer_bytes
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    b1 = eng.transfer_bytes
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del d_out, d_frames, h_out
+    return {"ms_device": float(ms.item()) / steps, "s_e2e": float(t.item()) / steps, "keypoints_per_step": n_kp,
+            "overflowed_frames": overflow, "h2d_bytes_per_step": (b1[0] - b0[0]) // steps,
+            "d2h_bytes_per_step": (b1[1] - b0[1]) // steps}
+
+
+def extra_configs(eng, L, torch, fixtures, rank, world, dist, peak):
+    """BASELINE.json configs[0], [2], [3] (configs[1] is the headline line, configs[4] the mosaic entry): throughput in
+    the headline's metric, as absolute Mpixel/s and as a fraction of the HBM roofline."""
+    out = {}
+
+    def entry(name, w, h, n_oct, per_rank, distinct, steps, scaling, note):
+        prm = L.default_params(numberOfOctaves=n_oct, scalesPerOctave=SPO, minBlurLevel=MIN_BLUR, assumedBlur=ASSUMED)
+        first = 1234 if scaling == "replicas" else 1234 + rank * per_rank          # cfg-3: contiguous blocks of the batch
+        frames = np.stack([fixtures.synthetic_u8(w, h, first + i) for i in range(min(per_rank, distinct))])
+        cap = max(1 << 13, (w * h) // 96)
+        r = bench_frames(eng, L, torch, frames, prm, per_rank, steps, 2, cap, dist if scaling != "replicas" else None)
+        ranks = 1 if scaling == "replicas" else world
+        px = ranks * per_rank * w * h
+        ab = algorithmic_bytes_per_input_px(n_oct)["total"]
+        dev = px / 1e6 / (r["ms_device"] / 1e3)
+        e2e = px / 1e6 / r["s_e2e"]
+        out[name] = {"workload": f"{w}x{h}, {n_oct} octaves x s={SPO}, sigma0={MIN_BLUR}", "frames_per_gpu_per_step": per_rank,
+                     "distinct_frames_per_gpu": int(frames.shape[0]), "n_gpus": ranks, "scaling": scaling,
+                     "value": dev, "unit": "Mpixel/s", "e2e": e2e, "ms_per_frame_per_gpu": r["ms_device"] / per_rank,
+                     "roofline_frac": ab * dev * 1e6 / ranks / 1e9 / peak, "algorithmic_bytes_per_input_px": ab,
+                     "keypoints_per_step_rank0": r["keypoints_per_step"], "overflowed_frames": r["overflowed_frames"],
+                     "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"], "note": note}
+
+    entry("cfg1_512x512_4oct", 512, 512, 4, 64, 64, 4, "replicas", "BASELINE configs[0] shape; rank 0 only")
+    per = max(1, 1024 // world)
+    entry("cfg3_batch_1024x720p", 1280, 720, 4, per, 128, 2, "strong" if world > 1 else "strong (1 GPU: the whole batch)",
+          f"BASELINE configs[2]: the fixed batch of 1024 frames, {per} per GPU in contiguous blocks, no collective; "
+          "the rank's frames cycle through at most 128 distinct synthetic frames (same cost per frame)")
+    entry("cfg4_3840x2160_6oct", 3840, 2160, 6, 8, 4, 3, "replicas", "BASELINE configs[3]; rank 0 only")
+    return out
+
+
+def mosaic_entry(eng, L, torch, fixtures, rank, world, local, dist):
+    """BASELINE configs[4]: a square mosaic cut into `world` row strips, one per GPU, seed-halo exchange per octave over
+    NCCL (the only path with a collective).  16384^2 at any N (checked against the whole-image result on rank 0);
+    32768^2 at N = 8."""
+    from sift_b200 import mosaic
+    out = {}
+    sizes = [16384] + ([32768] if world >= 8 else [])
+    for size in sizes:
+        prm = L.default_params(numberOfOctaves=N_OCT, scalesPerOctave=SPO, minBlurLevel=MIN_BLUR, assumedBlur=ASSUMED)
+        layouts = mosaic.plan_strips(prm, size, size, world, 64)
+        lay = layouts[rank]
+        nblobs = max(64, size * size // 16384)
+        t0 = time.perf_counter()
+        rows = fixtures.synthetic_u8_rows(size, size, lay.top[0] // 2, (lay.bottom[0] + 1) // 2, 4321, blobs=nblobs)
+        t_gen = time.perf_counter() - t0
+        rows = torch.from_numpy(rows).pin_memory().numpy()
+        phases = {}
+
+        def tick(name, t0):
+            torch.cuda.synchronize(); dist.barrier()
+            phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+
+        times = []
+        for rep in range(3):
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            kps, stats = mosaic.detect_mosaic_distributed(eng, rows, layouts, prm, rank)
+            torch.cuda.synchronize(); dist.barrier()
+            times.append(time.perf_counter() - t0)
+        # the same steps timed one by one (a barrier after each: the sum exceeds the pipelined time above)
+        dist.barrier(); t0 = time.perf_counter()
+        eng.strip_begin(prm, lay, rows); tick("upload_ms", t0)
+        halo_bytes = 0
+        for o in range(N_OCT):
+            t0 = time.perf_counter()
+            if o > 0:
+                mosaic.exchange_seed_halos(mosaic.seed_tensor(eng, lay, o), layouts, o, rank)
+                tick("halo_exchange_ms", t0); t0 = time.perf_counter()
+                halo_bytes += sum(n * lay.width[o] * 8 for s_, d_, r_, n in mosaic.halo_transfers(layouts, o) if d_ == rank)
+            eng.strip_octave(o); tick("blur_octaves_ms", t0)
+        t0 = time.perf_counter()
+        k2, st2 = eng.strip_finish(); tick("scan_refine_order_download_ms", t0)
+        t0 = time.perf_counter()
+        mosaic.resolve_escaped_distributed(eng, layouts, rank, k2, st2); tick("walk_handover_ms", t0)
+        merged = mosaic.gather_keypoints(kps, rank, world)
+        left = torch.tensor([stats["leftStrip"]], device="cuda")
+        hb = torch.tensor([halo_bytes], device="cuda", dtype=torch.int64)
+        dist.all_reduce(left); dist.all_reduce(hb)
+        e = None
+        if rank == 0:
+            best = min(times)
+            ab = algorithmic_bytes_per_input_px(N_OCT)["total"]
+            e = {"mosaic": f"{size}x{size}", "n_gpus": world, "strips": world, "octaves": N_OCT, "seconds": best,
+                 "value": size * size / 1e6 / best, "unit": "Mpixel/s", "reps_s": [round(t, 4) for t in times],
+                 "roofline_frac_per_gpu": ab * size * size / best / world / 1e9 / measured_peak_gbs()[0],
+                 "keypoints": int(len(merged)), "walks_handed_over": int(left.item()),
+                 "halo_rows_per_octave": [int(lay.halo[o]) for o in range(N_OCT)], "halo_bytes_received_all_ranks": int(hb.item()),
+                 "phases_ms": {k_: round(v, 3) for k_, v in phases.items()}, "generate_s_rank0": round(t_gen, 2),
+                 "timed": "strip upload from pinned host rows + octaves with NCCL halo exchange + scan + refine + ordering + "
+                          "download + walk hand-over, wall clock between two barriers, best of 3",
+                 "collective": "torch.distributed batch_isend_irecv (NCCL P2P over NVLink) of fp64 seed rows, per octave"}
+            if size == 16384:
+                del rows
+                img = fixtures.synthetic_u8(size, size, 4321, blobs=nblobs)
+                whole, _ = eng.detect(img, prm)
+                e["identical_to_whole_image"] = bool(whole.tobytes() == merged.tobytes())
+                e["whole_image_keypoints"] = int(len(whole))
+                del img, whole
+            out[f"{size}x{size}"] = e
+        dist.barrier()
+    return out
+
+
 # ------------------------------------------------------------------------------ CPU legs
 def cpu_tiles(n: int):
     """n CPU_TILE^2 crops (float64 in [0,1]) of the benchmark's first frame."""
@@ -154,9 +338,50 @@ def cpu_baseline_leg() -> dict:
                       f"{dt:.1f} s of CPU work (Node.js absent: float64 C restatement of the reference JS)"}
 
 
+def node_reference(tiles, cores):
+    """The UNMODIFIED reference under Node.js (baseline/run_reference.mjs over the copy in baseline/_ref), one image
+    per worker_thread.  Returns (seconds, info) or None when there is no `node` on this box / the copy is missing /
+    the harness fails (the caller then falls back to the float64 port and says so)."""
+    import shutil
+    import tempfile
+    node = shutil.which("node") or shutil.which("nodejs")
+    ref = os.path.join(ROOT, "baseline", "_ref", "background.js")
+    if not node or not os.path.exists(ref):
+        return None
+    try:
+        u8 = np.stack([np.rint(t * 255.0).astype(np.uint8) for t in tiles])
+        with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+            f.write(u8.tobytes())
+            path = f.name
+        r = subprocess.run([node, "--max-old-space-size=8192", os.path.join(ROOT, "baseline", "run_reference.mjs"), path,
+                            str(CPU_TILE), str(CPU_TILE), str(len(tiles)), str(N_OCT), str(SPO), str(MIN_BLUR), str(ASSUMED),
+                            str(cores)], capture_output=True, text=True, timeout=1500)
+        os.unlink(path)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not line:
+            return None
+        d = json.loads(line[-1])
+        return float(d["seconds"]), d
+    except Exception:
+        return None
+
+
+def separable_port_whole_frames(n_frames: int = 2):
+    """The separable float64 port (oracle_blur_image_separable: the same sums, row bands on all host cores) on WHOLE
+    1920x1080 frames -- reported beside the dense-2D figure, which is what the reference's algorithm costs."""
+    import oracle
+    from sift_b200 import fixtures
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        oracle.detect(fixtures.to_float(fixtures.synthetic_u8(W, H, 1234 + i)), numberOfOctaves=N_OCT, scalesPerOctave=SPO,
+                      minBlurLevel=MIN_BLUR, assumedBlur=ASSUMED, separable=True, keep_levels=False)
+    return n_frames * W * H / 1e6 / (time.perf_counter() - t0)
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (oracle port: no Node.js on the box) on all host cores,
-    one image per thread, same config / metric / unit."""
+    """--impl reference: the reference's own CPU implementation on all host cores, one image per thread (BASELINE.md
+    section 3), same config / metric / unit: the unmodified JavaScript under Node.js when the box has a `node`
+    (kind "reference"), else the float64 C port of its dense 2D algorithm (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -169,6 +394,21 @@ def run_reference(args):
     except Exception:
         pass
     tiles = cpu_tiles(cores)
+    js = node_reference(tiles, cores) if not os.environ.get("SIFT_BENCH_NO_NODE") else None
+    if js is not None:
+        dt, info = js
+        value = len(tiles) * CPU_TILE * CPU_TILE / 1e6 / dt
+        sample = (f"{len(tiles)} crops {CPU_TILE}x{CPU_TILE} of the 1920x1080 frame, one per worker_thread ({info.get('threads')} threads), "
+                  f"unmodified reference JavaScript under Node {info.get('node')} (baseline/run_reference.mjs), one pass")
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+                "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": int(info.get("threads") or cores), "kind": "reference",
+                                 "sample": sample},
+                "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "keypoints_per_crop": info.get("keypoints")}
+        print(json.dumps(line), flush=True)
+        return
     ex = cf.ThreadPoolExecutor(max_workers=cores)   # ctypes releases the GIL inside the C call
 
     def step():
@@ -182,14 +422,21 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * cores * CPU_TILE * CPU_TILE / 1e6 / dt
     sample = (f"{cores} crops {CPU_TILE}x{CPU_TILE} per step (one per thread) of the 1920x1080 frame, "
-              f"same params, dense 2D kernel")
+              f"same params, dense 2D kernel; no `node` binary on this box, so this is the float64 C port of the reference")
+    try:
+        sep = separable_port_whole_frames(1 if CPU_TILE < 128 else 2)
+    except Exception:
+        sep = None
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "separable_port_whole_1080p_frames": {"value": sep, "unit": "Mpixel/s", "cores": cores,
+                                                  "note": "same sums reorganised as two 1D passes (not the reference's "
+                                                          "algorithm: reported beside it, not as it)"}}
     print(json.dumps(line), flush=True)
 
 
@@ -296,7 +543,11 @@ def run_own(args):
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = args.steps * px_step_all / 1e6 / float(t_e2e.item())
-    d2h_per_frame = 64 + min(cap, 8192) * L.KEYPOINT_DTYPE.itemsize
+    # bytes counted by the engine where it issues the copies (sift_transfer_bytes), one more step
+    tb0 = eng.transfer_bytes
+    step_e2e()
+    tb1 = eng.transfer_bytes
+    h2d_step, d2h_step = tb1[0] - tb0[0], tb1[1] - tb0[1]
 
     # ---- per-kernel-class timing (separate instrumented pass, CUDA events on the engine's stream)
     eng.set_lanes(1)                 # one frame at a time: per-kernel times without cross-frame overlap
@@ -306,6 +557,23 @@ def run_own(args):
         step_device()
     prof = eng.get_profile()
     eng.set_profiling(False)
+    eng.set_lanes(LANES)
+
+    # ---- the other named shapes, and (N > 1) the mosaic: extra keys of the same line
+    from sift_b200 import fixtures
+    del d_out, d_frames
+    torch.cuda.empty_cache()
+    configs, mosaic_res = {}, {}
+    if not args.headline_only:
+        try:
+            configs = extra_configs(eng, L, torch, fixtures, rank, world, dist, measured_peak_gbs()[0])
+        except Exception as ex:                       # never lose the headline over an extra
+            configs = {"error": repr(ex)}
+        if world > 1:
+            try:
+                mosaic_res = mosaic_entry(eng, L, torch, fixtures, rank, world, local, dist)
+            except Exception as ex:
+                mosaic_res = {"error": repr(ex)}
 
     if rank == 0:
         ab = algorithmic_bytes_per_input_px()
@@ -316,6 +584,7 @@ def run_own(args):
             kinds[kind] = {"ms_per_frame": kms / (prof_steps * FRAMES), "launch_groups": cnt}
         tot_ms = sum(k["ms_per_frame"] for k in kinds.values()) or 1.0
         dom = "blur_octave0"
+        traffic, traffic_src = ncu_traffic(DOMINANT_KERNEL)
         dom_ms = kinds[dom]["ms_per_frame"]
         dom_bytes = ab["blur"][0] * n_px
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -327,16 +596,14 @@ def run_own(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
-            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": FRAMES * W * H,
-                    "d2h_bytes_per_step": FRAMES * d2h_per_frame,
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d_step,
+                    "d2h_bytes_per_step": d2h_step, "bytes_counted_by": "sift_transfer_bytes() around one step",
                     "note": "sift_detect_batch(): pinned host u8 frames in, ordered keypoint records out; "
                             "upload / compute / download+ordering of consecutive frames overlap"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "octave-0 upsample+blur+DoG (" + dom + ")",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_OCT0_BYTES, "peak_source": peak_src,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of fused_octave0_kernel, "
-                                           "ncu --set full, profiles/r01_ncu_fused_octave0_1.txt",
+                         "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "whole_path": {"algorithmic_bytes_per_input_px": ab["total"],
                                         "achieved": whole_gbs, "frac": whole_gbs / peak},
@@ -344,6 +611,9 @@ def run_own(args):
             "keypoints_per_step": n_kp,
             "clocks": clocks,
         }
+        line["configs"] = configs
+        if mosaic_res:
+            line["mosaic"] = mosaic_res
         if world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_leg()
@@ -363,6 +633,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra configs / mosaic entries")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -167,6 +167,9 @@ SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for
  * sift_strip_begin, a plan change).  A host that caches "the context still holds the pyramid of reply X" -- as the
  * reference's main thread holds gaussian_scale_space / difference_of_gaussians (main.js:31-32) -- compares this. */
 SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx);
+/* Running totals of the bytes the detect calls (sift_detect, sift_detect_batch, stage uploads) copied host -> device
+ * (images) and device -> host (counters + keypoint records), counted where the copies are issued. */
+SIFT_API void sift_transfer_bytes(const sift_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 
 /* Per-kernel-class device timing (CUDA events around each launch group on sift_stream).
  * Off by default; bench.py turns it on for a separate instrumented pass. */

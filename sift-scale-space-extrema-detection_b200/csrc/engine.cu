@@ -54,6 +54,7 @@ struct sift_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
+  uint64_t bytes_h2d = 0, bytes_d2h = 0;   // image uploads / record downloads of the detect calls (sift_transfer_bytes)
 
   Lane lanes[SIFT_MAX_LANES];
   Lane *L = nullptr;                    // lane the stage helpers address
@@ -681,6 +682,7 @@ static int upload_image(sift_ctx *ctx, const void *image, int dtype, int w, int 
   if ((rc = grow(ctx, ctx->L->image, row * h))) return rc;
   if (pitch_bytes == row) CK(cudaMemcpyAsync(ctx->L->image.p, image, row * h, cudaMemcpyHostToDevice, ctx->L->stream));
   else CK(cudaMemcpy2DAsync(ctx->L->image.p, row, image, pitch_bytes, row, h, cudaMemcpyHostToDevice, ctx->L->stream));
+  ctx->bytes_h2d += row * h;
   *dev_pitch = row;
   return SIFT_OK;
 }
@@ -695,8 +697,10 @@ static int download_keypoints(sift_ctx *ctx, Counters *c, sift_keypoint **kps)
     return rc;
   CK(cudaMemcpyAsync(ctx->L->h_out, ctx->L->outbuf.p, first, cudaMemcpyDeviceToHost, ctx->L->stream));
   CK(cudaStreamSynchronize(ctx->L->stream));
+  ctx->bytes_d2h += first;
   *c = *(Counters *)ctx->L->h_out;
   const int n = std::min(c->n_kp, ctx->L->kp_cap);
+  if (n > FIRST_CHUNK) ctx->bytes_d2h += (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint);
   if (n > FIRST_CHUNK) {
     CK(cudaMemcpyAsync((char *)ctx->L->h_out + first, (char *)ctx->L->outbuf.p + first,
                        (size_t)(n - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ctx->L->stream));
@@ -870,6 +874,11 @@ SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
 SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->main_stream : nullptr; }
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx) { return ctx ? ctx->launches : 0; }
 SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx) { return ctx ? ctx->pyramid_serial : 0; }
+SIFT_API void sift_transfer_bytes(const sift_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
+{
+  if (h2d) *h2d = ctx ? ctx->bytes_h2d : 0;
+  if (d2h) *d2h = ctx ? ctx->bytes_d2h : 0;
+}
 
 SIFT_API int sift_set_profiling(sift_ctx *ctx, int enabled)
 {
@@ -1048,6 +1057,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     const void *img = (const char *)images + (size_t)i * image_stride_bytes;
     if (pitch_bytes == row) CK(cudaMemcpyAsync(ln->image.p, img, row * height, cudaMemcpyHostToDevice, ln->stream));
     else CK(cudaMemcpy2DAsync(ln->image.p, row, img, pitch_bytes, row, height, cudaMemcpyHostToDevice, ln->stream));
+    ctx->bytes_h2d += row * height;
     CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream));
     int r;
     if ((r = run_pyramid(ctx, ln->image.p, dtype, row))) return r;
@@ -1055,6 +1065,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     if ((r = run_refine(ctx, -1, dev_keypoints(ctx), ln->kp_cap))) return r;
     const size_t first = sizeof(Counters) + (size_t)std::min(ln->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
     CK(cudaMemcpyAsync(hbuf(ln, i), ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
+    ctx->bytes_d2h += first;
     CK(cudaEventRecord(ln->ev_done, ln->stream));
     issued = i + 1;
     t_issue += now() - t0;
@@ -1101,6 +1112,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
       const size_t first = sizeof(Counters) + (size_t)FIRST_CHUNK * sizeof(sift_keypoint);
       CK(cudaMemcpyAsync((char *)hbuf(ln, j) + first, (char *)ln->outbuf.p + first,
                          (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ln->stream));
+      ctx->bytes_d2h += (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint);
       CK(cudaStreamSynchronize(ln->stream));
     }
     return SIFT_OK;

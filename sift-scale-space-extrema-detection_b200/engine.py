@@ -83,6 +83,13 @@ class Engine:
         """Generation of the pyramid the stage calls read; changes whenever any call rebuilds or invalidates it."""
         return int(self._lib.sift_pyramid_serial(self._h))
 
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied by the detect calls so far, counted where the copies are issued."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._lib.sift_transfer_bytes(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def synchronize(self):
         self._check(self._lib.sift_synchronize(self._h))
 
