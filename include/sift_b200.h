@@ -277,6 +277,13 @@ SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const si
  * = global row top[octave].  After sift_strip_octave(octave - 1) the OWNED rows are final; the caller fills
  * the halo rows from the neighbouring strips, then calls sift_strip_octave(octave). */
 SIFT_API int sift_strip_seed(sift_ctx *ctx, int octave, double **d_seed);
+/* The exchange step itself, for hosts that drive all strips from ONE process (a Node.js / C host with one context
+ * per GPU): fills the halo rows of every strip's seed image of `octave` from the strips that own them, device to
+ * device (cudaMemcpyPeerAsync: NVLink between GPUs), stream-ordered between the senders' sift_strip_octave(octave-1)
+ * and the receivers' sift_strip_octave(octave); the host is not blocked.  Call it once per octave >= 1 with every
+ * strip of the mosaic (any order).  One-process-per-GPU hosts exchange the rows of sift_strip_seed() themselves
+ * (mosaic.py: torch.distributed / NCCL send-recv). */
+SIFT_API int sift_mosaic_exchange(sift_ctx *const *ctxs, int n_strips, int octave);
 /* Blur + DoG of one octave (0, 1, 2 ... in order) and the owned rows of the next octave's seed.  Synchronous. */
 SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave);
 /* Scan + refine over all octaves: keypoints of the owned rows, global coordinates, reference order. */

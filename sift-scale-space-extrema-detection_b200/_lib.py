@@ -112,6 +112,7 @@ PROTOTYPES = {
     "sift_strip_begin": (C.c_int, [_VP, C.POINTER(Params), C.POINTER(StripLayout), _VP, C.c_int, C.c_size_t]),
     "sift_strip_seed": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "sift_strip_octave": (C.c_int, [_VP, C.c_int]),
+    "sift_mosaic_exchange": (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int]),
     "sift_strip_finish": (C.c_int, [_VP, _VP, C.c_int, _IP, C.POINTER(Stats)]),
     "sift_strip_escaped": (C.c_int, [_VP, _VP, C.c_int, _IP]),
     "sift_strip_resume": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, _IP, C.POINTER(Stats)]),

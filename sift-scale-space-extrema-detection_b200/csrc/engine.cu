@@ -1458,6 +1458,66 @@ SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave)
   return SIFT_OK;
 }
 
+// Seed-halo exchange between the strips of ONE process (one exchange step per octave): every strip
+// receives, from the strips that own them, the seed rows of `octave` it holds beyond its own range.  Device to
+// device: cudaMemcpyPeerAsync on the receiving strip's stream -- over NVLink when the contexts sit on different
+// GPUs, a plain device copy when they share one -- ordered after the sender's octave (octave - 1) by an event.
+// The host does not wait: the receivers' next sift_strip_octave is stream-ordered after the copies.
+SIFT_API int sift_mosaic_exchange(sift_ctx *const *ctxs, int n_strips, int octave)
+{
+  if (!ctxs || n_strips < 1) return SIFT_ERR_BAD_ARGS;
+  sift_ctx *ctx = ctxs[0];
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  for (int i = 0; i < n_strips; i++) {
+    sift_ctx *c = ctxs[i];
+    if (!c || !c->plan_valid || !c->is_strip) return fail(ctx, SIFT_ERR_STATE, "strip %d: call sift_strip_begin first", i);
+    if (octave < 1 || octave >= c->n_oct) return fail(ctx, SIFT_ERR_BAD_ARGS, "octave %d has no seed image", octave);
+    if (c->strip_next_octave != octave) return fail(ctx, SIFT_ERR_STATE, "strip %d is at octave %d, not %d", i, c->strip_next_octave, octave);
+    if (c->strip.width[octave] != ctx->strip.width[octave] || c->strip.height[octave] != ctx->strip.height[octave])
+      return fail(ctx, SIFT_ERR_BAD_ARGS, "strip %d belongs to another mosaic", i);
+  }
+  // every sender's seed rows are final once its octave (octave - 1) has run: one event per strip
+  for (int i = 0; i < n_strips; i++) {
+    sift_ctx *c = ctxs[i];
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->lanes[0].ev_done, c->lanes[0].stream));
+  }
+  const size_t row_bytes = (size_t)ctx->strip.width[octave] * sizeof(double);
+  for (int d = 0; d < n_strips; d++) {
+    sift_ctx *dst = ctxs[d];
+    const sift_strip_layout &dl = dst->strip;
+    CK(cudaSetDevice(dst->device));
+    for (int s2 = 0; s2 < n_strips; s2++) {             // direct NVLink path between the two GPUs (once per pair)
+      int can = 0;
+      if (ctxs[s2]->device != dst->device && cudaDeviceCanAccessPeer(&can, dst->device, ctxs[s2]->device) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[s2]->device, 0);
+        if (e != cudaSuccess) (void)cudaGetLastError();   // already enabled (or refused: the copy is then staged)
+      }
+    }
+    // halo rows = held rows outside the owned range: [top, own0) and [own1, bottom)
+    const int ranges[2][2] = { { dl.top[octave], dl.own0[octave] }, { dl.own1[octave], dl.bottom[octave] } };
+    for (int r = 0; r < 2; r++) {
+      int row = ranges[r][0];
+      while (row < ranges[r][1]) {
+        int owner = -1;
+        for (int s2 = 0; s2 < n_strips; s2++)
+          if (row >= ctxs[s2]->strip.own0[octave] && row < ctxs[s2]->strip.own1[octave]) { owner = s2; break; }
+        if (owner < 0 || owner == d) return fail(ctx, SIFT_ERR_BAD_ARGS, "row %d of octave %d is owned by no other strip", row, octave);
+        sift_ctx *src = ctxs[owner];
+        const int last = std::min(ranges[r][1], src->strip.own1[octave]);
+        const double *sp = src->lanes[0].octs[octave].seed64 + (size_t)(row - src->strip.top[octave]) * src->strip.width[octave];
+        double *dp = dst->lanes[0].octs[octave].seed64 + (size_t)(row - dl.top[octave]) * dl.width[octave];
+        CK(cudaStreamWaitEvent(dst->lanes[0].stream, src->lanes[0].ev_done, 0));
+        CK(cudaMemcpyPeerAsync(dp, dst->device, sp, src->device, (size_t)(last - row) * row_bytes, dst->lanes[0].stream));
+        row = last;
+      }
+    }
+  }
+  // a sender must not start overwriting ... nothing: octave `octave` only reads the seed; the next octave's seed is
+  // another buffer.  Receivers are stream-ordered; nothing to wait for on the host.
+  return SIFT_OK;
+}
+
 static int fetch_escaped(sift_ctx *ctx, const Counters &c);
 SIFT_API int sift_strip_finish(sift_ctx *ctx, sift_keypoint *out, int cap, int *n_out, sift_stats *stats)
 {

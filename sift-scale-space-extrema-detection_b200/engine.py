@@ -193,7 +193,7 @@ class Engine:
         retry repeats the scan and the refinement), starting from one record per 64 owned octave-0 pixels."""
         cap = capacity or getattr(self, "_strip_cap", 1 << 16)
         while True:
-            out = np.empty(cap, dtype=L.KEYPOINT_DTYPE)
+            out = self._pinned_records(cap)
             n = C.c_int()
             st = L.Stats()
             rc = self._lib.sift_strip_finish(self._h, out.ctypes.data, cap, C.byref(n), C.byref(st))
@@ -202,7 +202,27 @@ class Engine:
                 continue
             self._check(rc)
             self._strip_cap = max(cap, n.value + n.value // 8)
-            return out[:n.value], st.as_dict()
+            return out[:n.value].copy() if self._pin is None else out[:n.value], st.as_dict()
+
+    _pin = None
+
+    def _pinned_records(self, cap: int) -> np.ndarray:
+        """A keypoint-record array of `cap` entries in page-locked host memory when torch is importable (a strip of a
+        gigapixel mosaic downloads 10^5..10^6 records: pageable memory makes that copy several times slower).  Two
+        buffers alternate, so a result stays valid until the SECOND strip_finish after it; callers that keep results
+        longer copy them (mosaic.merge_keypoints concatenates, which copies)."""
+        try:
+            import torch
+            if self._pin is None:
+                self._pin = [None, None, 0]
+            self._pin[2] ^= 1
+            i = self._pin[2]
+            if self._pin[i] is None or self._pin[i].numel() < cap * L.KEYPOINT_DTYPE.itemsize:
+                self._pin[i] = torch.empty(cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            return self._pin[i].numpy()[:cap * L.KEYPOINT_DTYPE.itemsize].view(L.KEYPOINT_DTYPE)
+        except Exception:
+            self._pin = None
+            return np.empty(cap, dtype=L.KEYPOINT_DTYPE)
 
     def strip_escaped(self) -> np.ndarray:
         """Refinement walks that left this strip's rows in the last strip_finish / strip_resume (WALK_DTYPE)."""

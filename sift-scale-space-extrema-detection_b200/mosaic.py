@@ -111,17 +111,31 @@ def source_rows(image: np.ndarray, layout: L.StripLayout) -> np.ndarray:
     return np.ascontiguousarray(image[layout.top[0] // 2:(layout.bottom[0] + 1) // 2])
 
 
-def detect_mosaic_local(engines: list, image: np.ndarray, params: L.Params, margin: int = 16, layouts: list | None = None):
+def exchange_local(engines: list, octave: int):
+    """sift_mosaic_exchange: the halo rows of every strip's seed of `octave`, device to device, inside the C ABI
+    (cudaMemcpyPeerAsync, stream-ordered, the host does not wait) -- what a host without torch calls."""
+    lib = L.load()
+    arr = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+    rc = lib.sift_mosaic_exchange(arr, len(engines), octave)
+    if rc != L.SIFT_OK:
+        raise L.SiftError(rc, (lib.sift_last_error(engines[0].handle) or b"").decode())
+
+
+def detect_mosaic_local(engines: list, image: np.ndarray, params: L.Params, margin: int = 16, layouts: list | None = None,
+                        exchange: str = "c_abi"):
     """All strips from one process (engine i = strip i; the engines may sit on different GPUs or share one).
-    Halo rows move device to device with torch copies.  `layouts`: explicit cuts (default: plan_strips).
-    Returns (keypoints in reference order, per-strip stats, layouts)."""
-    import torch
+    exchange = "c_abi": halo rows move with sift_mosaic_exchange (peer copies inside the library); "torch": with
+    torch tensor copies over the seed images (the form the distributed path uses).  `layouts`: explicit cuts
+    (default: plan_strips).  Returns (keypoints in reference order, per-strip stats, layouts)."""
     h, w = image.shape[:2]
     layouts = layouts or plan_strips(params, w, h, len(engines), margin)
     for eng, lay in zip(engines, layouts):
         eng.strip_begin(params, lay, source_rows(image, lay))
     for o in range(params.numberOfOctaves):
-        if o > 0:
+        if o > 0 and exchange == "c_abi":
+            exchange_local(engines, o)
+        elif o > 0:
+            import torch
             seeds = [seed_tensor(e, lay, o) for e, lay in zip(engines, layouts)]
             for src, dst, row, n in halo_transfers(layouts, o):
                 s0 = row - layouts[src].top[o]

@@ -39,7 +39,7 @@ def test_strip_layout_arithmetic():
 
 
 def test_mosaic_module_surface():
-    for name in ("strip_layout", "plan_strips", "halo_transfers", "exchange_seed_halos", "seed_tensor", "source_rows",
+    for name in ("strip_layout", "plan_strips", "halo_transfers", "exchange_seed_halos", "exchange_local", "seed_tensor", "source_rows",
                  "detect_mosaic_local", "detect_mosaic_distributed", "owner_of", "resolve_escaped_local",
                  "resolve_escaped_distributed", "merge_keypoints", "gather_keypoints"):
         assert callable(getattr(mosaic, name)), name
@@ -165,6 +165,26 @@ def test_strips_are_bit_identical_to_the_whole_image(engine, world, w, h, n_oct)
                     d = eng.get_level(L.SIFT_LEVEL_DOG, o, s)
                     a, b = lay.own0[o] - lay.top[o], lay.own1[o] - lay.top[o]
                     assert np.array_equal(d[a:b], levels[(o, s)][lay.own0[o]:lay.own1[o]]), (r, o, s)
+    finally:
+        for e in engines:
+            e.close()
+
+
+@pytest.mark.gpu
+def test_c_abi_exchange_equals_the_torch_exchange(engine):
+    """sift_mosaic_exchange (peer copies inside the library, what a host without torch calls) moves the same rows as
+    the torch copies: identical records, and both equal the whole image."""
+    w, h, n_oct = 160, 1200, 4
+    u8 = fixtures.synthetic_u8(w, h, 31, blobs=w * h // 512, sigma_lo=1.0, sigma_hi=6.0)
+    prm = _params(n_oct)
+    whole, _ = engine.detect(u8, prm)
+    engines = [sift_b200.Engine(0) for _ in range(3)]
+    try:
+        a, _, lays = mosaic.detect_mosaic_local(engines, u8, prm, margin=16, exchange="c_abi")
+        b, _, _ = mosaic.detect_mosaic_local(engines, u8, prm, margin=16, exchange="torch")
+        assert a.tobytes() == b.tobytes() == whole.tobytes() and len(whole) > 100
+        with pytest.raises(sift_b200.SiftError):                 # strips must be at the octave being exchanged
+            mosaic.exchange_local(engines, 1)
     finally:
         for e in engines:
             e.close()
