@@ -167,6 +167,9 @@ SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for
  * sift_strip_begin, a plan change).  A host that caches "the context still holds the pyramid of reply X" -- as the
  * reference's main thread holds gaussian_scale_space / difference_of_gaussians (main.js:31-32) -- compares this. */
 SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx);
+/* Test hook: fill every device buffer of the context (planes, seeds, intermediates, record buffers) with `byte` and
+ * invalidate the pyramid.  Results of later calls must not depend on the pattern (tests/test_memory_hygiene.py). */
+SIFT_API int sift_debug_poison(sift_ctx *ctx, int byte);
 /* Running totals of the bytes the detect calls (sift_detect, sift_detect_batch, stage uploads) copied host -> device
  * (images) and device -> host (counters + keypoint records), counted where the copies are issued. */
 SIFT_API void sift_transfer_bytes(const sift_ctx *ctx, uint64_t *h2d, uint64_t *d2h);

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "sift_set_keep_gaussian": (C.c_int, [_VP, C.c_int]),
     "sift_kernel_launches": (C.c_int64, [_VP]),
     "sift_pyramid_serial": (C.c_uint64, [_VP]),
+    "sift_debug_poison": (C.c_int, [_VP, C.c_int]),
     "sift_transfer_bytes": (None, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sift_set_profiling": (C.c_int, [_VP, C.c_int]),
     "sift_get_profile": (C.c_int, [_VP, _FP, _IP, C.c_int]),

@@ -303,6 +303,7 @@ fir_pass_b_tma_kernel(const double *__restrict__ weights, const FirArgs A)
   const CUtensorMap *maps = (const CUtensorMap *)A.tmaps;
 
   auto issue = [&](int li) {                                // one thread: arm the barrier, one box
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read / patched through the generic proxy
     const int R = A.radius[li];
     const unsigned bytes = (unsigned)(FP_LINES * fir_box_span(NW * NO, R, NO) * sizeof(double));
     const unsigned b = fir_smem_u32(&bar[li & 1]);
@@ -374,6 +375,9 @@ fir_pass_b_tma_kernel(const double *__restrict__ weights, const FirArgs A)
           const double v = ln[last];
           for (int e = last + 1 + warp; e < pitch_l; e += NW) ln[e] = v;
         }
+        // these generic-proxy stores land in a buffer the TMA unit (async proxy) refills two levels later: order them
+        // before that write (the CTA barrier at the end of the level carries the fence to the issuing thread)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
       }
     }

@@ -874,6 +874,27 @@ SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
 SIFT_API void *sift_stream(sift_ctx *ctx) { return ctx ? (void *)ctx->main_stream : nullptr; }
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx) { return ctx ? ctx->launches : 0; }
 SIFT_API uint64_t sift_pyramid_serial(const sift_ctx *ctx) { return ctx ? ctx->pyramid_serial : 0; }
+// Test hook (compute-sanitizer is closed on the B200 pool): overwrite every device buffer the context owns -- level
+// planes, fp64 seeds, the pass intermediate, candidate / record / walk buffers -- with `byte`.  A detection whose
+// result depends on what these buffers held before it ran (a read of memory the path did not write first, a tile
+// that is skipped, a stale halo) then changes with the pattern; tests/test_memory_hygiene.py compares the results
+// bit for bit under 0x00 / 0xFF (NaN) / 0x7F fills.
+SIFT_API int sift_debug_poison(sift_ctx *ctx, int byte)
+{
+  if (!ctx) return SIFT_ERR_BAD_ARGS;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = sift_synchronize(ctx))) return rc;
+  for (Lane &ln : ctx->lanes) {
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.cand, &ln.outbuf, &ln.order, &ln.walks };
+    for (Scratch *sc : all)
+      if (sc->p) CK(cudaMemset(sc->p, byte, sc->cap));
+  }
+  ctx->pyramid_built = false;
+  ctx->pyramid_serial++;
+  return SIFT_OK;
+}
+
 SIFT_API void sift_transfer_bytes(const sift_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
 {
   if (h2d) *h2d = ctx ? ctx->bytes_h2d : 0;

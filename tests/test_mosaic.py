@@ -174,7 +174,7 @@ def test_strips_are_bit_identical_to_the_whole_image(engine, world, w, h, n_oct)
 def test_c_abi_exchange_equals_the_torch_exchange(engine):
     """sift_mosaic_exchange (peer copies inside the library, what a host without torch calls) moves the same rows as
     the torch copies: identical records, and both equal the whole image."""
-    w, h, n_oct = 160, 1200, 4
+    w, h, n_oct = 160, 1200, 3
     u8 = fixtures.synthetic_u8(w, h, 31, blobs=w * h // 512, sigma_lo=1.0, sigma_hi=6.0)
     prm = _params(n_oct)
     whole, _ = engine.detect(u8, prm)
