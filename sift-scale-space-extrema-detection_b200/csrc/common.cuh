@@ -103,6 +103,12 @@ void launch_oct0_v2(cudaStream_t st, const void *src, int dtype, size_t src_pitc
                     const OctaveDev &oct, const OctaveDev *next, const double *d_weights, const LevelPlan *plans,
                     int poly_woff, int nlev, int spo, int keep_gauss, const void *d_out_maps);
 
+// blur_oct0s.cu: octave 0, small-CTA form (64 x 32 output tiles, <= 64 registers, four CTAs per SM)
+bool oct0_small_supported(const LevelPlan *plans, int nlev);
+void launch_oct0_small(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                       const OctaveDev &oct, const OctaveDev *next, const double *d_weights, const LevelPlan *plans,
+                       int poly_woff, int nlev, int spo, int keep_gauss);
+
 // scan.cu
 void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
                      double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,

@@ -484,7 +484,10 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
   if (o == 0 && ctx->fused0) {
     prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
-    if (ctx->L->oct0_maps)
+    if (!ctx->L->oct0_maps && oct0_small_supported(ctx->plans[0], ctx->nlev))
+      launch_oct0_small(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
+                        ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss);
+    else if (ctx->L->oct0_maps)
       launch_oct0_v2(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
                      ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, ctx->L->tmaps_o0.p);
     else
