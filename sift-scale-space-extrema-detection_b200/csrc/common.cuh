@@ -109,6 +109,16 @@ void launch_oct0_small(cudaStream_t st, const void *src, int dtype, size_t src_p
                        const OctaveDev &oct, const OctaveDev *next, const double *d_weights, const LevelPlan *plans,
                        int poly_woff, int nlev, int spo, int keep_gauss);
 
+// blur_oct0p.cu: octave 0 as two polyphase passes over row bands, intermediate in L2
+bool oct0p_supported(const LevelPlan *plans, int nlev);
+int oct0p_band_rows(int src_w, int src_h, int nlev);
+size_t oct0p_t_bytes(int src_w, int src_h, int nlev);
+size_t oct0p_map_bytes(int nlev);
+bool oct0p_build_maps(double *tbase, int src_w, int src_h, int nlev, void *h_maps);
+int launch_oct0p(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                 const OctaveDev &oct, const OctaveDev *next, const double *d_weights, const LevelPlan *plans,
+                 int poly_woff, int nlev, int spo, int keep_gauss, double *tbase, const void *d_maps);
+
 // scan.cu
 void launch_scan_all(cudaStream_t st, const OctaveDev *h_octs, const OctaveDev *d_octs, int n_oct, int spo,
                      double pix_threshold, int count_low, sift_candidate *cand, int cand_cap, sift_candidate *low,

@@ -33,7 +33,8 @@ struct Scratch {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, tmaps_o0, order, walks;
+  Scratch planes, seeds, tbuf, image, cand, outbuf, tmaps, tmaps_t, tmaps_o0, tmaps_p0, order, walks;
+  bool p0_maps = false;        // tmaps_p0 holds the TMA descriptors of octave 0's banded intermediate (blur_oct0p.cu)
   bool oct0_maps = false;      // tmaps_o0 holds the TMA-store descriptors of octave 0's planes (blur_oct0.cu)
   bool tma_scan = false;       // tmaps holds valid TMA descriptors of the DoG planes
   int tma_blur[SIFT_MAX_OCTAVES];   // per octave: maps of its T^T planes start at tmaps_t[tma_blur[o]] (-1: none)
@@ -362,6 +363,8 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
     if (o > 0 || !ctx->fused0)
       t_bytes = std::max(t_bytes, std::max(tl * trows * ow[o], sep_t_elems(ow[o], oh[o], (int)trows, ctx->plans[o], o == 0 ? 0 : 1, nlev)) * sizeof(double));
   }
+  const bool want_p0 = ctx->fused0 && !ctx->no_tma && oct0p_supported(ctx->plans[0], nlev);
+  if (want_p0) t_bytes = std::max(t_bytes, oct0p_t_bytes(w, h, nlev));
   int rc = SIFT_OK;
   do {
     if ((rc = grow(ctx, ln->planes, plane_elems * sizeof(float)))) break;
@@ -410,6 +413,20 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
           break;
         }
         ln->tma_scan = true;
+      }
+    }
+    // TMA descriptors of octave 0's banded intermediate (blur_oct0p.cu); the planes alias tbuf
+    ln->p0_maps = false;
+    if (want_p0) {
+      std::vector<char> hm(oct0p_map_bytes(nlev));
+      if (oct0p_build_maps((double *)ln->tbuf.p, w, h, nlev, hm.data())) {
+        if ((rc = grow(ctx, ln->tmaps_p0, hm.size()))) break;
+        if (cudaMemcpyAsync(ln->tmaps_p0.p, hm.data(), hm.size(), cudaMemcpyHostToDevice, ln->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ln->stream) != cudaSuccess) {
+          rc = fail(ctx, SIFT_ERR_CUDA, "upload of the octave-0 band TMA descriptors failed");
+          break;
+        }
+        ln->p0_maps = true;
       }
     }
     // TMA-store descriptors of octave 0's Gaussian / DoG planes (blur_oct0.cu)
@@ -484,7 +501,10 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
   if (o == 0 && ctx->fused0) {
     prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
-    if (!ctx->L->oct0_maps && oct0_small_supported(ctx->plans[0], ctx->nlev))
+    if (ctx->L->p0_maps && !ctx->L->oct0_maps && !oct0_small_supported(ctx->plans[0], ctx->nlev)) {
+      ctx->launches += launch_oct0p(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
+                                    ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, (double *)ctx->L->tbuf.p, ctx->L->tmaps_p0.p) - 1;
+    } else if (!ctx->L->oct0_maps && oct0_small_supported(ctx->plans[0], ctx->nlev))
       launch_oct0_small(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
                         ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss);
     else if (ctx->L->oct0_maps)
@@ -802,7 +822,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (Lane &ln : c->lanes) {
-    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.tmaps_o0, &ln.order, &ln.walks };
+    Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.tmaps_o0, &ln.tmaps_p0, &ln.order, &ln.walks };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);

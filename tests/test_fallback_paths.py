@@ -35,7 +35,8 @@ for (w, h, n_oct, seed) in ((208, 144, 3, 3), (1200, 900, 2, 8)):     # the seco
 # SIFT_B200_OCT0_WS: the persistent warp-specialised octave-0 kernel of blur_oct0.cu (TMA source boxes, TMA stores);
 # "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR": the same kernel with the source tile loaded by plain loads
 KNOBS = ["", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD", "SIFT_B200_NO_TMA", "SIFT_B200_NO_TMA_BLUR",
-         "SIFT_B200_FUSED0_LO", "SIFT_B200_FIR_NO8", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR"]
+         "SIFT_B200_FUSED0_LO", "SIFT_B200_FIR_NO8", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR",
+         "SIFT_B200_OCT0_SMALL", "SIFT_B200_OCT0_BANDS", "SIFT_B200_OCT0_BANDS+SIFT_B200_OCT0_BAND=64"]
 
 
 @pytest.mark.gpu
@@ -44,10 +45,11 @@ def test_forced_kernel_variant_meets_the_parity_bars(knob):
     env = dict(os.environ)
     for k in KNOBS:
         for part in k.split("+"):
-            env.pop(part, None)
+            env.pop(part.partition("=")[0], None)
     for part in knob.split("+"):
         if part:
-            env[part] = "1"
+            name, _, val = part.partition("=")
+            env[name] = val or "1"
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (knob, r.stdout[-2000:], r.stderr[-3000:])
     assert r.stdout.count("OK ") == 2

@@ -65,7 +65,7 @@ for pattern in (None, 0xFF, 0x00):
 print("OK strips", len(km))
 """
 
-KNOBS = ["", "SIFT_B200_OCT0_WS", "SIFT_B200_FUSED0_LO", "SIFT_B200_NO_TMA_BLUR", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD",
+KNOBS = ["", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_SMALL", "SIFT_B200_OCT0_BANDS", "SIFT_B200_FUSED0_LO", "SIFT_B200_NO_TMA_BLUR", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD",
          "SIFT_B200_NO_TMA"]
 
 
