@@ -99,25 +99,31 @@ __device__ __forceinline__ void poly_window(const TS *__restrict__ base, const i
   const double2 *__restrict__ w2 = reinterpret_cast<const double2 *>(w);
   double vw[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) { vw[k] = (double)base[k * stride]; a0[k] = 0.0; a1[k] = 0.0; }
+  for (int k = 0; k < 8; k++) vw[k] = (double)base[k * stride];
   const TS *nxt = base + 8 * stride;
-  int j = 0;
-  for (; j + 8 <= n; j += 8) {
+  {                                                          // the first tap initialises the accumulators (c * v = fma(c, v, 0))
+    const double2 c = w2[0];
 #pragma unroll
-    for (int u = 0; u < 8; u++) POLY_STEP(u, j + u)
+    for (int k = 0; k < 8; k++) { a0[k] = c.x * vw[k]; a1[k] = c.y * vw[k]; }
+    vw[0] = (double)nxt[0];
+  }
+  int j = 1;
+  for (; j + 8 <= n; j += 8) {
+    POLY_STEP(1, j) POLY_STEP(2, j + 1) POLY_STEP(3, j + 2) POLY_STEP(4, j + 3)
+    POLY_STEP(5, j + 4) POLY_STEP(6, j + 5) POLY_STEP(7, j + 6) POLY_STEP(0, j + 7)
   }
   const int rem = n - j;                                     // 0..7, uniform over the CTA
-  if (rem & 4) { POLY_STEP(0, j) POLY_STEP(1, j + 1) POLY_STEP(2, j + 2) POLY_STEP(3, j + 3) }
+  if (rem & 4) { POLY_STEP(1, j) POLY_STEP(2, j + 1) POLY_STEP(3, j + 2) POLY_STEP(4, j + 3) }
   if (rem & 2) {
-    if (rem & 4) { POLY_STEP(4, j + 4) POLY_STEP(5, j + 5) }
-    else { POLY_STEP(0, j) POLY_STEP(1, j + 1) }
+    if (rem & 4) { POLY_STEP(5, j + 4) POLY_STEP(6, j + 5) }
+    else { POLY_STEP(1, j) POLY_STEP(2, j + 1) }
   }
   if (rem & 1) {
     switch (rem & 6) {
-      case 0: POLY_STEP(0, j) break;
-      case 2: POLY_STEP(2, j + 2) break;
-      case 4: POLY_STEP(4, j + 4) break;
-      default: POLY_STEP(6, j + 6) break;
+      case 0: POLY_STEP(1, j) break;
+      case 2: POLY_STEP(3, j + 2) break;
+      case 4: POLY_STEP(5, j + 4) break;
+      default: POLY_STEP(7, j + 6) break;
     }
   }
 }
