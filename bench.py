@@ -40,7 +40,7 @@ FRAMES = 64                    # frames per GPU per step (distinct seeds)
 # `ncu --set full` captures of this round (roofline.traffic is read from this file by kernel name, null if absent)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")
 DOMINANT_KERNEL = "fused_octave0_hi_kernel"
-LANES = int(os.environ.get("SIFT_B200_LANES", "3"))   # frames in flight per GPU (engine lanes)
+LANES = int(os.environ.get("SIFT_B200_LANES", "0"))   # frames in flight per GPU (engine lanes); 0 = the engine picks by frame size
 CPU_TILE = int(os.environ.get("SIFT_BENCH_CPU_TILE", "256"))   # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
 
@@ -226,7 +226,7 @@ def extra_configs(eng, L, torch, fixtures, rank, world, dist, peak):
     entry("cfg3_batch_1024x720p", 1280, 720, 4, per, 128, 2, "strong" if world > 1 else "strong (1 GPU: the whole batch)",
           f"BASELINE configs[2]: the fixed batch of 1024 frames, {per} per GPU in contiguous blocks, no collective; "
           "the rank's frames cycle through at most 128 distinct synthetic frames (same cost per frame)")
-    entry("cfg4_3840x2160_6oct", 3840, 2160, 6, 8, 4, 3, "replicas", "BASELINE configs[3]; rank 0 only")
+    entry("cfg4_3840x2160_6oct", 3840, 2160, 6, 8, 8, 3, "replicas", "BASELINE configs[3]; rank 0 only")
     return out
 
 
@@ -445,7 +445,7 @@ def workload_config(n_gpus: int) -> dict:
                         f"(6 blur levels), sigma0={MIN_BLUR}, assumed blur {ASSUMED}, contrast 0.015 "
                         f"(reference constant), edge r=10, 2x-upsampled base octave",
             "frames_per_gpu_per_step": FRAMES, "sharding": f"images split by rank x{n_gpus}, no collective",
-            "frames_in_flight_per_gpu": LANES,
+            "frames_in_flight_per_gpu": LANES or "auto by frame size: 4 at 1920x1080, 6 at 1280x720 and 3840x2160, 8 at 512x512",
             "l2": "no flush: one frame's pyramid (735 MB algorithmic) exceeds the 126 MB L2 and frames rotate"}
 
 

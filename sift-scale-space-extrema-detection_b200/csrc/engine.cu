@@ -29,7 +29,7 @@ struct Scratch {
 // batch are dealt round-robin to lanes and their kernels overlap: the small, latency-bound launches of
 // the high octaves of one frame run next to the octave-0 launch of another, and uploads / downloads of
 // one lane overlap the kernels of the others.  The stage API and single-image calls use lane 0.
-#define SIFT_MAX_LANES 4
+#define SIFT_MAX_LANES 8
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
@@ -59,7 +59,7 @@ struct sift_ctx {
 
   Lane lanes[SIFT_MAX_LANES];
   Lane *L = nullptr;                    // lane the stage helpers address
-  int n_lanes = 3, next_lane = 0;
+  int n_lanes = 0, next_lane = 0;       // n_lanes == 0: chosen from the frame size (auto_lanes)
 
   // ---- optional per-kernel-class CUDA-event profiling (sift_set_profiling)
   bool profiling = false;
@@ -811,7 +811,7 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   const char *nt = getenv("SIFT_B200_NO_TMA");
   c->no_tma = nt && nt[0] == '1';
   const char *nl = getenv("SIFT_B200_LANES");
-  if (nl && nl[0] >= '1' && nl[0] <= '0' + SIFT_MAX_LANES) c->n_lanes = nl[0] - '0';
+  if (nl && nl[0] >= '0' && nl[0] <= '0' + SIFT_MAX_LANES) c->n_lanes = nl[0] - '0';   // 0 = by frame size
   *out = c;
   return SIFT_OK;
 }
@@ -843,6 +843,22 @@ SIFT_API void sift_destroy(sift_ctx *c)
 }
 
 SIFT_API const char *sift_last_error(const sift_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+// Frames in flight when the caller did not say: the grid of a small frame does not fill the GPU (a 512 x 512 frame
+// is 256 octave-0 tiles for 444 resident CTAs), so more of them run side by side.  Measured on the B200
+// (tools/kernel_times.py): 1080p 3 lanes = 4 lanes; 720p +6 % and 512^2 +16 % from 3 to 4 lanes, more beyond.
+static int auto_lanes(const sift_ctx *ctx)
+{
+  if (ctx->n_lanes > 0) return ctx->n_lanes;
+  const long long px = (long long)ctx->in_w * ctx->in_h;
+  // 1080p: 3 = 4 = 8 lanes (6 250 Mpixel/s); 720p: 5 500 (3) -> 5 880 (6); 512^2: 3 510 (3) -> 5 210 (8);
+  // 3840x2160 / 6 octaves: 5 920 (3) -> 6 080 (6)
+  int lanes = px >= 6000000 ? 6 : (px >= 1500000 ? 4 : (px >= 700000 ? 6 : 8));
+  // a lane holds a whole pyramid (~240 bytes per input pixel): keep the lanes of large images within ~32 GB
+  const long long per_lane = px * 240;
+  while (lanes > 1 && per_lane * lanes > (32LL << 30)) lanes--;
+  return lanes;
+}
 
 // Make the public stream wait for every lane that has work in flight (non-blocking for the host).
 static int join_lanes(sift_ctx *ctx)
@@ -886,7 +902,7 @@ SIFT_API int sift_set_keep_gaussian(sift_ctx *ctx, int keep)
 SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes)
 {
   if (!ctx) return SIFT_ERR_BAD_ARGS;
-  if (n_lanes < 1 || n_lanes > SIFT_MAX_LANES) return fail(ctx, SIFT_ERR_BAD_ARGS, "lanes %d outside 1..%d", n_lanes, SIFT_MAX_LANES);
+  if (n_lanes < 0 || n_lanes > SIFT_MAX_LANES) return fail(ctx, SIFT_ERR_BAD_ARGS, "lanes %d outside 0..%d", n_lanes, SIFT_MAX_LANES);
   int rc;
   if ((rc = sift_synchronize(ctx))) return rc;
   ctx->n_lanes = n_lanes;
@@ -996,8 +1012,10 @@ SIFT_API int sift_detect_device(sift_ctx *ctx, const void *d_image, int dtype, i
   CK(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = ensure_plan(ctx, width, height, params))) return rc;
+  const int nl_eff = auto_lanes(ctx);
+  if (ctx->next_lane >= nl_eff) ctx->next_lane = 0;
   Lane *ln = &ctx->lanes[ctx->next_lane];
-  ctx->next_lane = (ctx->next_lane + 1) % ctx->n_lanes;
+  ctx->next_lane = (ctx->next_lane + 1) % nl_eff;
   if ((rc = ensure_lane(ctx, ln))) return rc;
   ctx->L = ln;
   if (pitch_bytes == 0) pitch_bytes = (size_t)width * es;
@@ -1068,7 +1086,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
   const size_t row = (size_t)width * es;
   if (pitch_bytes == 0) pitch_bytes = row;
   if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
-  const int NL = std::min(ctx->n_lanes, n_images);
+  const int NL = std::min(auto_lanes(ctx), n_images);
   auto prepare_lanes = [&]() -> int {
     for (int l = 0; l < NL; l++) {
       Lane *ln = &ctx->lanes[l];

@@ -238,7 +238,7 @@ def test_device_resident_frames_in_flight_equal_single(engine):
     cap = 4096
     out = torch.zeros(n, cap * L.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
     cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
-    for lanes in (3, 1, 4):
+    for lanes in (3, 1, 4, 8, 0):                                # 0 = chosen by the engine from the frame size
         engine.set_lanes(lanes)
         out.zero_(); cnt.zero_()
         torch.cuda.synchronize()
@@ -252,7 +252,7 @@ def test_device_resident_frames_in_flight_equal_single(engine):
             key = lambda a: np.lexsort((a["candX"], a["candY"], a["candScale"], a["octave"]))
             assert k == len(want) and k > 5
             assert got[key(got)].tobytes() == want.tobytes()
-    engine.set_lanes(3)
+    engine.set_lanes(0)
 
 
 def test_device_resident_ordered_output(engine):

@@ -20,7 +20,7 @@ def step():
     for f in range(FR):
         eng.detect_device(frames[f].data_ptr(), L.SIFT_U8, W, H, 0, prm, out[f].data_ptr(), cap, cnt[f].data_ptr())
 
-for lanes in (1, 3):
+for lanes in (1, 3, 4, 5, 6, 8, 0):
     eng.set_lanes(lanes)
     for _ in range(3):
         step()
