@@ -47,6 +47,13 @@ struct Lane {
   OctaveDev *d_octs = nullptr;
   uint64_t plan_id = 0;        // plan the buffers above are laid out for
   bool busy = false;           // device work issued since the last join with the public stream
+  // One frame of sift_detect_batch as a CUDA graph (counter reset, every blur launch, scan, refinement): the lane's
+  // buffers do not move between frames, so the ~13 launches of a frame are replayed with one call.
+  cudaGraphExec_t frame_graph = nullptr;
+  uint64_t graph_plan = 0, graph_bufs = 0;      // plan / buffer generation the graph was captured for
+  int graph_dtype = -1, graph_keep = -1, graph_launches = 0;
+  sift_params graph_prm;
+  uint64_t buf_version = 1;    // bumped whenever one of the lane's device buffers is (re)allocated
 };
 
 struct sift_ctx {
@@ -59,6 +66,8 @@ struct sift_ctx {
 
   Lane lanes[SIFT_MAX_LANES];
   Lane *L = nullptr;                    // lane the stage helpers address
+  double kp_running = 6500;             // decaying maximum of the keypoints per frame seen by sift_detect_batch (sizes the first download)
+  bool use_graphs = true;               // SIFT_B200_NO_GRAPH=1: launch every kernel of a batch frame individually
   int n_lanes = 0, next_lane = 0;       // n_lanes == 0: chosen from the frame size (auto_lanes)
 
   // ---- optional per-kernel-class CUDA-event profiling (sift_set_profiling)
@@ -130,6 +139,7 @@ static int grow(sift_ctx *ctx, Scratch &s, size_t bytes)
   bytes = (bytes + 255) & ~(size_t)255;
   CK(cudaMalloc(&s.p, bytes));
   s.cap = bytes;
+  ctx->L->buf_version++;                 // captured frame graphs of this lane point at the old buffers
   return SIFT_OK;
 }
 
@@ -752,6 +762,69 @@ static int scan_refine_download(sift_ctx *ctx, Counters *c, sift_keypoint **kps,
   return fail(ctx, SIFT_ERR_CAPACITY, "candidate buffer kept overflowing");
 }
 
+// The device work of one batch frame on the current lane, image already in ln->image: counter reset, pyramid, scan,
+// refinement into the lane's own record buffer.
+static int issue_frame_kernels(sift_ctx *ctx, int dtype, size_t row_bytes)
+{
+  Lane *ln = ctx->L;
+  int r;
+  CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream));
+  if ((r = run_pyramid(ctx, ln->image.p, dtype, row_bytes))) return r;
+  if ((r = run_scan(ctx, 0))) return r;
+  return run_refine(ctx, -1, dev_keypoints(ctx), ln->kp_cap);
+}
+
+static bool same_thresholds(const sift_params &a, const sift_params &b)
+{
+  return same_params(a, b) && a.contrastThreshold == b.contrastThreshold && a.preFilterFactor == b.preFilterFactor &&
+         a.edgeRatio == b.edgeRatio && a.maxIterations == b.maxIterations && a.offsetBound == b.offsetBound &&
+         a.minInterpixelDistance == b.minInterpixelDistance;
+}
+
+// The same through a CUDA graph captured once per (plan, buffers, parameters): one launch call per frame.
+static int launch_frame(sift_ctx *ctx, int dtype, size_t row_bytes)
+{
+  Lane *ln = ctx->L;
+  if (!ctx->use_graphs || ctx->profiling || ctx->is_strip) return issue_frame_kernels(ctx, dtype, row_bytes);
+  const bool valid = ln->frame_graph && ln->graph_plan == ctx->plan_id && ln->graph_bufs == ln->buf_version &&
+                     ln->graph_dtype == dtype && ln->graph_keep == ctx->keep_gauss && same_thresholds(ln->graph_prm, ctx->prm);
+  if (!valid) {
+    if (ln->frame_graph) { cudaGraphExecDestroy(ln->frame_graph); ln->frame_graph = nullptr; }
+    const int64_t l0 = ctx->launches;
+    const uint64_t serial = ctx->pyramid_serial;
+    if (cudaStreamBeginCapture(ln->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return issue_frame_kernels(ctx, dtype, row_bytes);
+    }
+    const int r = issue_frame_kernels(ctx, dtype, row_bytes);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ln->stream, &g);
+    ln->graph_launches = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    ctx->pyramid_serial = serial;
+    if (r != SIFT_OK || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+      if (r != SIFT_OK) return r;
+      return issue_frame_kernels(ctx, dtype, row_bytes);          // capture refused: plain launches
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&ln->frame_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+      ln->frame_graph = nullptr;
+      (void)cudaGetLastError();
+      return issue_frame_kernels(ctx, dtype, row_bytes);
+    }
+    ln->graph_plan = ctx->plan_id; ln->graph_bufs = ln->buf_version; ln->graph_dtype = dtype;
+    ln->graph_keep = ctx->keep_gauss; ln->graph_prm = ctx->prm;
+  }
+  CK(cudaGraphLaunch(ln->frame_graph, ln->stream));
+  ctx->launches += ln->graph_launches;
+  ctx->pyramid_serial++;
+  ctx->pyramid_built = true;
+  return SIFT_OK;
+}
+
 // ------------------------------------------------------------------- C ABI ----
 extern "C" {
 
@@ -810,6 +883,8 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   c->force_old = fo && fo[0] == '1';
   const char *nt = getenv("SIFT_B200_NO_TMA");
   c->no_tma = nt && nt[0] == '1';
+  const char *ng = getenv("SIFT_B200_NO_GRAPH");
+  c->use_graphs = !(ng && ng[0] == '1');
   const char *nl = getenv("SIFT_B200_LANES");
   if (nl && nl[0] >= '0' && nl[0] <= '0' + SIFT_MAX_LANES) c->n_lanes = nl[0] - '0';   // 0 = by frame size
   *out = c;
@@ -824,6 +899,7 @@ SIFT_API void sift_destroy(sift_ctx *c)
   for (Lane &ln : c->lanes) {
     Scratch *all[] = { &ln.planes, &ln.seeds, &ln.tbuf, &ln.image, &ln.cand, &ln.outbuf, &ln.tmaps, &ln.tmaps_t, &ln.tmaps_o0, &ln.tmaps_p0, &ln.order, &ln.walks };
     for (Scratch *s : all) if (s->p) cudaFree(s->p);
+    if (ln.frame_graph) cudaGraphExecDestroy(ln.frame_graph);
     if (ln.d_octs) cudaFree(ln.d_octs);
     if (ln.h_out) cudaFreeHost(ln.h_out);
     if (ln.h_out2) cudaFreeHost(ln.h_out2);
@@ -1111,6 +1187,7 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
   int done = 0, issued = 0;     // frames consumed by the host / frames whose device work has been issued
   CK(cudaEventRecord(ctx->ev0, ctx->lanes[0].stream));
   auto take = [&](int j, int ni, const sift_stats &si) { n += ni; offsets[j + 1] = n; add_stats(total, si); };
+  int first_n[2 * SIFT_MAX_LANES] = { 0 };   // records covered by the first download of each frame in flight
 
   auto issue = [&](int i) -> int {
     const double t0 = now();
@@ -1120,12 +1197,12 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
     if (pitch_bytes == row) CK(cudaMemcpyAsync(ln->image.p, img, row * height, cudaMemcpyHostToDevice, ln->stream));
     else CK(cudaMemcpy2DAsync(ln->image.p, row, img, pitch_bytes, row, height, cudaMemcpyHostToDevice, ln->stream));
     ctx->bytes_h2d += row * height;
-    CK(cudaMemsetAsync(dev_counters(ctx), 0, sizeof(Counters), ln->stream));
     int r;
-    if ((r = run_pyramid(ctx, ln->image.p, dtype, row))) return r;
-    if ((r = run_scan(ctx, 0))) return r;
-    if ((r = run_refine(ctx, -1, dev_keypoints(ctx), ln->kp_cap))) return r;
-    const size_t first = sizeof(Counters) + (size_t)std::min(ln->kp_cap, FIRST_CHUNK) * sizeof(sift_keypoint);
+    if ((r = launch_frame(ctx, dtype, row))) return r;
+    // counters + as many records as recent frames produced (+ 25 %): one download in the common case, without
+    // shipping a fixed 8192-record block for frames that yield a thousand
+    first_n[i % (2 * SIFT_MAX_LANES)] = std::min(ln->kp_cap, std::max(256, (int)(ctx->kp_running * 1.25) + 64));
+    const size_t first = sizeof(Counters) + (size_t)first_n[i % (2 * SIFT_MAX_LANES)] * sizeof(sift_keypoint);
     CK(cudaMemcpyAsync(hbuf(ln, i), ln->outbuf.p, first, cudaMemcpyDeviceToHost, ln->stream));
     ctx->bytes_d2h += first;
     CK(cudaEventRecord(ln->ev_done, ln->stream));
@@ -1170,11 +1247,13 @@ SIFT_API int sift_detect_batch(sift_ctx *ctx, const void *images, int dtype, int
       }
       return prepare_lanes();
     }
-    if (c.n_kp > FIRST_CHUNK) {
-      const size_t first = sizeof(Counters) + (size_t)FIRST_CHUNK * sizeof(sift_keypoint);
+    ctx->kp_running = std::max((double)c.n_kp, ctx->kp_running * 0.97);
+    const int got = first_n[j % (2 * SIFT_MAX_LANES)];
+    if (c.n_kp > got) {
+      const size_t first = sizeof(Counters) + (size_t)got * sizeof(sift_keypoint);
       CK(cudaMemcpyAsync((char *)hbuf(ln, j) + first, (char *)ln->outbuf.p + first,
-                         (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ln->stream));
-      ctx->bytes_d2h += (size_t)(c.n_kp - FIRST_CHUNK) * sizeof(sift_keypoint);
+                         (size_t)(c.n_kp - got) * sizeof(sift_keypoint), cudaMemcpyDeviceToHost, ln->stream));
+      ctx->bytes_d2h += (size_t)(c.n_kp - got) * sizeof(sift_keypoint);
       CK(cudaStreamSynchronize(ln->stream));
     }
     return SIFT_OK;
