@@ -8,7 +8,7 @@ for extra in "$@"; do
   rm -f $C/$stem.o
   if ! make -C $C EXTRA="$extra" > gpurun_out/variant_build.log 2>&1; then echo "BUILD FAILED: $extra"; tail -5 gpurun_out/variant_build.log; continue; fi
   grep -A2 "scan_tma_kernelILi5ELb0" gpurun_out/variant_build.log | grep -o "Used [0-9]* registers.*" | head -1
-  python bench.py --steps 5 --warmup 3 > gpurun_out/bench_variant.log 2>&1
+  python bench.py --headline-only --steps 5 --warmup 3 > gpurun_out/bench_variant.log 2>&1
   python - "$extra" <<'PY'
 import json, sys
 l=[x for x in open("gpurun_out/bench_variant.log") if x.startswith("{")]
