@@ -396,6 +396,205 @@ fused_octave0_hi_kernel(const double *__restrict__ weights, const Fused0Args A)
   }
 }
 
+// ---- third form of the tile kernel (default for u8 / f32 sources) -------------------------------------------
+// Same tile, same two phases per level and the same arithmetic (bit-identical outputs) as the kernel above, with
+// the per-output instruction count cut down:
+//   * V pass: a thread owns TWO neighbouring output columns x 4 source rows x 2 row phases (16 accumulators as
+//     before): samples arrive as LDS.128 column pairs, the previous level as LDS.128 / STS.128 pairs and every
+//     Gaussian / DoG row leaves as ONE 8-byte store per thread (a warp writes 256 contiguous bytes per row);
+//   * H pass: its 16 outputs per item leave as 8 STS.128 (Ts rows are 16-byte aligned, pitch 66 doubles:
+//     conflict-free for lanes along rows);
+//   * per-level parameters come from shared memory and the plane pointers advance by a constant stride (no indexed
+//     constant loads behind the barriers), weights are fetched one tap ahead.
+#define F3_TPITCH (2 * F0_SW + 2)                                    // 66 doubles: rows start 16-byte aligned
+#ifndef F3_WARPS
+#define F3_WARPS 8
+#endif
+#ifndef F3_CTAS
+#define F3_CTAS 3
+#endif
+template <int NW> struct F3 {
+  static constexpr int THREADS = 32 * NW;
+  static constexpr int SH = 4 * NW;                                  // source rows per tile
+  static constexpr int SROWS = SH + 2 * F0_HALO;
+  static constexpr int TROWS = SROWS + 1;                            // +1 slack row for the window prefetch
+  static constexpr int S_FLOATS = SROWS * F0_SPITCH;
+  static constexpr int TS_OFF = (S_FLOATS / 2 + 2) & ~1;             // doubles
+  static constexpr int P_OFF = TS_OFF + TROWS * F3_TPITCH;
+  static constexpr int WV_OFF = P_OFF + 16 * THREADS;
+  static constexpr int doubles(int nlev) { return WV_OFF + 2 * nlev * 2 * F0_WSTRIDE; }
+};
+
+struct Fused3Args {
+  Fused0Args a;
+  long long plane;          // floats between consecutive Gaussian (and DoG) planes
+  long long dog_delta;      // dog[s-1] = gauss[s] + dog_delta
+};
+
+// a0[k] (row phase 0) and a1[k] (row phase 1) of 4 neighbouring source rows for a pair of columns:
+//   a_p[k] = sum_{j<n} w_p[j] v[k+j],  v[r] = the double2 at base + r * F3_TPITCH (doubles)
+#define POLY2_STEP(U, JJ)                                                                   \
+  {                                                                                         \
+    const double2 c = w2[(JJ)];                                                             \
+    _Pragma("unroll") for (int k = 0; k < 4; k++) {                                         \
+      const double2 v = vw[(k + (U)) & 3];                                                  \
+      a0[k].x = fma(c.x, v.x, a0[k].x); a0[k].y = fma(c.x, v.y, a0[k].y);                   \
+      a1[k].x = fma(c.y, v.x, a1[k].x); a1[k].y = fma(c.y, v.y, a1[k].y);                   \
+    }                                                                                       \
+    vw[(U) & 3] = *reinterpret_cast<const double2 *>(nxt + (JJ) * F3_TPITCH);               \
+  }
+__device__ __forceinline__ void poly_window2(const double *__restrict__ base, const double *__restrict__ w, const int n,
+                                             double2 (&a0)[4], double2 (&a1)[4])
+{
+  const double2 *__restrict__ w2 = reinterpret_cast<const double2 *>(w);
+  double2 vw[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) vw[k] = *reinterpret_cast<const double2 *>(base + k * F3_TPITCH);
+  const double *nxt = base + 4 * F3_TPITCH;
+  {                                                          // the first tap initialises the accumulators
+    const double2 c = w2[0];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      a0[k].x = c.x * vw[k].x; a0[k].y = c.x * vw[k].y;
+      a1[k].x = c.y * vw[k].x; a1[k].y = c.y * vw[k].y;
+    }
+    vw[0] = *reinterpret_cast<const double2 *>(nxt);
+  }
+  int j = 1;
+  for (; j + 4 <= n; j += 4) { POLY2_STEP(1, j) POLY2_STEP(2, j + 1) POLY2_STEP(3, j + 2) POLY2_STEP(0, j + 3) }
+  const int rem = n - j;                                     // 0..3, uniform over the CTA
+  if (rem & 2) { POLY2_STEP(1, j) POLY2_STEP(2, j + 1) }
+  if (rem & 1) {
+    if (rem & 2) POLY2_STEP(3, j + 2) else POLY2_STEP(1, j)
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, F3_CTAS)
+fused_octave0_hi3_kernel(const double *__restrict__ weights, const Fused3Args B)
+{
+  typedef F3<NW> G;
+  const Fused0Args &A = B.a;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int lvR[SIFT_MAX_LEVELS];
+  float *S = reinterpret_cast<float *>(smem);           // [SROWS][49] source tile (exact u8 / f32 values)
+  double *Ts = smem + G::TS_OFF;                         // [TROWS][66] horizontally blurred rows, both phases
+  double2 *P = reinterpret_cast<double2 *>(smem + G::P_OFF);   // previous level, unrounded: P[i * THREADS + tid]
+  double *Wv = smem + G::WV_OFF;                         // V-pass taps [nlev][F0_WSTRIDE]{w0, w1}
+  double *Wh = Wv + A.nlev * 2 * F0_WSTRIDE;             // H-pass taps (scaled by 1/255 for u8 sources)
+  const int tid = threadIdx.x;
+  const int a_tile = blockIdx.x * F0_SW, b_tile = blockIdx.y * G::SH;
+
+  {
+    const double hscale = A.dtype == SIFT_U8 ? 1.0 / 255.0 : 1.0;
+    for (int e = tid; e < A.nlev * 2 * F0_WSTRIDE; e += G::THREADS) {
+      const double wv = __ldg(weights + A.woff + e);
+      Wv[e] = wv;
+      Wh[e] = wv * hscale;
+    }
+    if (tid < A.nlev) lvR[tid] = A.radius[tid];
+  }
+#pragma unroll
+  for (int i = 0; i < (G::SROWS * F0_SCOLS + G::THREADS - 1) / G::THREADS; i++) {
+    const int e = tid + i * G::THREADS;
+    if ((G::SROWS * F0_SCOLS) % G::THREADS == 0 || e < G::SROWS * F0_SCOLS) {
+      const int rr = e / F0_SCOLS, cc = e - rr * F0_SCOLS;
+      const int gy = min(max(b_tile - F0_HALO + rr, 0), A.src_h - 1);          // clamp-to-edge, sift.js:116-119
+      const int gx = min(max(a_tile - F0_HALO + cc, 0), A.src_w - 1);
+      const char *row = (const char *)A.src + (size_t)gy * A.src_pitch;
+      S[rr * F0_SPITCH + cc] = A.dtype == SIFT_U8 ? (float)__ldg((const unsigned char *)row + gx) : __ldg((const float *)row + gx);
+    }
+  }
+  for (int e = tid; e < F3_TPITCH; e += G::THREADS) Ts[(G::TROWS - 1) * F3_TPITCH + e] = 0.0;    // slack row
+  if (tid < G::SROWS) S[tid * F0_SPITCH + F0_SCOLS] = 0.f;                                       // pad column
+
+  // V-pass ownership: output columns X, X+1 of the tile, source rows 4*rg .. 4*rg+3, both row phases
+  const int X = 2 * (tid & 31), rg = tid >> 5;
+  const int x = 2 * a_tile + X;
+  const int y_first = 2 * (b_tile + 4 * rg);
+  // row pairs of this thread inside the octave (its width and height are even): 0 = nothing to store
+  const int rows_ok = x < A.oct.w ? min(4, (A.oct.h - y_first) >> 1) : 0;
+  const unsigned rowp = (unsigned)A.oct.pitch;
+  float *gp_level = A.oct.gauss[0] + ((size_t)y_first * rowp + x);
+  double2 *Pt = P + tid;
+
+  for (int s = 0; s < A.nlev; s++) {                     // octave 0 blurs every level from the base (background.js:110)
+    __syncthreads();                                     // source tile + level table ready (s = 0) / Ts free again (s > 0)
+    const int R = lvR[s];
+    const int clo0 = -((R + 1) / 2);
+    const int n = R + 1 + (R & 1);                       // taps per phase incl. the phase-1 shift for odd R
+    {                                                    // ---- H pass: one row x 8 source columns x 2 phases per item
+      const int nrows = G::SH + n - 1;
+      if (tid < nrows * (F0_SW / 8)) {
+        const int g = (tid >= nrows) + (tid >= 2 * nrows) + (tid >= 3 * nrows), rr = F0_HALO + clo0 + (tid - g * nrows);
+        double a0[8], a1[8];
+        poly_window<float>(S + rr * F0_SPITCH + F0_HALO + 8 * g + clo0, 1, Wh + s * 2 * F0_WSTRIDE, n, a0, a1);
+        double2 *t = reinterpret_cast<double2 *>(Ts + rr * F3_TPITCH + 16 * g);
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = make_double2(a0[k], a1[k]);
+      }
+    }
+    __syncthreads();
+    // ---- V pass
+    double2 a0[4], a1[4];
+    poly_window2(Ts + (F0_HALO + 4 * rg + clo0) * F3_TPITCH + X, Wv + s * 2 * F0_WSTRIDE, n, a0, a1);
+    // ---- epilogue: G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) against the unrounded previous level in P
+    if (rows_ok > 0) {
+      const bool wg = A.keep_gauss != 0, wd = s > 0;
+      if (rows_ok >= 4) {
+        if (wg) {
+          float *gp = gp_level;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            *reinterpret_cast<float2 *>(gp) = make_float2((float)a0[k].x, (float)a0[k].y); gp += rowp;
+            *reinterpret_cast<float2 *>(gp) = make_float2((float)a1[k].x, (float)a1[k].y); gp += rowp;
+          }
+        }
+        if (wd) {
+          float *dp = gp_level + B.dog_delta;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const double2 p0 = Pt[k * G::THREADS], p1 = Pt[(4 + k) * G::THREADS];
+            *reinterpret_cast<float2 *>(dp) = make_float2((float)(p0.x - a0[k].x), (float)(p0.y - a0[k].y)); dp += rowp;
+            *reinterpret_cast<float2 *>(dp) = make_float2((float)(p1.x - a1[k].x), (float)(p1.y - a1[k].y)); dp += rowp;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k < rows_ok) {
+            float *gp = gp_level + (size_t)(2 * k) * rowp, *dp = gp + B.dog_delta;
+            if (wg) {
+              *reinterpret_cast<float2 *>(gp) = make_float2((float)a0[k].x, (float)a0[k].y);
+              *reinterpret_cast<float2 *>(gp + rowp) = make_float2((float)a1[k].x, (float)a1[k].y);
+            }
+            if (wd) {
+              const double2 p0 = Pt[k * G::THREADS], p1 = Pt[(4 + k) * G::THREADS];
+              *reinterpret_cast<float2 *>(dp) = make_float2((float)(p0.x - a0[k].x), (float)(p0.y - a0[k].y));
+              *reinterpret_cast<float2 *>(dp + rowp) = make_float2((float)(p1.x - a1[k].x), (float)(p1.y - a1[k].y));
+            }
+          }
+        }
+      }
+      if (s == A.spo && A.has_next) {                    // in[2a][2b] (matrix2d.js:129): even rows (phase 0), even columns (.x)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int nr = b_tile + 4 * rg + k + A.oct.seed_off;        // row of the next octave (strip-local)
+          if (k < rows_ok && nr >= 0 && nr < A.next.h) {
+            A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = a0[k].x;
+            A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)a0[k].x;
+          }
+        }
+      }
+    }
+    if (s + 1 < A.nlev) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { Pt[k * G::THREADS] = a0[k]; Pt[(4 + k) * G::THREADS] = a1[k]; }
+    }
+    gp_level += B.plane;
+  }
+}
+
 // Host: zero-padded merged polyphase taps of one level, the two phases interleaved: out[F0_WSTRIDE]{w0, w1}.
 //   phase 0: w0[j] = W0[j], j = c - floor(-R/2);  phase 1: w1[j + d] = W0[R - j], d = R & 1.
 void fused0_merge_taps(const double *w, int R, double *out)
@@ -437,9 +636,35 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
   A.u8lut = d_u8lut;
   dim3 grid((src_w + F0_SW - 1) / F0_SW, (src_h + F0_SH - 1) / F0_SH);
   static const bool no_hi = getenv("SIFT_B200_FUSED0_LO") != nullptr;
+  static const bool no_hi3 = getenv("SIFT_B200_FUSED0_HI1") != nullptr;
+  if (!no_hi && !no_hi3 && (dtype == SIFT_U8 || dtype == SIFT_F32) && nlev >= 2) {
+    // the pair-column kernel walks the planes with a constant stride: check the layout it assumes
+    Fused3Args B;
+    B.a = A;
+    B.plane = oct.gauss[1] - oct.gauss[0];
+    B.dog_delta = oct.dog[0] - oct.gauss[1];
+    bool uniform = (oct.pitch & 1) == 0 && (oct.w & 1) == 0 && (oct.h & 1) == 0 && (((uintptr_t)oct.gauss[0] | (uintptr_t)oct.dog[0]) & 7) == 0 &&
+                   (B.plane & 1) == 0;
+    for (int s = 0; s < nlev; s++) uniform = uniform && oct.gauss[s] == oct.gauss[0] + (long long)s * B.plane;
+    for (int s = 0; s + 1 < nlev; s++) uniform = uniform && oct.dog[s] == oct.gauss[s + 1] + B.dog_delta;
+    size_t smem3 = (size_t)F3<F3_WARPS>::doubles(nlev) * sizeof(double);
+    if (uniform && smem3 <= 75 * 1024) {
+      static const char *cap3 = getenv("SIFT_B200_OCT0_CTAS");
+      if (cap3 && cap3[0] == '2') smem3 = 78 * 1024;
+      dim3 grid3((src_w + F0_SW - 1) / F0_SW, (src_h + F3<F3_WARPS>::SH - 1) / F3<F3_WARPS>::SH);
+      cudaFuncSetAttribute(fused_octave0_hi3_kernel<F3_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+      fused_octave0_hi3_kernel<F3_WARPS><<<grid3, 32 * F3_WARPS, smem3, st>>>(d_weights, B);
+      return;
+    }
+  }
   if (!no_hi && (dtype == SIFT_U8 || dtype == SIFT_F32)) {
-    const size_t smem_hi = (size_t)F0H_DOUBLES(nlev) * sizeof(double);
+    size_t smem_hi = (size_t)F0H_DOUBLES(nlev) * sizeof(double);
+    // SIFT_B200_OCT0_CTAS=2: ask for more shared memory than the tile needs so that only two CTAs fit an SM and a
+    // third of its registers / shared memory stays free for the scan / refine CTAs of the other frames in flight
+    static const char *cap = getenv("SIFT_B200_OCT0_CTAS");
     if (smem_hi <= 75 * 1024) {
+      if (cap && cap[0] == '2') smem_hi = 78 * 1024;
+      if (cap && cap[0] == '1') smem_hi = 120 * 1024;
       cudaFuncSetAttribute(fused_octave0_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hi);
       fused_octave0_hi_kernel<<<grid, F0_THREADS, smem_hi, st>>>(d_weights, A);
       return;
