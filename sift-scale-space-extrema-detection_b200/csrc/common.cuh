@@ -95,6 +95,14 @@ void launch_fused_octave0(cudaStream_t st, const void *src, int dtype, size_t sr
                           const LevelPlan *plans, int poly_woff, int nlev, int spo, int keep_gauss,
                           const double *d_u8lut);
 
+// blur_mma.cu: the blur as banded-Toeplitz products on the fp64 matrix instruction (DMMA.8x8x4)
+bool mma0_supported(const LevelPlan *plans, int nlev);
+int mma0_frag_doubles(int nlev);
+void mma0_build_frags(const double *merged, int R, double *out /* mma0_frag_doubles(1) */);
+bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
+                     const OctaveDev &oct, const OctaveDev *next, const double *d_frags, const LevelPlan *plans,
+                     int nlev, int spo, int keep_gauss);
+
 // blur_oct0.cu: octave 0, second generation (column pass first, row pass last; TMA source tile)
 bool oct0_v2_supported(const LevelPlan *plans, int nlev);
 size_t oct0_out_map_bytes(int nlev);

@@ -94,6 +94,9 @@ struct sift_ctx {
   std::vector<double> h_weights;   // [0,256): u8 -> v/255.0 table, then per-level taps
   int poly_woff = 0;               // octave 0: merged polyphase tap table (blur_fused.cu)
   bool fused0 = false;             // octave 0 runs the fused polyphase kernel
+  int mma0_woff = -1;              // octave 0: per-lane band fragments of the DMMA kernel (blur_mma.cu), -1: not usable
+  bool no_mma = false;             // SIFT_B200_NO_MMA=1: scalar-FMA blur kernels everywhere
+  bool oct0_variant_forced = false;  // one of the octave-0 variant knobs is set: it wins over the DMMA kernel
   bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
   bool no_tma = false;             // SIFT_B200_NO_TMA=1: the pointer-chasing scan instead of the TMA-tiled one
   bool force_old = false;          // SIFT_B200_FORCE_OLD=1: the row-major-T fallback kernels (blur_generic.cu) everywhere
@@ -336,6 +339,15 @@ static int ensure_plan(sift_ctx *ctx, int w, int h, const sift_params *p, const 
       fused0_merge_taps(ctx->h_weights.data() + lp.woff, lp.radius, ctx->h_weights.data() + ctx->poly_woff + (size_t)s * per);
     }
   }
+  ctx->mma0_woff = -1;
+  if (ctx->fused0 && !ctx->no_mma && mma0_supported(ctx->plans[0], nlev)) {
+    const int per = fused0_taps_per_level(), fper = mma0_frag_doubles(1);
+    ctx->mma0_woff = (int)ctx->h_weights.size();
+    ctx->h_weights.resize(ctx->h_weights.size() + (size_t)mma0_frag_doubles(nlev), 0.0);
+    for (int s = 0; s < nlev; s++)
+      mma0_build_frags(ctx->h_weights.data() + ctx->poly_woff + (size_t)s * per, ctx->plans[0][s].radius,
+                       ctx->h_weights.data() + ctx->mma0_woff + (size_t)s * fper);
+  }
 
   for (int o = 0; o < n_oct; o++) { ctx->ow[o] = ow[o]; ctx->oh[o] = oh[o]; }
   // ---- weights (shared by all lanes)
@@ -511,7 +523,11 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const OctaveDev *next = (o + 1 < ctx->n_oct) ? &ctx->L->octs[o + 1] : nullptr;
   if (o == 0 && ctx->fused0) {
     prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
-    if (ctx->L->p0_maps && !ctx->L->oct0_maps && !oct0_small_supported(ctx->plans[0], ctx->nlev)) {
+    if (ctx->mma0_woff >= 0 && !ctx->oct0_variant_forced &&
+        launch_oct0_mma(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights + ctx->mma0_woff,
+                        ctx->plans[0], ctx->nlev, spo, ctx->keep_gauss)) {
+      // done
+    } else if (ctx->L->p0_maps && !ctx->L->oct0_maps && !oct0_small_supported(ctx->plans[0], ctx->nlev)) {
       ctx->launches += launch_oct0p(st, d_image, dtype, pitch_bytes, ctx->in_w, ctx->in_h, od, next, ctx->d_weights, ctx->plans[0],
                                     ctx->poly_woff, ctx->nlev, spo, ctx->keep_gauss, (double *)ctx->L->tbuf.p, ctx->L->tmaps_p0.p) - 1;
     } else if (!ctx->L->oct0_maps && oct0_small_supported(ctx->plans[0], ctx->nlev))
@@ -879,6 +895,9 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   sift_default_params(&c->prm);
   const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
+  { const char *nm = getenv("SIFT_B200_NO_MMA"); c->no_mma = nm && nm[0] == '1'; }
+  c->oct0_variant_forced = getenv("SIFT_B200_OCT0_WS") || getenv("SIFT_B200_OCT0_SMALL") || getenv("SIFT_B200_OCT0_BANDS") ||
+                           getenv("SIFT_B200_FUSED0_LO") || getenv("SIFT_B200_FUSED0_HI1") || getenv("SIFT_B200_FUSED0_HI3");
   const char *fo = getenv("SIFT_B200_FORCE_OLD");
   c->force_old = fo && fo[0] == '1';
   const char *nt = getenv("SIFT_B200_NO_TMA");
