@@ -87,6 +87,24 @@ __device__ __forceinline__ double mma0_sample(const Mma0Args &A, const char *row
   }
 }
 
+#if defined(M0_EXP_NOCVT)
+__device__ __forceinline__ float m0_cvt(double x) { return __int_as_float(__double2hiint(x)); }          // experiment: no conversion at all
+#elif defined(M0_EXP_INTCVT)
+// fp64 -> fp32 on the integer pipe (round half up, values below 2^-126 flushed to zero): 64-bit add, funnel shift
+__device__ __forceinline__ float m0_cvt(double x)
+{
+  const unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
+  const unsigned ahi = hi & 0x7fffffffu;
+  const unsigned lo2 = lo + 0x10000000u;
+  const unsigned hi2 = ahi - 0x38000000u + (lo2 < lo ? 1u : 0u);
+  unsigned r = __funnelshift_l(lo2, hi2, 3);
+  r = ahi < 0x38100000u ? 0u : r;
+  return __uint_as_float(r | (hi & 0x80000000u));
+}
+#else
+__device__ __forceinline__ float m0_cvt(double x) { return (float)x; }
+#endif
+
 // Both passes of one level for ONE WARP, no CTA barrier: the warp blurs the rows its own vertical window needs
 // (4 D + 12 rows x its 16 columns; 12 % more multiply-adds than sharing the rows across the CTA) into its private
 // 4 KB of Ts and consumes them itself, so the eight warps of a CTA drift through H pass / V pass / epilogue
@@ -205,6 +223,14 @@ oct0_mma_kernel(const Mma0Args A)
     for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
   }
   __syncthreads();                                      // source tile, level table, fragments staged: the only CTA barrier
+#ifdef M0_STAGGER
+  {                                                     // experiment: de-phase the warps that share an SM sub-partition
+    unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    const long long t0 = clock64();
+    const long long delay = (long long)M0_STAGGER * ((warp >> 2) + 2 * ((blockIdx.x + blockIdx.y) & 1));
+    while (clock64() - t0 < delay) { }
+  }
+#endif
 
   // V-pass ownership of this warp: output rows 32 wy .. +31 (source rows 16 wy .. +15), columns 16 wx .. +15
   const int wy = warp >> 2, wx = warp & 3;
@@ -231,21 +257,25 @@ oct0_mma_kernel(const Mma0Args A)
     }
     const bool wg = A.keep_gauss != 0, wd = s > 0;
     float *gl = gthr + (long long)s * A.plane;
+#ifdef M0_EXP_NOSTORE
+    if (cur[0][0][0] == 123.456 && prv[1][1][1] == 0.5) gl[0] = 1.f;
+    if (false)
+#endif
     if (interior) {
       if (wg) {
         float *r = gl;
 #pragma unroll
         for (int mb = 0; mb < 4; mb++, r += row8) {
-          *reinterpret_cast<float2 *>(r) = make_float2((float)cur[mb][0][0], (float)cur[mb][0][1]);
-          *reinterpret_cast<float2 *>(r + 8) = make_float2((float)cur[mb][1][0], (float)cur[mb][1][1]);
+          *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(cur[mb][0][0]), m0_cvt(cur[mb][0][1]));
+          *reinterpret_cast<float2 *>(r + 8) = make_float2(m0_cvt(cur[mb][1][0]), m0_cvt(cur[mb][1][1]));
         }
       }
       if (wd) {
         float *r = gl + A.dog_delta;
 #pragma unroll
         for (int mb = 0; mb < 4; mb++, r += row8) {
-          *reinterpret_cast<float2 *>(r) = make_float2((float)(prv[mb][0][0] - cur[mb][0][0]), (float)(prv[mb][0][1] - cur[mb][0][1]));
-          *reinterpret_cast<float2 *>(r + 8) = make_float2((float)(prv[mb][1][0] - cur[mb][1][0]), (float)(prv[mb][1][1] - cur[mb][1][1]));
+          *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(prv[mb][0][0] - cur[mb][0][0]), m0_cvt(prv[mb][0][1] - cur[mb][0][1]));
+          *reinterpret_cast<float2 *>(r + 8) = make_float2(m0_cvt(prv[mb][1][0] - cur[mb][1][0]), m0_cvt(prv[mb][1][1] - cur[mb][1][1]));
         }
       }
     } else {
@@ -257,10 +287,10 @@ oct0_mma_kernel(const Mma0Args A)
           for (int nb = 0; nb < 2; nb++) {
             if (x0 + 8 * nb < ow) {                     // the octave width is even: both columns or none
               float *r = gl + mb * row8 + 8 * nb;
-              if (wg) *reinterpret_cast<float2 *>(r) = make_float2((float)cur[mb][nb][0], (float)cur[mb][nb][1]);
+              if (wg) *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(cur[mb][nb][0]), m0_cvt(cur[mb][nb][1]));
               if (wd)
                 *reinterpret_cast<float2 *>(r + A.dog_delta) =
-                    make_float2((float)(prv[mb][nb][0] - cur[mb][nb][0]), (float)(prv[mb][nb][1] - cur[mb][nb][1]));
+                    make_float2(m0_cvt(prv[mb][nb][0] - cur[mb][nb][0]), m0_cvt(prv[mb][nb][1] - cur[mb][nb][1]));
             }
           }
         }
@@ -341,8 +371,406 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   A.row_shift = (oct.y_top >> 1) & 3;
   const size_t smem = (size_t)M0_SMEM_DOUBLES(nlev) * sizeof(double);
   dim3 grid((src_w + M0_SW - 1) / M0_SW, (src_h + A.row_shift + M0_SH - 1) / M0_SH);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
   oct0_mma_kernel<<<grid, M0_THREADS, smem, st>>>(A);
   return true;
+}
+
+// =====================================================================================================
+// Octaves >= 1: two passes over the octave base (the unrounded fp64 seed), all blurred levels per launch.
+//   pass A (along x)  base[y][x]  ->  T_s[y][x]   fp64, row-major (no transposition: the fragment loads of a DMMA
+//                                                  read a 4 x 8 patch of the staged tile in either orientation)
+//   pass B (along y)  T_s[y][x]   ->  G_s, D_{s-1} = G_{s-1} - G_s (fp32), seed of the next octave
+// The band of an 8-position block is  Wm[p][k] = w[k - p]  over K = 8 + taps - 1 samples; a lane's fragment of
+// chunk d is  w[4 d + t - g]  for both operand orders, read straight from the zero-padded taps in shared memory
+// (11 neighbouring doubles per load: no bank conflicts), so any radius runs the same code.
+#define MS_WFRONT 8                       // zeros in front of a level's taps (4 d + t - g >= -7)
+#define MS_WBACK 24                       // zeros behind (chunks are whole: up to 4 D + 3 - 0 taps are read)
+#define MS_THREADS 256
+
+struct MmaSepArgs {
+  const double *src;                      // octave base: dense fp64 [h][w]
+  int w, h;
+  int nlev, rmax;
+  int level[SIFT_MAX_LEVELS], radius[SIFT_MAX_LEVELS], woff[SIFT_MAX_LEVELS];   // woff: raw taps in the weight buffer
+  int wsm[SIFT_MAX_LEVELS + 1];           // offset of the level's padded taps in shared memory (doubles); [nlev] = total
+  double *T[SIFT_MAX_LEVELS];
+  size_t t_pitch;                         // doubles per T row (even)
+  int tile_pitch;                         // pass A: doubles per staged row (= 4 mod 16)
+  int buf_rows[2];                        // pass B: rows of the two staging buffers (levels 0, 2, .. / 1, 3, ..)
+  OctaveDev oct, next;
+  int has_next, spo, keep_gauss;
+  long long plane, dog_delta;
+  int row_shift;                          // pass B tiles start at row -row_shift (mosaic strips: blocks aligned with the whole image's)
+};
+
+__device__ __forceinline__ void ms_stage_taps(const double *__restrict__ weights, const MmaSepArgs &A, double *wsm)
+{
+  for (int li = 0; li < A.nlev; li++) {
+    const int n = 2 * A.radius[li] + 1, len = A.wsm[li + 1] - A.wsm[li];
+    for (int e = threadIdx.x; e < len; e += MS_THREADS)
+      wsm[A.wsm[li] + e] = (e >= MS_WFRONT && e < MS_WFRONT + n) ? __ldg(weights + A.woff[li] + e - MS_WFRONT) : 0.0;
+  }
+}
+
+__device__ __forceinline__ void ms_cp8(double *dst_smem, const double *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ms_cp16(double *dst_smem, const double *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
+// ---- pass A: CTA = 32 rows x 128 columns of every T_s; warp (wr, wc) = 16 rows (2 M blocks) x 32 columns (4 N blocks)
+#define MA_ROWS 32
+#define MA_COLS 128
+#ifndef MSA_CTAS
+#define MSA_CTAS 2
+#endif
+#ifndef MSB_CTAS
+#define MSB_CTAS 2
+#endif
+__global__ void __launch_bounds__(MS_THREADS, MSA_CTAS)
+sep_a_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
+{
+  extern __shared__ __align__(16) double smem[];
+  double *tile = smem;                                   // [32][tile_pitch]: columns x_tile - rmax .. (clamped)
+  double *wsm = smem + MA_ROWS * A.tile_pitch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int x_tile = blockIdx.x * MA_COLS, y_tile = blockIdx.y * MA_ROWS;
+  const int tp = A.tile_pitch;
+
+  const int xl = x_tile - A.rmax;                        // first staged column (rmax is rounded up to even by the host)
+  if (xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h && (A.w & 1) == 0) {
+    // interior tile: whole 16-byte pairs, pointers advanced by constants (a warp copies 4 rows)
+    const double *src = A.src + (size_t)(y_tile + warp) * A.w + xl + 2 * lane;
+    double *dst = tile + warp * tp + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < MA_ROWS / 8; i++, src += (size_t)8 * A.w, dst += 8 * tp)
+      for (int cc = 2 * lane; cc < tp; cc += 64) ms_cp16(dst + cc - 2 * lane, src + cc - 2 * lane);
+  } else {
+    for (int rr = warp; rr < MA_ROWS; rr += MS_THREADS / 32) {       // every staged column holds a (clamped) sample: finite
+      const double *row = A.src + (size_t)min(y_tile + rr, A.h - 1) * A.w;
+      double *dst = tile + rr * tp;
+      for (int cc = lane; cc < tp; cc += 32) ms_cp8(dst + cc, row + min(max(xl + cc, 0), A.w - 1));      // sift.js:116-119
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  ms_stage_taps(weights, A, wsm);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int wr = warp >> 2, wc = warp & 3;
+  const int y0 = y_tile + 16 * wr + g;                   // + 8 mb
+  const int x0 = x_tile + 32 * wc + 2 * t;               // + 8 nb
+  for (int li = 0; li < A.nlev; li++) {
+    const int R = A.radius[li];
+    const int D = (2 * R + 8 + 3) >> 2;                  // chunks of the band: ceil((taps + 7) / 4)
+    const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;        // fragment of chunk d: wp[4 d] (zero outside the taps)
+    const double *sp = tile + (16 * wr + g) * tp + (A.rmax - R) + 32 * wc + t;
+    double acc[2][4][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    // fragment d of the band meets chunk d + 2 nb of the samples of block nb: no ramp, every DMMA is useful work
+    for (int d = 0; d < D; d++) {
+      const double wv = wp[4 * d];
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        const double a0 = sp[4 * d + 8 * nb], a1 = sp[8 * tp + 4 * d + 8 * nb];
+        dmma884(acc[0][nb][0], acc[0][nb][1], a0, wv);
+        dmma884(acc[1][nb][0], acc[1][nb][1], a1, wv);
+      }
+    }
+    double *T = A.T[li];
+#pragma unroll
+    for (int mb = 0; mb < 2; mb++) {
+      const int y = y0 + 8 * mb;
+      if (y < A.h) {
+        double *trow = T + (size_t)y * A.t_pitch;
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+          const int x = x0 + 8 * nb;
+          if (x + 1 < A.w) *reinterpret_cast<double2 *>(trow + x) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+          else if (x < A.w) trow[x] = acc[mb][nb][0];
+        }
+      }
+    }
+  }
+}
+
+// ---- pass B: CTA = 64 MB rows x 32 columns; warp w = rows 8 MB w .. (MB M blocks) x 32 columns (4 N blocks).
+// Level s stages rows y_tile - R_s .. y_tile + 64 MB + R_s (+ slack, clamped) of T_s with cp.async, one level ahead
+// of the one being blurred (two buffers); the previous level stays in registers for the DoG.
+#define MB_COLS 32
+#define MB_PITCH 36                                      // = 4 (mod 16)
+#define MB_SLACK 4
+template <int MB>
+__global__ void __launch_bounds__(MS_THREADS, MSB_CTAS)
+sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
+{
+  // A CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: the tile of the NEXT step (next level, or
+  // level 0 of the next tile) is staged with cp.async while this one is blurred, and a level is written out in
+  // the shadow of the next level's DMMAs.  Measured (profiles/r02_dmma_experiments.md): one tile per CTA at two
+  // CTAs per SM beats the persistent launch (one CTA per SM: 8 warps do not cover the per-level barrier), so the
+  // host launches one CTA per tile; the loop is kept for grids that are capped.
+  constexpr int Y = 64 * MB;
+  extern __shared__ __align__(16) double smem[];
+  double *buf0 = smem, *buf1 = smem + A.buf_rows[0] * MB_PITCH;       // both sized for the largest radius
+  double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int w = A.oct.w, h = A.oct.h;
+  const int tiles_x = (w + MB_COLS - 1) / MB_COLS, tiles_y = (h + A.row_shift + Y - 1) / Y;
+  const int ntiles = tiles_x * tiles_y;
+  if ((int)blockIdx.x >= ntiles) return;
+
+  auto stage = [&](const int tile, const int li, double *buf) {      // all threads: rows y_tile - R .. of T_li
+    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
+    const int R = A.radius[li];
+    const double *T = A.T[li];
+    const int rows = Y + 2 * R + MB_SLACK;
+    const bool wide = x_tile + MB_COLS <= w;             // CTA-uniform: whole 16-byte pairs inside the rows
+    if (wide && y_tile - R >= 0 && y_tile - R + rows <= h) {
+      // interior tile: no clamping, pointers advanced by constants (16 threads per row, 16 rows per sweep)
+      const double *src = T + (size_t)(y_tile - R + (tid >> 4)) * A.t_pitch + x_tile + (tid & 15) * 2;
+      double *dst = buf + (tid >> 4) * MB_PITCH + (tid & 15) * 2;
+      const size_t sstep = (size_t)16 * A.t_pitch;
+      int rr = tid >> 4;
+      for (; rr + 48 < rows; rr += 64, src += 4 * sstep, dst += 64 * MB_PITCH) {
+        ms_cp16(dst, src); ms_cp16(dst + 16 * MB_PITCH, src + sstep);
+        ms_cp16(dst + 32 * MB_PITCH, src + 2 * sstep); ms_cp16(dst + 48 * MB_PITCH, src + 3 * sstep);
+      }
+      for (; rr < rows; rr += 16, src += sstep, dst += 16 * MB_PITCH) ms_cp16(dst, src);
+    } else {
+      for (int e = tid; e < rows * (MB_COLS / 2); e += MS_THREADS) {
+        const int rr = e >> 4, c2 = (e & 15) * 2;
+        const double *row = T + (size_t)min(max(y_tile - R + rr, 0), h - 1) * A.t_pitch;          // sift.js:116-119 clamp-to-edge
+        double *dst = buf + rr * MB_PITCH + c2;
+        if (wide) ms_cp16(dst, row + x_tile + c2);
+        else { ms_cp8(dst, row + min(x_tile + c2, w - 1)); ms_cp8(dst + 1, row + min(x_tile + c2 + 1, w - 1)); }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // level 0 of octaves >= 1 is the unblurred seed (background.js:114-130): this lane's values of a tile
+  auto load_seed = [&](const int tile, double (&sd)[MB][4][2]) {
+    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
+#pragma unroll
+    for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        const int y = min(max(y_tile + 8 * MB * warp + g + 8 * mb, 0), h - 1), x = x_tile + 2 * t + 8 * nb;
+        sd[mb][nb][0] = A.src[(size_t)y * w + min(x, w - 1)];
+        sd[mb][nb][1] = A.src[(size_t)y * w + min(x + 1, w - 1)];
+      }
+  };
+
+  int step = 0;                                          // (tile, level) steps run so far: buffer = step & 1
+  stage(blockIdx.x, 0, buf0);
+  ms_stage_taps(weights, A, wsm);
+  double seed_next[MB][4][2];
+  load_seed(blockIdx.x, seed_next);
+  const size_t row8 = (size_t)8 * A.oct.pitch;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
+    const int y0 = y_tile + 8 * MB * warp + g;           // + 8 mb
+    const int x0 = x_tile + 2 * t;                       // + 8 nb
+    const bool interior = y_tile >= 0 && y_tile + Y <= h && x_tile + MB_COLS <= w;     // CTA-uniform
+    float *gthr = A.oct.gauss[A.level[0]] + ((long long)y0 * A.oct.pitch + x0);
+    const int next_tile = tile + gridDim.x;
+
+    // G_s and D_{s-1} = G_{s-1} - G_s (sift.js:172) of block (mb, nb), from the unrounded accumulators
+    auto emit = [&](const int li, const int mb, const int nb, const double (&older)[MB][4][2], const double (&newer)[MB][4][2]) {
+      float *r = gthr + (long long)li * A.plane + mb * row8 + 8 * nb;
+      if (interior) {
+        if (A.keep_gauss) *reinterpret_cast<float2 *>(r) = make_float2((float)newer[mb][nb][0], (float)newer[mb][nb][1]);
+        *reinterpret_cast<float2 *>(r + A.dog_delta) =
+            make_float2((float)(older[mb][nb][0] - newer[mb][nb][0]), (float)(older[mb][nb][1] - newer[mb][nb][1]));
+      } else {
+        const int y = y0 + 8 * mb, x = x0 + 8 * nb;
+        if (y >= 0 && y < h) {
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+            if (x + i < w) {
+              if (A.keep_gauss) r[i] = (float)newer[mb][nb][i];
+              r[A.dog_delta + i] = (float)(older[mb][nb][i] - newer[mb][nb][i]);
+            }
+        }
+      }
+    };
+
+    // One level: stage the next step's tile, blur this one, and meanwhile write out the PREVIOUS level.
+    //   older = level li - 2, newer = level li - 1 (both unrounded), acc receives level li.
+    auto level = [&](const int li, const double (&older)[MB][4][2], const double (&newer)[MB][4][2], double (&acc)[MB][4][2]) {
+      const int R = A.radius[li];
+      const int D = (2 * R + 8 + 3) >> 2;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                   // this step's tile (and, first time, the taps) visible; the other buffer is free
+      double *other = (step & 1) ? buf0 : buf1;
+      if (li + 1 < A.nlev) stage(tile, li + 1, other);
+      else if (next_tile < ntiles) { stage(next_tile, 0, other); load_seed(next_tile, seed_next); }
+      const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;
+      const double *sp = ((step & 1) ? buf1 : buf0) + (8 * MB * warp + t) * MB_PITCH + g;
+      step++;
+#pragma unroll
+      for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+      auto chunk = [&](const int d) {                    // fragment d meets the sample rows 8 mb + 4 d + t of block mb
+        const double wv = wp[4 * d];
+#pragma unroll
+        for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+          for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], wv, sp[(8 * mb + 4 * d) * MB_PITCH + 8 * nb]);
+      };
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 4 * MB; k++) {                 // the first chunks carry one block of the previous level each
+        if (d < D) { chunk(d); d++; }
+        if (li > 0) emit(li - 1, k >> 2, k & 3, older, newer);
+      }
+      for (; d < D; d++) chunk(d);
+      if (A.has_next && A.level[li] == A.spo && (g & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
+#pragma unroll
+        for (int mb = 0; mb < MB; mb++) {
+          const int y = y0 + 8 * mb;
+          const int nr = (y >> 1) + A.oct.seed_off;      // row of the next octave (strip-local)
+          if (y >= 0 && y < h && nr >= 0 && nr < A.next.h) {
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+              const int x = x0 + 8 * nb;
+              if (x < w) {
+                A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = acc[mb][nb][0];
+                A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)acc[mb][nb][0];
+              }
+            }
+          }
+        }
+      }
+    };
+
+    double ga[MB][4][2], gb[MB][4][2], gc[MB][4][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        gb[mb][nb][0] = seed_next[mb][nb][0]; gb[mb][nb][1] = seed_next[mb][nb][1];
+        ga[mb][nb][0] = ga[mb][nb][1] = 0.0;
+      }
+    // roles rotate: (older, newer, acc) = (a, b, c) -> (b, c, a) -> (c, a, b)
+    for (int li = 0; li < A.nlev; li += 3) {
+      level(li, ga, gb, gc);
+      if (li + 1 < A.nlev) level(li + 1, gb, gc, ga); else break;
+      if (li + 2 < A.nlev) level(li + 2, gc, ga, gb); else break;
+    }
+    // the last level of the tile is written out on its own (its roles follow from its index mod 3)
+    {
+      const int last = A.nlev - 1;
+#pragma unroll
+      for (int k = 0; k < 4 * MB; k++) {
+        if (last % 3 == 0) emit(last, k >> 2, k & 3, gb, gc);
+        else if (last % 3 == 1) emit(last, k >> 2, k & 3, gc, ga);
+        else emit(last, k >> 2, k & 3, ga, gb);
+      }
+    }
+  }
+}
+
+// ---- host side of octaves >= 1 ----------------------------------------------------------------------------
+static int ms_tile_pitch(int rmax)
+{
+  int p = MA_COLS + 2 * rmax + 24;                       // + the chunks that run past the last tap (zero weights)
+  return p + ((4 - (p & 15)) & 15);                      // smallest p' >= p with p' % 16 == 4
+}
+
+static size_t ms_fill(MmaSepArgs &A, const LevelPlan *plans, int nlev_total, int w, int h, double *tbase)
+{
+  memset(&A, 0, sizeof A);
+  A.w = w; A.h = h;
+  A.nlev = nlev_total - 1;
+  A.t_pitch = (size_t)((w + 1) & ~1);
+  int off = 0;
+  for (int i = 0; i < A.nlev; i++) {
+    const LevelPlan &p = plans[1 + i];
+    A.level[i] = 1 + i; A.radius[i] = p.radius; A.woff[i] = p.woff;
+    A.rmax = A.rmax > p.radius ? A.rmax : p.radius;
+    A.wsm[i] = off;
+    off += (MS_WFRONT + 2 * p.radius + 1 + MS_WBACK + 1) & ~1;
+    A.T[i] = tbase + (size_t)i * h * A.t_pitch;
+  }
+  A.wsm[A.nlev] = off;
+  A.rmax = (A.rmax + 1) & ~1;                            // even: the staged rows of pass A start on 16-byte boundaries
+  A.tile_pitch = ms_tile_pitch(A.rmax);
+  return (size_t)A.nlev * h * A.t_pitch;
+}
+
+static void ms_buf_rows(MmaSepArgs &A, int mb)
+{
+  A.buf_rows[0] = A.buf_rows[1] = 0;
+  for (int i = 0; i < A.nlev; i++) {
+    const int rows = 64 * mb + 2 * A.radius[i] + MB_SLACK;      // steps alternate between the buffers across tiles: equal sizes
+    if (rows > A.buf_rows[0]) A.buf_rows[0] = A.buf_rows[1] = rows;
+  }
+}
+static size_t ms_smem_a(const MmaSepArgs &A) { return ((size_t)MA_ROWS * A.tile_pitch + A.wsm[A.nlev]) * sizeof(double); }
+static size_t ms_smem_b(MmaSepArgs &A, int mb)
+{
+  ms_buf_rows(A, mb);
+  return ((size_t)(A.buf_rows[0] + A.buf_rows[1]) * MB_PITCH + A.wsm[A.nlev]) * sizeof(double);
+}
+// 64-row tiles (MB = 1): 124 registers, two CTAs per SM; 128-row tiles (MB = 2) spill at that budget and measured slower
+static int ms_pick_mb(MmaSepArgs &A) { (void)A; return 1; }
+
+size_t mma_sep_t_elems(const LevelPlan *plans, int nlev, int w, int h)
+{
+  (void)plans;
+  return (size_t)(nlev - 1) * h * ((w + 1) & ~1);
+}
+
+bool mma_sep_supported(const LevelPlan *plans, int nlev, int w, int h)
+{
+  if (nlev < 2) return false;
+  MmaSepArgs A;
+  ms_fill(A, plans, nlev, w, h, nullptr);
+  for (int i = 0; i < A.nlev; i++)
+    if (A.radius[i] < 1) return false;
+  return ms_smem_a(A) <= 200 * 1024 && ms_smem_b(A, 1) <= 200 * 1024;
+}
+
+void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next, const double *d_weights,
+                    const LevelPlan *plans, double *tbase, int spo, int keep_gauss)
+{
+  MmaSepArgs A;
+  ms_fill(A, plans, oct.nlev, oct.w, oct.h, tbase);
+  A.src = oct.seed64;
+  A.oct = oct; A.next = next ? *next : oct; A.has_next = next ? 1 : 0;
+  A.spo = spo; A.keep_gauss = keep_gauss;
+  A.plane = oct.gauss[1] - oct.gauss[0];
+  A.dog_delta = oct.dog[0] - oct.gauss[1];
+  A.row_shift = oct.y_top & 7;
+  {
+    const size_t smem = ms_smem_a(A);
+    dim3 grid((oct.w + MA_COLS - 1) / MA_COLS, (oct.h + MA_ROWS - 1) / MA_ROWS);
+    cudaFuncSetAttribute(sep_a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sep_a_mma_kernel<<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+  }
+  const int mb = ms_pick_mb(A);
+  const size_t smem = ms_smem_b(A, mb);
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int ntiles = ((oct.w + MB_COLS - 1) / MB_COLS) * ((oct.h + A.row_shift + 64 * mb - 1) / (64 * mb));
+  static const bool persist = getenv("SIFT_B200_MMA_PERSIST") != nullptr;      // experiment knob: one CTA per SM
+  const int grid = (persist && ntiles > n_sm) ? n_sm : ntiles;
+  if (mb == 2) {
+    cudaFuncSetAttribute(sep_b_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sep_b_mma_kernel<2><<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+  } else {
+    cudaFuncSetAttribute(sep_b_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sep_b_mma_kernel<1><<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+  }
 }

@@ -103,6 +103,12 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
                      const OctaveDev &oct, const OctaveDev *next, const double *d_frags, const LevelPlan *plans,
                      int nlev, int spo, int keep_gauss);
 
+// octaves >= 1 as two DMMA passes (row-major fp64 intermediate)
+bool mma_sep_supported(const LevelPlan *plans, int nlev, int w, int h);
+size_t mma_sep_t_elems(const LevelPlan *plans, int nlev, int w, int h);
+void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next, const double *d_weights,
+                    const LevelPlan *plans, double *tbase, int spo, int keep_gauss);
+
 // blur_oct0.cu: octave 0, second generation (column pass first, row pass last; TMA source tile)
 bool oct0_v2_supported(const LevelPlan *plans, int nlev);
 size_t oct0_out_map_bytes(int nlev);

@@ -96,7 +96,9 @@ struct sift_ctx {
   bool fused0 = false;             // octave 0 runs the fused polyphase kernel
   int mma0_woff = -1;              // octave 0: per-lane band fragments of the DMMA kernel (blur_mma.cu), -1: not usable
   bool no_mma = false;             // SIFT_B200_NO_MMA=1: scalar-FMA blur kernels everywhere
+  bool mma_all = false;            // SIFT_B200_MMA_ALL=1: DMMA passes for every octave they support, whatever its size
   bool oct0_variant_forced = false;  // one of the octave-0 variant knobs is set: it wins over the DMMA kernel
+  bool sep_variant_forced = false;   // one of the knobs of the scalar two-pass kernels is set: they win over the DMMA passes
   bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
   bool no_tma = false;             // SIFT_B200_NO_TMA=1: the pointer-chasing scan instead of the TMA-tiled one
   bool force_old = false;          // SIFT_B200_FORCE_OLD=1: the row-major-T fallback kernels (blur_generic.cu) everywhere
@@ -384,6 +386,8 @@ static int ensure_lane(sift_ctx *ctx, Lane *ln)
     const size_t tl = (o == 0) ? nlev : nlev - 1;
     if (o > 0 || !ctx->fused0)
       t_bytes = std::max(t_bytes, std::max(tl * trows * ow[o], sep_t_elems(ow[o], oh[o], (int)trows, ctx->plans[o], o == 0 ? 0 : 1, nlev)) * sizeof(double));
+    if (o > 0 && !ctx->no_mma && mma_sep_supported(ctx->plans[o], nlev, ow[o], oh[o]))
+      t_bytes = std::max(t_bytes, mma_sep_t_elems(ctx->plans[o], nlev, ow[o], oh[o]) * sizeof(double));
   }
   const bool want_p0 = ctx->fused0 && !ctx->no_tma && oct0p_supported(ctx->plans[0], nlev);
   if (want_p0) t_bytes = std::max(t_bytes, oct0p_t_bytes(w, h, nlev));
@@ -546,6 +550,14 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const int first = (o == 0) ? 0 : 1;
   const int hrows = (o == 0) ? ctx->in_h : od.h;
   prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
+  // small octaves: too few tiles for the DMMA passes to fill the SMs, the scalar two-pass kernels are faster there
+  if (o > 0 && !ctx->no_mma && !ctx->force_old && !ctx->force_generic && !ctx->sep_variant_forced &&
+      ((long long)od.w * od.h >= (1 << 18) || ctx->mma_all) && mma_sep_supported(ctx->plans[o], ctx->nlev, od.w, od.h)) {
+    launch_mma_sep(st, od, next, ctx->d_weights, ctx->plans[o], (double *)ctx->L->tbuf.p, spo, ctx->keep_gauss);
+    ctx->launches += 2;
+    prof_end(ctx);
+    return;
+  }
   if (!ctx->force_old && sep_supported(ctx->plans[o], first, ctx->nlev, od.w, od.h)) {
     double *tb = (double *)ctx->L->tbuf.p;
     const void *tm = (o > 0 && ctx->L->tma_blur[o] >= 0) ? (const char *)ctx->L->tmaps_t.p + sep_tma_map_bytes(ctx->L->tma_blur[o]) : nullptr;
@@ -896,6 +908,8 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
   { const char *nm = getenv("SIFT_B200_NO_MMA"); c->no_mma = nm && nm[0] == '1'; }
+  c->mma_all = getenv("SIFT_B200_MMA_ALL") != nullptr;
+  c->sep_variant_forced = getenv("SIFT_B200_NO_TMA") || getenv("SIFT_B200_NO_TMA_BLUR") || getenv("SIFT_B200_FIR_NO8");
   c->oct0_variant_forced = getenv("SIFT_B200_OCT0_WS") || getenv("SIFT_B200_OCT0_SMALL") || getenv("SIFT_B200_OCT0_BANDS") ||
                            getenv("SIFT_B200_FUSED0_LO") || getenv("SIFT_B200_FUSED0_HI1") || getenv("SIFT_B200_FUSED0_HI3");
   const char *fo = getenv("SIFT_B200_FORCE_OLD");
