@@ -87,23 +87,7 @@ __device__ __forceinline__ double mma0_sample(const Mma0Args &A, const char *row
   }
 }
 
-#if defined(M0_EXP_NOCVT)
-__device__ __forceinline__ float m0_cvt(double x) { return __int_as_float(__double2hiint(x)); }          // experiment: no conversion at all
-#elif defined(M0_EXP_INTCVT)
-// fp64 -> fp32 on the integer pipe (round half up, values below 2^-126 flushed to zero): 64-bit add, funnel shift
-__device__ __forceinline__ float m0_cvt(double x)
-{
-  const unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
-  const unsigned ahi = hi & 0x7fffffffu;
-  const unsigned lo2 = lo + 0x10000000u;
-  const unsigned hi2 = ahi - 0x38000000u + (lo2 < lo ? 1u : 0u);
-  unsigned r = __funnelshift_l(lo2, hi2, 3);
-  r = ahi < 0x38100000u ? 0u : r;
-  return __uint_as_float(r | (hi & 0x80000000u));
-}
-#else
 __device__ __forceinline__ float m0_cvt(double x) { return (float)x; }
-#endif
 
 // Both passes of one level for ONE WARP, no CTA barrier: the warp blurs the rows its own vertical window needs
 // (4 D + 12 rows x its 16 columns; 12 % more multiply-adds than sharing the rows across the CTA) into its private
@@ -223,14 +207,6 @@ oct0_mma_kernel(const Mma0Args A)
     for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
   }
   __syncthreads();                                      // source tile, level table, fragments staged: the only CTA barrier
-#ifdef M0_STAGGER
-  {                                                     // experiment: de-phase the warps that share an SM sub-partition
-    unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    const long long t0 = clock64();
-    const long long delay = (long long)M0_STAGGER * ((warp >> 2) + 2 * ((blockIdx.x + blockIdx.y) & 1));
-    while (clock64() - t0 < delay) { }
-  }
-#endif
 
   // V-pass ownership of this warp: output rows 32 wy .. +31 (source rows 16 wy .. +15), columns 16 wx .. +15
   const int wy = warp >> 2, wx = warp & 3;
@@ -257,10 +233,6 @@ oct0_mma_kernel(const Mma0Args A)
     }
     const bool wg = A.keep_gauss != 0, wd = s > 0;
     float *gl = gthr + (long long)s * A.plane;
-#ifdef M0_EXP_NOSTORE
-    if (cur[0][0][0] == 123.456 && prv[1][1][1] == 0.5) gl[0] = 1.f;
-    if (false)
-#endif
     if (interior) {
       if (wg) {
         float *r = gl;
@@ -512,26 +484,19 @@ template <int MB>
 __global__ void __launch_bounds__(MS_THREADS, MSB_CTAS)
 sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
 {
-  // A CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: the tile of the NEXT step (next level, or
-  // level 0 of the next tile) is staged with cp.async while this one is blurred, and a level is written out in
-  // the shadow of the next level's DMMAs.  Measured (profiles/r02_dmma_experiments.md): one tile per CTA at two
-  // CTAs per SM beats the persistent launch (one CTA per SM: 8 warps do not cover the per-level barrier), so the
-  // host launches one CTA per tile; the loop is kept for grids that are capped.
   constexpr int Y = 64 * MB;
   extern __shared__ __align__(16) double smem[];
-  double *buf0 = smem, *buf1 = smem + A.buf_rows[0] * MB_PITCH;       // both sized for the largest radius
+  double *buf0 = smem, *buf1 = smem + A.buf_rows[0] * MB_PITCH;
   double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int x_tile = blockIdx.x * MB_COLS, y_tile = blockIdx.y * Y - A.row_shift;
   const int w = A.oct.w, h = A.oct.h;
-  const int tiles_x = (w + MB_COLS - 1) / MB_COLS, tiles_y = (h + A.row_shift + Y - 1) / Y;
-  const int ntiles = tiles_x * tiles_y;
-  if ((int)blockIdx.x >= ntiles) return;
 
-  auto stage = [&](const int tile, const int li, double *buf) {      // all threads: rows y_tile - R .. of T_li
-    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
+  auto stage = [&](const int li) {                       // all threads: rows y_tile - R .. of T_li into its buffer
     const int R = A.radius[li];
     const double *T = A.T[li];
+    double *buf = (li & 1) ? buf1 : buf0;
     const int rows = Y + 2 * R + MB_SLACK;
     const bool wide = x_tile + MB_COLS <= w;             // CTA-uniform: whole 16-byte pairs inside the rows
     if (wide && y_tile - R >= 0 && y_tile - R + rows <= h) {
@@ -556,127 +521,107 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  // level 0 of octaves >= 1 is the unblurred seed (background.js:114-130): this lane's values of a tile
-  auto load_seed = [&](const int tile, double (&sd)[MB][4][2]) {
-    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
+  stage(0);
+  ms_stage_taps(weights, A, wsm);
+
+  const int y0 = y_tile + 8 * MB * warp + g;             // + 8 mb
+  const int x0 = x_tile + 2 * t;                         // + 8 nb
+  const bool interior = y_tile >= 0 && y_tile + Y <= h && x_tile + MB_COLS <= w;     // CTA-uniform
+  const size_t row8 = (size_t)8 * A.oct.pitch;
+  float *gthr = A.oct.gauss[A.level[0]] + ((long long)y0 * A.oct.pitch + x0);
+
+  // G_s and D_{s-1} = G_{s-1} - G_s (sift.js:172) of block (mb, nb), from the unrounded accumulators
+  auto emit = [&](const int li, const int mb, const int nb, const double (&older)[MB][4][2], const double (&newer)[MB][4][2]) {
+    float *r = gthr + (long long)li * A.plane + mb * row8 + 8 * nb;
+    if (interior) {
+      if (A.keep_gauss) *reinterpret_cast<float2 *>(r) = make_float2((float)newer[mb][nb][0], (float)newer[mb][nb][1]);
+      *reinterpret_cast<float2 *>(r + A.dog_delta) =
+          make_float2((float)(older[mb][nb][0] - newer[mb][nb][0]), (float)(older[mb][nb][1] - newer[mb][nb][1]));
+    } else {
+      const int y = y0 + 8 * mb, x = x0 + 8 * nb;
+      if (y >= 0 && y < h) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+          if (x + i < w) {
+            if (A.keep_gauss) r[i] = (float)newer[mb][nb][i];
+            r[A.dog_delta + i] = (float)(older[mb][nb][i] - newer[mb][nb][i]);
+          }
+      }
+    }
+  };
+
+  // One level: stage the next tile, blur this one, and meanwhile write out the PREVIOUS level (its conversions and
+  // stores ride in the shadow of this level's DMMAs instead of idling the pipe between two levels).
+  //   older = level li - 2, newer = level li - 1 (both unrounded), acc receives level li.
+  auto level = [&](const int li, const double (&older)[MB][4][2], const double (&newer)[MB][4][2], double (&acc)[MB][4][2]) {
+    const int R = A.radius[li];
+    const int D = (2 * R + 8 + 3) >> 2;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                     // tile li (and, first time, the taps) visible; the other buffer is free
+    if (li + 1 < A.nlev) stage(li + 1);
+    const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;
+    const double *sp = ((li & 1) ? buf1 : buf0) + (8 * MB * warp + t) * MB_PITCH + g;
 #pragma unroll
     for (int mb = 0; mb < MB; mb++)
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        const int y = min(max(y_tile + 8 * MB * warp + g + 8 * mb, 0), h - 1), x = x_tile + 2 * t + 8 * nb;
-        sd[mb][nb][0] = A.src[(size_t)y * w + min(x, w - 1)];
-        sd[mb][nb][1] = A.src[(size_t)y * w + min(x + 1, w - 1)];
-      }
-  };
-
-  int step = 0;                                          // (tile, level) steps run so far: buffer = step & 1
-  stage(blockIdx.x, 0, buf0);
-  ms_stage_taps(weights, A, wsm);
-  double seed_next[MB][4][2];
-  load_seed(blockIdx.x, seed_next);
-  const size_t row8 = (size_t)8 * A.oct.pitch;
-
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int x_tile = (tile % tiles_x) * MB_COLS, y_tile = (tile / tiles_x) * Y - A.row_shift;
-    const int y0 = y_tile + 8 * MB * warp + g;           // + 8 mb
-    const int x0 = x_tile + 2 * t;                       // + 8 nb
-    const bool interior = y_tile >= 0 && y_tile + Y <= h && x_tile + MB_COLS <= w;     // CTA-uniform
-    float *gthr = A.oct.gauss[A.level[0]] + ((long long)y0 * A.oct.pitch + x0);
-    const int next_tile = tile + gridDim.x;
-
-    // G_s and D_{s-1} = G_{s-1} - G_s (sift.js:172) of block (mb, nb), from the unrounded accumulators
-    auto emit = [&](const int li, const int mb, const int nb, const double (&older)[MB][4][2], const double (&newer)[MB][4][2]) {
-      float *r = gthr + (long long)li * A.plane + mb * row8 + 8 * nb;
-      if (interior) {
-        if (A.keep_gauss) *reinterpret_cast<float2 *>(r) = make_float2((float)newer[mb][nb][0], (float)newer[mb][nb][1]);
-        *reinterpret_cast<float2 *>(r + A.dog_delta) =
-            make_float2((float)(older[mb][nb][0] - newer[mb][nb][0]), (float)(older[mb][nb][1] - newer[mb][nb][1]));
-      } else {
-        const int y = y0 + 8 * mb, x = x0 + 8 * nb;
-        if (y >= 0 && y < h) {
-#pragma unroll
-          for (int i = 0; i < 2; i++)
-            if (x + i < w) {
-              if (A.keep_gauss) r[i] = (float)newer[mb][nb][i];
-              r[A.dog_delta + i] = (float)(older[mb][nb][i] - newer[mb][nb][i]);
-            }
-        }
-      }
-    };
-
-    // One level: stage the next step's tile, blur this one, and meanwhile write out the PREVIOUS level.
-    //   older = level li - 2, newer = level li - 1 (both unrounded), acc receives level li.
-    auto level = [&](const int li, const double (&older)[MB][4][2], const double (&newer)[MB][4][2], double (&acc)[MB][4][2]) {
-      const int R = A.radius[li];
-      const int D = (2 * R + 8 + 3) >> 2;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();                                   // this step's tile (and, first time, the taps) visible; the other buffer is free
-      double *other = (step & 1) ? buf0 : buf1;
-      if (li + 1 < A.nlev) stage(tile, li + 1, other);
-      else if (next_tile < ntiles) { stage(next_tile, 0, other); load_seed(next_tile, seed_next); }
-      const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;
-      const double *sp = ((step & 1) ? buf1 : buf0) + (8 * MB * warp + t) * MB_PITCH + g;
-      step++;
+      for (int nb = 0; nb < 4; nb++) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    auto chunk = [&](const int d) {                      // fragment d meets the sample rows 8 mb + 4 d + t of block mb
+      const double wv = wp[4 * d];
 #pragma unroll
       for (int mb = 0; mb < MB; mb++)
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-      auto chunk = [&](const int d) {                    // fragment d meets the sample rows 8 mb + 4 d + t of block mb
-        const double wv = wp[4 * d];
+        for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], wv, sp[(8 * mb + 4 * d) * MB_PITCH + 8 * nb]);
+    };
+    int d = 0;
 #pragma unroll
-        for (int mb = 0; mb < MB; mb++)
+    for (int k = 0; k < 4 * MB; k++) {                   // the first chunks carry one block of the previous level each
+      if (d < D) { chunk(d); d++; }
+      if (li > 0) emit(li - 1, k >> 2, k & 3, older, newer);
+    }
+    for (; d < D; d++) chunk(d);
+    if (A.has_next && A.level[li] == A.spo && (g & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
 #pragma unroll
-          for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], wv, sp[(8 * mb + 4 * d) * MB_PITCH + 8 * nb]);
-      };
-      int d = 0;
+      for (int mb = 0; mb < MB; mb++) {
+        const int y = y0 + 8 * mb;
+        const int nr = (y >> 1) + A.oct.seed_off;        // row of the next octave (strip-local)
+        if (y >= 0 && y < h && nr >= 0 && nr < A.next.h) {
 #pragma unroll
-      for (int k = 0; k < 4 * MB; k++) {                 // the first chunks carry one block of the previous level each
-        if (d < D) { chunk(d); d++; }
-        if (li > 0) emit(li - 1, k >> 2, k & 3, older, newer);
-      }
-      for (; d < D; d++) chunk(d);
-      if (A.has_next && A.level[li] == A.spo && (g & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
-#pragma unroll
-        for (int mb = 0; mb < MB; mb++) {
-          const int y = y0 + 8 * mb;
-          const int nr = (y >> 1) + A.oct.seed_off;      // row of the next octave (strip-local)
-          if (y >= 0 && y < h && nr >= 0 && nr < A.next.h) {
-#pragma unroll
-            for (int nb = 0; nb < 4; nb++) {
-              const int x = x0 + 8 * nb;
-              if (x < w) {
-                A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = acc[mb][nb][0];
-                A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)acc[mb][nb][0];
-              }
+          for (int nb = 0; nb < 4; nb++) {
+            const int x = x0 + 8 * nb;
+            if (x < w) {
+              A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = acc[mb][nb][0];
+              A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)acc[mb][nb][0];
             }
           }
         }
       }
-    };
-
-    double ga[MB][4][2], gb[MB][4][2], gc[MB][4][2];
-#pragma unroll
-    for (int mb = 0; mb < MB; mb++)
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        gb[mb][nb][0] = seed_next[mb][nb][0]; gb[mb][nb][1] = seed_next[mb][nb][1];
-        ga[mb][nb][0] = ga[mb][nb][1] = 0.0;
-      }
-    // roles rotate: (older, newer, acc) = (a, b, c) -> (b, c, a) -> (c, a, b)
-    for (int li = 0; li < A.nlev; li += 3) {
-      level(li, ga, gb, gc);
-      if (li + 1 < A.nlev) level(li + 1, gb, gc, ga); else break;
-      if (li + 2 < A.nlev) level(li + 2, gc, ga, gb); else break;
     }
-    // the last level of the tile is written out on its own (its roles follow from its index mod 3)
-    {
-      const int last = A.nlev - 1;
+  };
+
+  double ga[MB][4][2], gb[MB][4][2], gc[MB][4][2];
 #pragma unroll
-      for (int k = 0; k < 4 * MB; k++) {
-        if (last % 3 == 0) emit(last, k >> 2, k & 3, gb, gc);
-        else if (last % 3 == 1) emit(last, k >> 2, k & 3, gc, ga);
-        else emit(last, k >> 2, k & 3, ga, gb);
-      }
+  for (int mb = 0; mb < MB; mb++)
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {                     // level 0 of octaves >= 1 is the unblurred seed (background.js:114-130)
+      const int y = min(max(y0 + 8 * mb, 0), h - 1), x = x0 + 8 * nb;
+      gb[mb][nb][0] = A.src[(size_t)y * w + min(x, w - 1)];
+      gb[mb][nb][1] = A.src[(size_t)y * w + min(x + 1, w - 1)];
+      ga[mb][nb][0] = ga[mb][nb][1] = 0.0;
+    }
+  // roles rotate: (older, newer, acc) = (a, b, c) -> (b, c, a) -> (c, a, b)
+  for (int li = 0; li < A.nlev; li += 3) {
+    level(li, ga, gb, gc);
+    if (li + 1 < A.nlev) level(li + 1, gb, gc, ga); else break;
+    if (li + 2 < A.nlev) level(li + 2, gc, ga, gb); else break;
+  }
+  // the last level is written out on its own (its roles follow from its index mod 3)
+  {
+    const int last = A.nlev - 1;
+#pragma unroll
+    for (int k = 0; k < 4 * MB; k++) {
+      if (last % 3 == 0) emit(last, k >> 2, k & 3, gb, gc);
+      else if (last % 3 == 1) emit(last, k >> 2, k & 3, gc, ga);
+      else emit(last, k >> 2, k & 3, ga, gb);
     }
   }
 }
@@ -713,8 +658,8 @@ static void ms_buf_rows(MmaSepArgs &A, int mb)
 {
   A.buf_rows[0] = A.buf_rows[1] = 0;
   for (int i = 0; i < A.nlev; i++) {
-    const int rows = 64 * mb + 2 * A.radius[i] + MB_SLACK;      // steps alternate between the buffers across tiles: equal sizes
-    if (rows > A.buf_rows[0]) A.buf_rows[0] = A.buf_rows[1] = rows;
+    const int rows = 64 * mb + 2 * A.radius[i] + MB_SLACK;
+    if (rows > A.buf_rows[i & 1]) A.buf_rows[i & 1] = rows;
   }
 }
 static size_t ms_smem_a(const MmaSepArgs &A) { return ((size_t)MA_ROWS * A.tile_pitch + A.wsm[A.nlev]) * sizeof(double); }
@@ -761,11 +706,7 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   }
   const int mb = ms_pick_mb(A);
   const size_t smem = ms_smem_b(A, mb);
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-  const int ntiles = ((oct.w + MB_COLS - 1) / MB_COLS) * ((oct.h + A.row_shift + 64 * mb - 1) / (64 * mb));
-  static const bool persist = getenv("SIFT_B200_MMA_PERSIST") != nullptr;      // experiment knob: one CTA per SM
-  const int grid = (persist && ntiles > n_sm) ? n_sm : ntiles;
+  dim3 grid((oct.w + MB_COLS - 1) / MB_COLS, (oct.h + A.row_shift + 64 * mb - 1) / (64 * mb));
   if (mb == 2) {
     cudaFuncSetAttribute(sep_b_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sep_b_mma_kernel<2><<<grid, MS_THREADS, smem, st>>>(d_weights, A);
