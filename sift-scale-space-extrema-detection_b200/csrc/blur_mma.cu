@@ -93,7 +93,7 @@ __device__ __forceinline__ float m0_cvt(double x) { return (float)x; }
 // (4 D + 12 rows x its 16 columns; 12 % more multiply-adds than sharing the rows across the CTA) into its private
 // 4 KB of Ts and consumes them itself, so the eight warps of a CTA drift through H pass / V pass / epilogue
 // independently and cover each other's latencies.  D = chunks of the band (CTA-uniform), acc = the warp's 32 x 16 outputs.
-// Ts layout: [32 rows][16 columns], column index XOR-swizzled by the row (8 (r & 1) + 4 ((r >> 1) & 1)): the
+// Ts layout: [32 rows][16 columns], column index XOR-swizzled by the row (8 (r & 1) + 2 ((r >> 1) & 1)): the
 // H-pass 16-byte stores (lanes along rows) and the V-pass 8-byte loads (lanes along 4 rows x 8 columns) are both
 // conflict-free without padding.
 template <int D>
@@ -131,7 +131,7 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
       }
     }
     __syncwarp();                                       // the previous level's V pass has read Tw
-    const int sw = 8 * (g & 1) + 4 * ((g >> 1) & 1);
+    const int sw = 8 * (g & 1) + 2 * ((g >> 1) & 1);
     double *tp = Tw + g * 16;
 #pragma unroll
     for (int mb = 0; mb < MBH; mb++)
@@ -142,8 +142,11 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
   __syncwarp();
   // ---- V pass: 4 M blocks (4 source rows x 2 phases = 8 output rows each) x 2 N blocks (8 columns each)
   {
-    const int sw = 8 * (t & 1) + 4 * (t >> 1);
-    const double *tp0 = Tw + t * 16 + (g ^ sw), *tp1 = Tw + t * 16 + ((g ^ sw) ^ 8);
+    // N block nb takes the columns {0,1, 4,5, 8,9, 12,13} + 2 nb of the warp's 16: a lane's two blocks then hold FOUR
+    // neighbouring columns of one row (one 16-byte store per row and plane instead of two 8-byte ones)
+    const int sw = 8 * (t & 1) + 2 * (t >> 1);
+    const int col = 4 * (g >> 1) + (g & 1);
+    const double *tp0 = Tw + t * 16 + (col ^ sw), *tp1 = Tw + t * 16 + ((col + 2) ^ sw);
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -211,7 +214,7 @@ oct0_mma_kernel(const Mma0Args A)
   // V-pass ownership of this warp: output rows 32 wy .. +31 (source rows 16 wy .. +15), columns 16 wx .. +15
   const int wy = warp >> 2, wx = warp & 3;
   const int y0 = 2 * (b_tile + 16 * wy) + g;            // + 8 mb: output row of fragment row g
-  const int x0 = 2 * a_tile + 16 * wx + 2 * t;          // + 8 nb: first of the two columns of this lane
+  const int x0 = 2 * a_tile + 16 * wx + 4 * t;          // first of this lane's four columns: block 0 holds x0, x0 + 1, block 1 x0 + 2, x0 + 3
   const int ow = A.oct.w, oh = A.oct.h;
   const size_t row8 = (size_t)8 * A.oct.pitch;
   const bool interior = b_tile >= 0 && 2 * (b_tile + M0_SH) <= oh && 2 * (a_tile + M0_SW) <= ow;   // CTA-uniform
@@ -237,18 +240,15 @@ oct0_mma_kernel(const Mma0Args A)
       if (wg) {
         float *r = gl;
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++, r += row8) {
-          *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(cur[mb][0][0]), m0_cvt(cur[mb][0][1]));
-          *reinterpret_cast<float2 *>(r + 8) = make_float2(m0_cvt(cur[mb][1][0]), m0_cvt(cur[mb][1][1]));
-        }
+        for (int mb = 0; mb < 4; mb++, r += row8)
+          *reinterpret_cast<float4 *>(r) = make_float4(m0_cvt(cur[mb][0][0]), m0_cvt(cur[mb][0][1]), m0_cvt(cur[mb][1][0]), m0_cvt(cur[mb][1][1]));
       }
       if (wd) {
         float *r = gl + A.dog_delta;
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++, r += row8) {
-          *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(prv[mb][0][0] - cur[mb][0][0]), m0_cvt(prv[mb][0][1] - cur[mb][0][1]));
-          *reinterpret_cast<float2 *>(r + 8) = make_float2(m0_cvt(prv[mb][1][0] - cur[mb][1][0]), m0_cvt(prv[mb][1][1] - cur[mb][1][1]));
-        }
+        for (int mb = 0; mb < 4; mb++, r += row8)
+          *reinterpret_cast<float4 *>(r) = make_float4(m0_cvt(prv[mb][0][0] - cur[mb][0][0]), m0_cvt(prv[mb][0][1] - cur[mb][0][1]),
+                                                       m0_cvt(prv[mb][1][0] - cur[mb][1][0]), m0_cvt(prv[mb][1][1] - cur[mb][1][1]));
       }
     } else {
 #pragma unroll
@@ -257,8 +257,8 @@ oct0_mma_kernel(const Mma0Args A)
         if (y >= 0 && y < oh) {
 #pragma unroll
           for (int nb = 0; nb < 2; nb++) {
-            if (x0 + 8 * nb < ow) {                     // the octave width is even: both columns or none
-              float *r = gl + mb * row8 + 8 * nb;
+            if (x0 + 2 * nb < ow) {                     // the octave width is even: both columns or none
+              float *r = gl + mb * row8 + 2 * nb;
               if (wg) *reinterpret_cast<float2 *>(r) = make_float2(m0_cvt(cur[mb][nb][0]), m0_cvt(cur[mb][nb][1]));
               if (wd)
                 *reinterpret_cast<float2 *>(r + A.dog_delta) =
@@ -276,7 +276,7 @@ oct0_mma_kernel(const Mma0Args A)
         if (y >= 0 && y < oh && nr >= 0 && nr < A.next.h) {
 #pragma unroll
           for (int nb = 0; nb < 2; nb++) {
-            const int x = x0 + 8 * nb;
+            const int x = x0 + 2 * nb;
             if (x < ow) {
               A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = cur[mb][nb][0];
               A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)cur[mb][nb][0];
@@ -330,8 +330,8 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   A.plane = oct.gauss[1] - oct.gauss[0];
   A.dog_delta = oct.dog[0] - oct.gauss[1];
   // the kernel walks the planes with a constant stride and stores column pairs: check the layout it assumes
-  bool ok = (oct.pitch & 1) == 0 && (oct.w & 1) == 0 && (oct.h & 1) == 0 && (A.plane & 1) == 0 && (A.dog_delta & 1) == 0 &&
-            (((uintptr_t)oct.gauss[0]) & 7) == 0;
+  bool ok = (oct.pitch & 3) == 0 && (oct.w & 1) == 0 && (oct.h & 1) == 0 && (A.plane & 3) == 0 && (A.dog_delta & 3) == 0 &&
+            (((uintptr_t)oct.gauss[0]) & 15) == 0;
   for (int s = 0; s < nlev; s++) ok = ok && oct.gauss[s] == oct.gauss[0] + (long long)s * A.plane;
   for (int s = 0; s + 1 < nlev; s++) ok = ok && oct.dog[s] == oct.gauss[s + 1] + A.dog_delta;
   if (!ok) return false;
