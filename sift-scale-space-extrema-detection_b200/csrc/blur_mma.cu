@@ -478,7 +478,10 @@ sep_a_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
 // Level s stages rows y_tile - R_s .. y_tile + 64 MB + R_s (+ slack, clamped) of T_s with cp.async, one level ahead
 // of the one being blurred (two buffers); the previous level stays in registers for the DoG.
 #define MB_COLS 32
-#define MB_PITCH 36                                      // = 4 (mod 16)
+#define MB_PITCH 32                                      // dense rows; the column index is XOR-swizzled by the row (see MB_SWZ)
+// rows r, r+1, r+2, r+3 of a chunk are read by the lanes t = 0..3 at the columns {0,1,4,5,..} of an N block: the
+// offsets 0, 8, 2, 10 keep the four column sets on distinct 8-byte banks, and 16-byte pairs stay together
+#define MB_SWZ(r) (8 * ((r) & 1) + 2 * (((r) >> 1) & 1))
 #define MB_SLACK 4
 template <int MB>
 __global__ void __launch_bounds__(MS_THREADS, MSB_CTAS)
@@ -502,7 +505,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     if (wide && y_tile - R >= 0 && y_tile - R + rows <= h) {
       // interior tile: no clamping, pointers advanced by constants (16 threads per row, 16 rows per sweep)
       const double *src = T + (size_t)(y_tile - R + (tid >> 4)) * A.t_pitch + x_tile + (tid & 15) * 2;
-      double *dst = buf + (tid >> 4) * MB_PITCH + (tid & 15) * 2;
+      double *dst = buf + (tid >> 4) * MB_PITCH + (((tid & 15) * 2) ^ MB_SWZ(tid >> 4));
       const size_t sstep = (size_t)16 * A.t_pitch;
       int rr = tid >> 4;
       for (; rr + 48 < rows; rr += 64, src += 4 * sstep, dst += 64 * MB_PITCH) {
@@ -514,7 +517,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
       for (int e = tid; e < rows * (MB_COLS / 2); e += MS_THREADS) {
         const int rr = e >> 4, c2 = (e & 15) * 2;
         const double *row = T + (size_t)min(max(y_tile - R + rr, 0), h - 1) * A.t_pitch;          // sift.js:116-119 clamp-to-edge
-        double *dst = buf + rr * MB_PITCH + c2;
+        double *dst = buf + rr * MB_PITCH + (c2 ^ MB_SWZ(rr));
         if (wide) ms_cp16(dst, row + x_tile + c2);
         else { ms_cp8(dst, row + min(x_tile + c2, w - 1)); ms_cp8(dst + 1, row + min(x_tile + c2 + 1, w - 1)); }
       }
@@ -525,26 +528,30 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   ms_stage_taps(weights, A, wsm);
 
   const int y0 = y_tile + 8 * MB * warp + g;             // + 8 mb
-  const int x0 = x_tile + 2 * t;                         // + 8 nb
+  const int x0 = x_tile + 4 * t;                         // + 16 (nb >> 1) + 2 (nb & 1): first column of block nb
   const bool interior = y_tile >= 0 && y_tile + Y <= h && x_tile + MB_COLS <= w;     // CTA-uniform
   const size_t row8 = (size_t)8 * A.oct.pitch;
   float *gthr = A.oct.gauss[A.level[0]] + ((long long)y0 * A.oct.pitch + x0);
 
-  // G_s and D_{s-1} = G_{s-1} - G_s (sift.js:172) of block (mb, nb), from the unrounded accumulators
-  auto emit = [&](const int li, const int mb, const int nb, const double (&older)[MB][4][2], const double (&newer)[MB][4][2]) {
-    float *r = gthr + (long long)li * A.plane + mb * row8 + 8 * nb;
+  // G_s and D_{s-1} = G_{s-1} - G_s (sift.js:172) of the block pair (mb, 2 q), (mb, 2 q + 1), from the unrounded accumulators
+  auto emit = [&](const int li, const int mb, const int q, const double (&older)[MB][4][2], const double (&newer)[MB][4][2]) {
+    float *r = gthr + (long long)li * A.plane + mb * row8 + 16 * q;
+    const int n0 = 2 * q, n1 = 2 * q + 1;
     if (interior) {
-      if (A.keep_gauss) *reinterpret_cast<float2 *>(r) = make_float2((float)newer[mb][nb][0], (float)newer[mb][nb][1]);
-      *reinterpret_cast<float2 *>(r + A.dog_delta) =
-          make_float2((float)(older[mb][nb][0] - newer[mb][nb][0]), (float)(older[mb][nb][1] - newer[mb][nb][1]));
+      if (A.keep_gauss)
+        *reinterpret_cast<float4 *>(r) = make_float4((float)newer[mb][n0][0], (float)newer[mb][n0][1], (float)newer[mb][n1][0], (float)newer[mb][n1][1]);
+      *reinterpret_cast<float4 *>(r + A.dog_delta) =
+          make_float4((float)(older[mb][n0][0] - newer[mb][n0][0]), (float)(older[mb][n0][1] - newer[mb][n0][1]),
+                      (float)(older[mb][n1][0] - newer[mb][n1][0]), (float)(older[mb][n1][1] - newer[mb][n1][1]));
     } else {
-      const int y = y0 + 8 * mb, x = x0 + 8 * nb;
+      const int y = y0 + 8 * mb, x = x0 + 16 * q;
       if (y >= 0 && y < h) {
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < 4; i++)
           if (x + i < w) {
-            if (A.keep_gauss) r[i] = (float)newer[mb][nb][i];
-            r[A.dog_delta + i] = (float)(older[mb][nb][i] - newer[mb][nb][i]);
+            const double nv = newer[mb][n0 + (i >> 1)][i & 1], ov = older[mb][n0 + (i >> 1)][i & 1];
+            if (A.keep_gauss) r[i] = (float)nv;
+            r[A.dog_delta + i] = (float)(ov - nv);
           }
       }
     }
@@ -560,7 +567,10 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     __syncthreads();                                     // tile li (and, first time, the taps) visible; the other buffer is free
     if (li + 1 < A.nlev) stage(li + 1);
     const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;
-    const double *sp = ((li & 1) ? buf1 : buf0) + (8 * MB * warp + t) * MB_PITCH + g;
+    // N block nb takes the columns {0,1, 4,5, 8,9, 12,13} + 2 (nb & 1) + 16 (nb >> 1): a lane's blocks 0, 1 (2, 3)
+    // hold four neighbouring columns of one row -> one 16-byte store per row, plane and block pair
+    const double *sp = ((li & 1) ? buf1 : buf0) + (8 * MB * warp + t) * MB_PITCH;
+    const int c0 = (4 * (g >> 1) + (g & 1)) ^ MB_SWZ(t), c1 = (4 * (g >> 1) + (g & 1) + 2) ^ MB_SWZ(t);
 #pragma unroll
     for (int mb = 0; mb < MB; mb++)
 #pragma unroll
@@ -570,13 +580,15 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
 #pragma unroll
       for (int mb = 0; mb < MB; mb++)
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], wv, sp[(8 * mb + 4 * d) * MB_PITCH + 8 * nb]);
+        for (int nb = 0; nb < 4; nb++)
+          dmma884(acc[mb][nb][0], acc[mb][nb][1], wv, sp[(8 * mb + 4 * d) * MB_PITCH + 16 * (nb >> 1) + ((nb & 1) ? c1 : c0)]);
     };
     int d = 0;
 #pragma unroll
-    for (int k = 0; k < 4 * MB; k++) {                   // the first chunks carry one block of the previous level each
+    for (int k = 0; k < 2 * MB; k++) {                   // the first chunks carry one block pair of the previous level each
       if (d < D) { chunk(d); d++; }
-      if (li > 0) emit(li - 1, k >> 2, k & 3, older, newer);
+      if (d < D) { chunk(d); d++; }
+      if (li > 0) emit(li - 1, k >> 1, k & 1, older, newer);
     }
     for (; d < D; d++) chunk(d);
     if (A.has_next && A.level[li] == A.spo && (g & 1) == 0) {      // matrix2d.js:129 in[2a][2b]: even rows, even columns
@@ -587,7 +599,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
         if (y >= 0 && y < h && nr >= 0 && nr < A.next.h) {
 #pragma unroll
           for (int nb = 0; nb < 4; nb++) {
-            const int x = x0 + 8 * nb;
+            const int x = x0 + 16 * (nb >> 1) + 2 * (nb & 1);
             if (x < w) {
               A.next.seed64[(size_t)nr * A.next.w + (x >> 1)] = acc[mb][nb][0];
               A.next.gauss[0][(size_t)nr * A.next.pitch + (x >> 1)] = (float)acc[mb][nb][0];
@@ -603,7 +615,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   for (int mb = 0; mb < MB; mb++)
 #pragma unroll
     for (int nb = 0; nb < 4; nb++) {                     // level 0 of octaves >= 1 is the unblurred seed (background.js:114-130)
-      const int y = min(max(y0 + 8 * mb, 0), h - 1), x = x0 + 8 * nb;
+      const int y = min(max(y0 + 8 * mb, 0), h - 1), x = x0 + 16 * (nb >> 1) + 2 * (nb & 1);
       gb[mb][nb][0] = A.src[(size_t)y * w + min(x, w - 1)];
       gb[mb][nb][1] = A.src[(size_t)y * w + min(x + 1, w - 1)];
       ga[mb][nb][0] = ga[mb][nb][1] = 0.0;
@@ -618,10 +630,10 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   {
     const int last = A.nlev - 1;
 #pragma unroll
-    for (int k = 0; k < 4 * MB; k++) {
-      if (last % 3 == 0) emit(last, k >> 2, k & 3, gb, gc);
-      else if (last % 3 == 1) emit(last, k >> 2, k & 3, gc, ga);
-      else emit(last, k >> 2, k & 3, ga, gb);
+    for (int k = 0; k < 2 * MB; k++) {
+      if (last % 3 == 0) emit(last, k >> 1, k & 1, gb, gc);
+      else if (last % 3 == 1) emit(last, k >> 1, k & 1, gc, ga);
+      else emit(last, k >> 1, k & 1, ga, gb);
     }
   }
 }
