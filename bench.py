@@ -39,7 +39,11 @@ FRAMES = 64                    # frames per GPU per step (distinct seeds)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, written by tools/ncu_traffic.py from the
 # `ncu --set full` captures of this round (roofline.traffic is read from this file by kernel name, null if absent)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")
-DOMINANT_KERNEL = "fused_octave0_hi_kernel"
+DOMINANT_KERNEL = "oct0_mma_kernel"
+# separable float64 blur of the reference radii: multiply-adds per input pixel (octave 0 polyphase-merged)
+# and the measured fp64 peak of this B200 (DFMA 36.5, DMMA 37.0 TFLOP/s: tools/micro/fp64_pipes.cu) -- the binding unit of the path
+FMA_PER_INPUT_PX = {4: 982.0, 6: 1048.0}
+FP64_PEAK_TFMA = 18.5
 LANES = int(os.environ.get("SIFT_B200_LANES", "0"))   # frames in flight per GPU (engine lanes); 0 = the engine picks by frame size
 CPU_TILE = int(os.environ.get("SIFT_BENCH_CPU_TILE", "256"))   # cpu baseline / reference arm sample: CPU_TILE^2 crops of the same frames
 
@@ -607,6 +611,12 @@ def run_own(args):
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "whole_path": {"algorithmic_bytes_per_input_px": ab["total"],
                                         "achieved": whole_gbs, "frac": whole_gbs / peak},
+                         "fp64_pipe": {"note": "the blur is bound by the fp64 pipe, not by HBM (DESIGN.md section 3): useful "
+                                               "multiply-adds of the separable float64 blur against the measured fp64 peak",
+                                       "useful_fma_per_input_px": FMA_PER_INPUT_PX[N_OCT],
+                                       "achieved_tfma_per_s": FMA_PER_INPUT_PX[N_OCT] * (value * 1e6 / world) / 1e12,
+                                       "peak_tfma_per_s": FP64_PEAK_TFMA,
+                                       "frac": FMA_PER_INPUT_PX[N_OCT] * (value * 1e6 / world) / 1e12 / FP64_PEAK_TFMA},
                          "kernels": kinds},
             "keypoints_per_step": n_kp,
             "clocks": clocks,

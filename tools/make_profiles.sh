@@ -11,8 +11,9 @@ fi
 python tools/prof_detect.py > gpurun_out/plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -s 10 -c 10 --csv --log-file gpurun_out/launches.csv python tools/prof_detect.py > gpurun_out/ncu.log 2>&1
-# kernel:launches-to-skip (tools/prof_detect.py runs 3 detections; take the 2nd one's launches; fir_pass 6 = pass A, 7 = pass B of octave 1)
-for k in fused_octave0:1 fir_pass:6 fir_pass:7 scan_tma:1 refine_kernel:1; do
+# kernel:launches-to-skip (tools/prof_detect.py runs 3 detections; take the 2nd one's launches: sep_a / sep_b run for
+# octaves 1 and 2 -> skip 2 = octave 1 of the 2nd detection; fir_pass = the scalar passes of octave 3)
+for k in oct0_mma:1 sep_a_mma:2 sep_b_mma:2 fir_pass:2 scan_tma:1 refine_kernel:1; do
   name=${k%%:*}; skip=${k##*:}
   ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -o gpurun_out/prof_${name}_$skip \
       python tools/prof_detect.py > gpurun_out/ncu_$name.log 2>&1
