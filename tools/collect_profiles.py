@@ -23,7 +23,8 @@ with open(os.path.join(P, f"{rnd}_ncu_launch_list.txt"), "w") as f:
     for k, v in sorted(d.items()):
         us = v["gpu__time_duration.sum"] / 1000
         f.write(f"{k[0]:3d} {k[1]:60s} {us:8.1f} us {100 * v['gpu__time_duration.sum'] / tot:5.1f}%  fp64 pipe "
-                f"{v['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active']:5.1f}%  dram rd "
+                f"{v['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active']:5.1f}% (DFMA) "
+                f"{v.get('sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active', 0.0):5.1f}% (DMMA)  dram rd "
                 f"{v['dram__bytes_read.sum'] / 1e6:7.1f} MB  wr {v['dram__bytes_write.sum'] / 1e6:7.1f} MB\n")
     f.write(f"total {tot / 1000:.1f} us\n")
 for rep in sorted(os.listdir(G)):

@@ -9,7 +9,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; tail -c 400 g
 fi
 [ "${1:-all}" = "tests" ] && exit 0          # tests + smoke + bench only (kernels unchanged since the last ncu pass)
 python tools/prof_detect.py > gpurun_out/plain.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
+ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -s 10 -c 10 --csv --log-file gpurun_out/launches.csv python tools/prof_detect.py > gpurun_out/ncu.log 2>&1
 # kernel:launches-to-skip (tools/prof_detect.py runs 3 detections; take the 2nd one's launches: sep_a / sep_b run for
 # octaves 1 and 2 -> skip 2 = octave 1 of the 2nd detection; fir_pass = the scalar passes of octave 3)
