@@ -30,6 +30,56 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- TMA (cp.async.bulk.tensor) helpers: one elected thread issues a 2-D box, everybody waits on the mbarrier ----
+#include <cuda.h>
+__device__ __forceinline__ unsigned mm_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mm_bar_init(unsigned long long *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mm_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mm_tma_load_2d(void *dst_smem, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mm_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(mm_smem_u32(dst_smem)), "l"(map), "r"(mm_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mm_bar_wait(unsigned long long *bar, unsigned parity)
+{
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mm_smem_u32(bar)), "r"(parity) : "memory");
+}
+typedef CUresult (*MmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// 2-D tiled map over a pitched plane; false when the driver entry point is missing or the layout is not TMA-able
+static bool mm_encode_2d(CUtensorMap *m, CUtensorMapDataType ty, size_t esz, const void *base, size_t pitch_bytes, int w, int h,
+                         int box_w, int box_h)
+{
+  static MmEncodeTiledFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+        q == cudaDriverEntryPointSuccess)
+      encode = (MmEncodeTiledFn)fn;
+  }
+  static const bool no_tma = getenv("SIFT_B200_NO_TMA") != nullptr || getenv("SIFT_B200_NO_TMA_BLUR") != nullptr ||
+                             getenv("SIFT_B200_MMA_NO_TMA") != nullptr;
+  if (!encode || no_tma) return false;
+  if ((pitch_bytes % 16) != 0 || ((uintptr_t)base % 16) != 0 || box_w > 256 || box_h > 256 || ((size_t)box_w * esz) % 16 != 0) return false;
+  const cuuint64_t gdim[2] = { (cuuint64_t)w, (cuuint64_t)h };
+  const cuuint64_t gstride[1] = { (cuuint64_t)pitch_bytes };
+  const cuuint32_t box[2] = { (cuuint32_t)box_w, (cuuint32_t)box_h };
+  const cuuint32_t estride[2] = { 1, 1 };
+  return encode(m, ty, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // =====================================================================================================
 // Octave 0: 2x nearest-neighbour upsample + all levels + DoG + seed of octave 1 in one kernel (polyphase).
 //
@@ -49,9 +99,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
 #define M0_TW_DOUBLES (32 * 16)          // per-warp Ts: 32 rows x 16 columns
 #define M0_THREADS 256
 #define M0_MAXD 5                        // chunks of 4 samples per 8 x K band: ceil((n + 3) / 4), n <= 17
-#define M0_S_DOUBLES (M0_SROWS * M0_SPITCH + 8)
+#define M0_S_DOUBLES (M0_SROWS * M0_SPITCH + 16)       // 2928: keeps everything behind it on 128-byte boundaries
 #define M0_T_DOUBLES (8 * M0_TW_DOUBLES)
-#define M0_SMEM_DOUBLES(nlev) (M0_S_DOUBLES + M0_T_DOUBLES + (nlev) * M0_MAXD * 32)
+#define M0_RAW_DOUBLES (M0_SCOLS * M0_SCOLS / 2)       // TMA destination: 48 x 48 raw samples of at most 4 bytes
+#define M0_SMEM_DOUBLES(nlev) (M0_S_DOUBLES + M0_T_DOUBLES + (nlev) * M0_MAXD * 32 + M0_RAW_DOUBLES)
 
 struct Mma0Args {
   const void *src;
@@ -63,6 +114,7 @@ struct Mma0Args {
   const double *wfrag;                   // [nlev][M0_MAXD][32] per-lane band fragments (zero padded)
   long long plane;                       // floats between consecutive Gaussian (and DoG) planes
   long long dog_delta;                   // dog[s-1] = gauss[s] + dog_delta
+  int use_tma;                           // interior source tiles arrive as one TMA box (u8 / f32 sources with a TMA-able pitch)
   int row_shift;                         // tiles start at source row -row_shift: keeps the 4-row blocks aligned with the
                                          // whole image's when this octave is a mosaic strip (bit-identical sums)
 };
@@ -167,10 +219,11 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
 }
 
 __global__ void __launch_bounds__(M0_THREADS, 2)
-oct0_mma_kernel(const Mma0Args A)
+oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUtensorMap src_map)
 {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   __shared__ int lvR[SIFT_MAX_LEVELS];
+  __shared__ __align__(8) unsigned long long src_bar;
   double *S = smem;                                     // [56][52] source tile v / 255 (rows / columns >= 48: zero)
   double *Tw = smem + M0_S_DOUBLES + (threadIdx.x >> 5) * M0_TW_DOUBLES;   // this warp's horizontally blurred rows
   double *Wf = smem + M0_S_DOUBLES + M0_T_DOUBLES;                       // [nlev][M0_MAXD][32] band fragments
@@ -178,9 +231,30 @@ oct0_mma_kernel(const Mma0Args A)
   const int g = lane >> 2, t = lane & 3;
   const int a_tile = blockIdx.x * M0_SW, b_tile = blockIdx.y * M0_SH - A.row_shift;
 
+  // interior tiles: the 48 x 48 window of u8 / f32 source samples arrives as ONE TMA box in `raw` (the unit would
+  // zero-fill outside the image where the reference clamps: border tiles are gathered with clamped loads below)
+  unsigned char *raw = reinterpret_cast<unsigned char *>(smem + M0_S_DOUBLES + M0_T_DOUBLES + A.nlev * M0_MAXD * 32);
+  const bool by_tma = A.use_tma && a_tile >= M0_HALO && a_tile + M0_SW + M0_HALO <= A.src_w && b_tile >= M0_HALO &&
+                      b_tile + M0_SH + M0_HALO <= A.src_h;                     // CTA-uniform
+  if (by_tma && tid == 0) {
+    mm_bar_init(&src_bar, 1);
+    // a box starts on a 16-byte boundary of its row (TMA requirement): u8 tiles take 16 columns of left halo
+    // (box 64 x 48, the window starts at byte 8 of each row), f32 tiles the 8 they need (box 48 x 48)
+    if (A.dtype == SIFT_U8) mm_tma_load_2d(raw, &src_map, &src_bar, a_tile - 16, b_tile - M0_HALO, 64u * M0_SCOLS);
+    else mm_tma_load_2d(raw, &src_map, &src_bar, a_tile - M0_HALO, b_tile - M0_HALO, (unsigned)(M0_SCOLS * M0_SCOLS * 4));
+  }
   if (tid < A.nlev) lvR[tid] = A.radius[tid];
   for (int e = tid; e < A.nlev * M0_MAXD * 32; e += M0_THREADS) Wf[e] = __ldg(A.wfrag + e);
-  {
+  if (by_tma) {
+    __syncthreads();                                    // barrier initialisation visible
+    mm_bar_wait(&src_bar, 0);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const int e = tid + i * M0_THREADS;
+      const int rr = e / M0_SCOLS, cc = e - rr * M0_SCOLS;
+      S[rr * M0_SPITCH + cc] = A.dtype == SIFT_U8 ? mma0_u8(raw[rr * 64 + 8 + cc]) : (double)reinterpret_cast<const float *>(raw)[e];
+    }
+  } else {
     static_assert(M0_SCOLS * M0_SCOLS == 9 * M0_THREADS, "tile load assumes 9 samples per thread");
     int so[9];
     const char *rowp[9];
@@ -204,12 +278,12 @@ oct0_mma_kernel(const Mma0Args A)
 #pragma unroll
       for (int i = 0; i < 9; i++) S[so[i]] = mma0_sample(A, rowp[i], gxs[i]);
     }
-    // everything else of S is read against zero weights only: keep it finite
-    for (int e = tid; e < M0_SCOLS * (M0_SPITCH - M0_SCOLS); e += M0_THREADS)
-      S[(e >> 2) * M0_SPITCH + M0_SCOLS + (e & 3)] = 0.0;
-    for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
   }
-  __syncthreads();                                      // source tile, level table, fragments staged: the only CTA barrier
+  // everything else of S is read against zero weights only: keep it finite
+  for (int e = tid; e < M0_SCOLS * (M0_SPITCH - M0_SCOLS); e += M0_THREADS)
+    S[(e >> 2) * M0_SPITCH + M0_SCOLS + (e & 3)] = 0.0;
+  for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
+  __syncthreads();                                      // source tile, level table, fragments staged: the last CTA barrier
 
   // V-pass ownership of this warp: output rows 32 wy .. +31 (source rows 16 wy .. +15), columns 16 wx .. +15
   const int wy = warp >> 2, wx = warp & 3;
@@ -344,7 +418,14 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   const size_t smem = (size_t)M0_SMEM_DOUBLES(nlev) * sizeof(double);
   dim3 grid((src_w + M0_SW - 1) / M0_SW, (src_h + A.row_shift + M0_SH - 1) / M0_SH);
   cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
-  oct0_mma_kernel<<<grid, M0_THREADS, smem, st>>>(A);
+  CUtensorMap src_map;
+  memset(&src_map, 0, sizeof src_map);
+  // the raw tile must start on a 128-byte boundary of shared memory: S, Ts and the fragments before it are whole multiples
+  A.use_tma = 0;
+  if ((dtype == SIFT_U8 || dtype == SIFT_F32) && ((size_t)(M0_S_DOUBLES + M0_T_DOUBLES + nlev * M0_MAXD * 32) * sizeof(double)) % 128 == 0)
+    A.use_tma = (mm_encode_2d(&src_map, dtype == SIFT_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                              dtype == SIFT_U8 ? 1 : 4, src, src_pitch, src_w, src_h, dtype == SIFT_U8 ? 64 : M0_SCOLS, M0_SCOLS)) ? 1 : 0;
+  oct0_mma_kernel<<<grid, M0_THREADS, smem, st>>>(A, src_map);
   return true;
 }
 
@@ -369,6 +450,7 @@ struct MmaSepArgs {
   double *T[SIFT_MAX_LEVELS];
   size_t t_pitch;                         // doubles per T row (even)
   int tile_pitch;                         // pass A: doubles per staged row (= 4 mod 16)
+  int use_tma;                            // pass A: interior tiles arrive as one TMA box (src_map)
   int buf_rows[2];                        // pass B: rows of the two staging buffers (levels 0, 2, .. / 1, 3, ..)
   OctaveDev oct, next;
   int has_next, spo, keep_gauss;
@@ -404,9 +486,10 @@ __device__ __forceinline__ void ms_cp16(double *dst_smem, const double *src)
 #define MSB_CTAS 2
 #endif
 __global__ void __launch_bounds__(MS_THREADS, MSA_CTAS)
-sep_a_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
+sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ MmaSepArgs A, const __grid_constant__ CUtensorMap src_map)
 {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long tile_bar;
   double *tile = smem;                                   // [32][tile_pitch]: columns x_tile - rmax .. (clamped)
   double *wsm = smem + MA_ROWS * A.tile_pitch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -415,7 +498,15 @@ sep_a_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   const int tp = A.tile_pitch;
 
   const int xl = x_tile - A.rmax;                        // first staged column (rmax is rounded up to even by the host)
-  if (xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h && (A.w & 1) == 0) {
+  const bool by_tma = A.use_tma && xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h;      // CTA-uniform
+  if (by_tma) {
+    // interior tile: ONE TMA box (32 rows x tile_pitch fp64 of the seed plane) lands dense in the tile, completion
+    // on an mbarrier; border tiles need clamp-to-edge samples (the TMA unit would zero-fill) and are copied below
+    if (tid == 0) {
+      mm_bar_init(&tile_bar, 1);
+      mm_tma_load_2d(tile, &src_map, &tile_bar, xl, y_tile, (unsigned)(MA_ROWS * tp * sizeof(double)));
+    }
+  } else if (xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h && (A.w & 1) == 0) {
     // interior tile: whole 16-byte pairs, pointers advanced by constants (a warp copies 4 rows)
     const double *src = A.src + (size_t)(y_tile + warp) * A.w + xl + 2 * lane;
     double *dst = tile + warp * tp + 2 * lane;
@@ -432,7 +523,8 @@ sep_a_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   asm volatile("cp.async.commit_group;" ::: "memory");
   ms_stage_taps(weights, A, wsm);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  __syncthreads();                                       // taps, copied tile, barrier initialisation visible
+  if (by_tma) mm_bar_wait(&tile_bar, 0);
 
   const int wr = warp >> 2, wc = warp & 3;
   const int y0 = y_tile + 16 * wr + g;                   // + 8 mb
@@ -488,7 +580,7 @@ __global__ void __launch_bounds__(MS_THREADS, MSB_CTAS)
 sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
 {
   constexpr int Y = 64 * MB;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double *buf0 = smem, *buf1 = smem + A.buf_rows[0] * MB_PITCH;
   double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -713,8 +805,12 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   {
     const size_t smem = ms_smem_a(A);
     dim3 grid((oct.w + MA_COLS - 1) / MA_COLS, (oct.h + MA_ROWS - 1) / MA_ROWS);
+    CUtensorMap src_map;
+    memset(&src_map, 0, sizeof src_map);
+    A.use_tma = (mm_encode_2d(&src_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, oct.seed64, (size_t)oct.w * sizeof(double), oct.w, oct.h,
+                              A.tile_pitch, MA_ROWS)) ? 1 : 0;
     cudaFuncSetAttribute(sep_a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sep_a_mma_kernel<<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+    sep_a_mma_kernel<<<grid, MS_THREADS, smem, st>>>(d_weights, A, src_map);
   }
   const int mb = ms_pick_mb(A);
   const size_t smem = ms_smem_b(A, mb);
