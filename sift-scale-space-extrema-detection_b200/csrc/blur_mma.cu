@@ -458,11 +458,12 @@ struct MmaSepArgs {
   int row_shift;                          // pass B tiles start at row -row_shift (mosaic strips: blocks aligned with the whole image's)
 };
 
+template <int NT = MS_THREADS>
 __device__ __forceinline__ void ms_stage_taps(const double *__restrict__ weights, const MmaSepArgs &A, double *wsm)
 {
   for (int li = 0; li < A.nlev; li++) {
     const int n = 2 * A.radius[li] + 1, len = A.wsm[li + 1] - A.wsm[li];
-    for (int e = threadIdx.x; e < len; e += MS_THREADS)
+    for (int e = threadIdx.x; e < len; e += NT)
       wsm[A.wsm[li] + e] = (e >= MS_WFRONT && e < MS_WFRONT + n) ? __ldg(weights + A.woff[li] + e - MS_WFRONT) : 0.0;
   }
 }
@@ -575,11 +576,15 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
 // offsets 0, 8, 2, 10 keep the four column sets on distinct 8-byte banks, and 16-byte pairs stay together
 #define MB_SWZ(r) (8 * ((r) & 1) + 2 * (((r) >> 1) & 1))
 #define MB_SLACK 4
+#ifndef MSB_WARPS
+#define MSB_WARPS 8
+#endif
+#define MSB_THREADS (32 * MSB_WARPS)
 template <int MB>
-__global__ void __launch_bounds__(MS_THREADS, MSB_CTAS)
+__global__ void __launch_bounds__(MSB_THREADS, MSB_CTAS)
 sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
 {
-  constexpr int Y = 64 * MB;
+  constexpr int Y = 8 * MB * MSB_WARPS;
   extern __shared__ __align__(128) double smem[];
   double *buf0 = smem, *buf1 = smem + A.buf_rows[0] * MB_PITCH;
   double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
@@ -598,15 +603,16 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
       // interior tile: no clamping, pointers advanced by constants (16 threads per row, 16 rows per sweep)
       const double *src = T + (size_t)(y_tile - R + (tid >> 4)) * A.t_pitch + x_tile + (tid & 15) * 2;
       double *dst = buf + (tid >> 4) * MB_PITCH + (((tid & 15) * 2) ^ MB_SWZ(tid >> 4));
-      const size_t sstep = (size_t)16 * A.t_pitch;
+      const size_t sstep = (size_t)(MSB_THREADS / 16) * A.t_pitch;
+      constexpr int RS = MSB_THREADS / 16;             // rows per sweep
       int rr = tid >> 4;
-      for (; rr + 48 < rows; rr += 64, src += 4 * sstep, dst += 64 * MB_PITCH) {
-        ms_cp16(dst, src); ms_cp16(dst + 16 * MB_PITCH, src + sstep);
-        ms_cp16(dst + 32 * MB_PITCH, src + 2 * sstep); ms_cp16(dst + 48 * MB_PITCH, src + 3 * sstep);
+      for (; rr + 3 * RS < rows; rr += 4 * RS, src += 4 * sstep, dst += 4 * RS * MB_PITCH) {
+        ms_cp16(dst, src); ms_cp16(dst + RS * MB_PITCH, src + sstep);
+        ms_cp16(dst + 2 * RS * MB_PITCH, src + 2 * sstep); ms_cp16(dst + 3 * RS * MB_PITCH, src + 3 * sstep);
       }
-      for (; rr < rows; rr += 16, src += sstep, dst += 16 * MB_PITCH) ms_cp16(dst, src);
+      for (; rr < rows; rr += RS, src += sstep, dst += RS * MB_PITCH) ms_cp16(dst, src);
     } else {
-      for (int e = tid; e < rows * (MB_COLS / 2); e += MS_THREADS) {
+      for (int e = tid; e < rows * (MB_COLS / 2); e += MSB_THREADS) {
         const int rr = e >> 4, c2 = (e & 15) * 2;
         const double *row = T + (size_t)min(max(y_tile - R + rr, 0), h - 1) * A.t_pitch;          // sift.js:116-119 clamp-to-edge
         double *dst = buf + rr * MB_PITCH + (c2 ^ MB_SWZ(rr));
@@ -617,7 +623,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage(0);
-  ms_stage_taps(weights, A, wsm);
+  ms_stage_taps<MSB_THREADS>(weights, A, wsm);
 
   const int y0 = y_tile + 8 * MB * warp + g;             // + 8 mb
   const int x0 = x_tile + 4 * t;                         // + 16 (nb >> 1) + 2 (nb & 1): first column of block nb
@@ -762,7 +768,7 @@ static void ms_buf_rows(MmaSepArgs &A, int mb)
 {
   A.buf_rows[0] = A.buf_rows[1] = 0;
   for (int i = 0; i < A.nlev; i++) {
-    const int rows = 64 * mb + 2 * A.radius[i] + MB_SLACK;
+    const int rows = 8 * MSB_WARPS * mb + 2 * A.radius[i] + MB_SLACK;
     if (rows > A.buf_rows[i & 1]) A.buf_rows[i & 1] = rows;
   }
 }
@@ -814,12 +820,13 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   }
   const int mb = ms_pick_mb(A);
   const size_t smem = ms_smem_b(A, mb);
-  dim3 grid((oct.w + MB_COLS - 1) / MB_COLS, (oct.h + A.row_shift + 64 * mb - 1) / (64 * mb));
+  const int ytile = 8 * MSB_WARPS * mb;
+  dim3 grid((oct.w + MB_COLS - 1) / MB_COLS, (oct.h + A.row_shift + ytile - 1) / ytile);
   if (mb == 2) {
     cudaFuncSetAttribute(sep_b_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sep_b_mma_kernel<2><<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+    sep_b_mma_kernel<2><<<grid, MSB_THREADS, smem, st>>>(d_weights, A);
   } else {
     cudaFuncSetAttribute(sep_b_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sep_b_mma_kernel<1><<<grid, MS_THREADS, smem, st>>>(d_weights, A);
+    sep_b_mma_kernel<1><<<grid, MSB_THREADS, smem, st>>>(d_weights, A);
   }
 }
