@@ -275,7 +275,9 @@ typedef struct sift_strip_layout {
 SIFT_API int sift_strip_layout_compute(const sift_params *params, int full_width, int full_height, int row0,
                                        int row1, int margin, sift_strip_layout *out);
 /* Lay the strip's pyramid out on the device (lane 0) and upload the source rows
- * [top[0]/2, (bottom[0]+1)/2) of the full image (`rows` points at the first of them). */
+ * [top[0]/2, (bottom[0]+1)/2) of the full image (`rows` points at the first of them).  The upload is asynchronous
+ * (chunks on a copy stream; octave 0 runs band by band behind them): `rows` must stay valid until
+ * sift_strip_octave(ctx, 0) has returned, and should be page-locked for the copy to overlap. */
 SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const sift_strip_layout *layout,
                               const void *rows, int dtype, size_t pitch_bytes);
 /* Device pointer to the strip's fp64 seed image of octave >= 1: dense, width[octave] doubles per row, first row

@@ -115,6 +115,7 @@ struct Mma0Args {
   long long plane;                       // floats between consecutive Gaussian (and DoG) planes
   long long dog_delta;                   // dog[s-1] = gauss[s] + dog_delta
   int use_tma;                           // interior source tiles arrive as one TMA box (u8 / f32 sources with a TMA-able pitch)
+  int tile_y0;                           // first tile row of this launch (mosaic strips run octave 0 band by band behind their upload)
   int row_shift;                         // tiles start at source row -row_shift: keeps the 4-row blocks aligned with the
                                          // whole image's when this octave is a mosaic strip (bit-identical sums)
 };
@@ -229,7 +230,7 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
   double *Wf = smem + M0_S_DOUBLES + M0_T_DOUBLES;                       // [nlev][M0_MAXD][32] band fragments
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int a_tile = blockIdx.x * M0_SW, b_tile = blockIdx.y * M0_SH - A.row_shift;
+  const int a_tile = blockIdx.x * M0_SW, b_tile = ((int)blockIdx.y + A.tile_y0) * M0_SH - A.row_shift;
 
   // interior tiles: the 48 x 48 window of u8 / f32 source samples arrives as ONE TMA box in `raw` (the unit would
   // zero-fill outside the image where the reference clamps: border tiles are gathered with clamped loads below)
@@ -395,9 +396,12 @@ void mma0_build_frags(const double *merged, int R, double *out /* M0_MAXD * 32 *
     }
 }
 
+int mma0_tile_rows(const OctaveDev &oct, int src_h) { return (src_h + ((oct.y_top >> 1) & 3) + M0_SH - 1) / M0_SH; }
+
+// tile_row0 / tile_rows: the band of tile rows to run (tile_rows < 0: all of them)
 bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
                      const OctaveDev &oct, const OctaveDev *next, const double *d_frags, const LevelPlan *plans,
-                     int nlev, int spo, int keep_gauss)
+                     int nlev, int spo, int keep_gauss, int tile_row0, int tile_rows)
 {
   Mma0Args A;
   memset(&A, 0, sizeof A);
@@ -416,7 +420,11 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   A.wfrag = d_frags;
   A.row_shift = (oct.y_top >> 1) & 3;
   const size_t smem = (size_t)M0_SMEM_DOUBLES(nlev) * sizeof(double);
-  dim3 grid((src_w + M0_SW - 1) / M0_SW, (src_h + A.row_shift + M0_SH - 1) / M0_SH);
+  const int all_rows = (src_h + A.row_shift + M0_SH - 1) / M0_SH;
+  A.tile_y0 = tile_rows < 0 ? 0 : tile_row0;
+  const int n_rows = tile_rows < 0 ? all_rows : (tile_row0 + tile_rows <= all_rows ? tile_rows : all_rows - tile_row0);
+  if (n_rows <= 0) return true;
+  dim3 grid((src_w + M0_SW - 1) / M0_SW, n_rows);
   cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
   CUtensorMap src_map;
   memset(&src_map, 0, sizeof src_map);

@@ -101,7 +101,8 @@ int mma0_frag_doubles(int nlev);
 void mma0_build_frags(const double *merged, int R, double *out /* mma0_frag_doubles(1) */);
 bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pitch, int src_w, int src_h,
                      const OctaveDev &oct, const OctaveDev *next, const double *d_frags, const LevelPlan *plans,
-                     int nlev, int spo, int keep_gauss);
+                     int nlev, int spo, int keep_gauss, int tile_row0 = 0, int tile_rows = -1);
+int mma0_tile_rows(const OctaveDev &oct, int src_h);   // tile rows (32 source rows each) of a whole launch
 
 // octaves >= 1 as two DMMA passes (row-major fp64 intermediate)
 bool mma_sep_supported(const LevelPlan *plans, int nlev, int w, int h);

@@ -89,6 +89,10 @@ struct sift_ctx {
   int strip_next_octave = 0;            // octave sift_strip_octave expects next
   int strip_dtype = 0;
   size_t strip_pitch = 0;
+  // a strip's source rows are uploaded in STRIP_CHUNKS pieces on a copy stream; octave 0 runs band by band behind them
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t strip_ev[8] = {};
+  int strip_chunks = 0, strip_chunk_rows = 0;             // 0 chunks: the upload went through the lane stream
   LevelPlan plans[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   double dog_blur[SIFT_MAX_OCTAVES][SIFT_MAX_LEVELS];
   std::vector<double> h_weights;   // [0,256): u8 -> v/255.0 table, then per-level taps
@@ -948,6 +952,11 @@ SIFT_API void sift_destroy(sift_ctx *c)
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->main_stream) cudaStreamDestroy(c->main_stream);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    for (int k = 0; k < 8; k++) cudaEventDestroy(c->strip_ev[k]);
+    cudaStreamDestroy(c->copy_stream);
+  }
   delete c;
 }
 
@@ -1586,18 +1595,48 @@ SIFT_API int sift_strip_begin(sift_ctx *ctx, const sift_params *params, const si
   CK(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = sift_synchronize(ctx))) return rc;
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));     // an upload nobody consumed (strip_begin twice)
   const int src_w = layout->width[0] / 2;
   const int src_h = (layout->bottom[0] + 1) / 2 - layout->top[0] / 2;
   ctx->L = &ctx->lanes[0];
   if ((rc = ensure_plan(ctx, src_w, src_h, params, layout))) return rc;
   if ((rc = ensure_lane(ctx, ctx->L))) return rc;
   size_t dpitch;
-  if ((rc = upload_image(ctx, rows, dtype, src_w, src_h, pitch_bytes, &dpitch))) return rc;
+  ctx->strip_chunks = 0;
+  const size_t es = dtype_size(dtype);
+  static const bool no_overlap = getenv("SIFT_B200_STRIP_SYNC_UPLOAD") != nullptr;
+  if (es && ctx->mma0_woff >= 0 && !ctx->oct0_variant_forced && !no_overlap && src_h >= 8 * 64) {
+    // upload in 8 chunks of whole tile rows on a copy stream: sift_strip_octave(0) runs the octave-0 kernel band by
+    // band, each band behind the chunk that holds its last halo rows, so most of the copy hides behind the blur.
+    // `rows` must stay valid until sift_strip_octave(ctx, 0) has returned.
+    const size_t row = (size_t)src_w * es;
+    if (pitch_bytes == 0) pitch_bytes = row;
+    if (pitch_bytes < row) return fail(ctx, SIFT_ERR_BAD_ARGS, "pitch %zu < row bytes %zu", pitch_bytes, row);
+    if ((rc = grow(ctx, ctx->L->image, row * src_h))) return rc;
+    if (!ctx->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&ctx->strip_ev[k], cudaEventDisableTiming));
+    }
+    const int chunk = ((src_h + 8 * 32 - 1) / (8 * 32)) * 32;          // source rows per chunk: whole tile rows
+    ctx->strip_chunk_rows = chunk;
+    for (int k = 0; k < 8; k++) {
+      const int r0 = std::min(k * chunk, src_h), r1 = std::min(r0 + chunk, src_h);
+      if (r1 > r0)
+        CK(cudaMemcpy2DAsync((char *)ctx->L->image.p + (size_t)r0 * row, row, (const char *)rows + (size_t)r0 * pitch_bytes,
+                             pitch_bytes, row, r1 - r0, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->strip_ev[k], ctx->copy_stream));
+    }
+    ctx->bytes_h2d += row * src_h;
+    ctx->strip_chunks = 8;
+    dpitch = row;
+  } else {
+    if ((rc = upload_image(ctx, rows, dtype, src_w, src_h, pitch_bytes, &dpitch))) return rc;
+    CK(cudaStreamSynchronize(ctx->L->stream));
+  }
   ctx->strip_dtype = dtype; ctx->strip_pitch = dpitch;
   ctx->strip_next_octave = 0;
   ctx->pyramid_built = false;
   ctx->pyramid_serial++;
-  CK(cudaStreamSynchronize(ctx->L->stream));
   return SIFT_OK;
 }
 
@@ -1624,7 +1663,30 @@ SIFT_API int sift_strip_octave(sift_ctx *ctx, int octave)
     launch_seed_to_f32(ctx->L->stream, od.seed64, od.w, od.h, od.gauss[0], od.pitch);
     ctx->launches += 1;
   }
-  run_octave(ctx, octave, ctx->L->image.p, ctx->strip_dtype, ctx->strip_pitch);
+  if (octave == 0 && ctx->strip_chunks > 0) {
+    // octave 0 band by band behind the chunked upload: band k needs its own rows and the first halo rows of chunk k + 1
+    const OctaveDev &od = ctx->L->octs[0];
+    const OctaveDev *next = ctx->n_oct > 1 ? &ctx->L->octs[1] : nullptr;
+    const int per_band = ctx->strip_chunk_rows / 32, all_rows = mma0_tile_rows(od, ctx->in_h);
+    prof_begin(ctx, SIFT_PROF_BLUR_OCT0);
+    bool ok = true;
+    for (int k = 0; k < ctx->strip_chunks && ok; k++) {
+      CK(cudaStreamWaitEvent(ctx->L->stream, ctx->strip_ev[std::min(k + 1, ctx->strip_chunks - 1)], 0));
+      const int r0 = k * per_band, n = (k + 1 == ctx->strip_chunks) ? all_rows - r0 : per_band;
+      if (n <= 0 || r0 >= all_rows) continue;
+      ok = launch_oct0_mma(ctx->L->stream, ctx->L->image.p, ctx->strip_dtype, ctx->strip_pitch, ctx->in_w, ctx->in_h, od, next,
+                           ctx->d_weights + ctx->mma0_woff, ctx->plans[0], ctx->nlev, ctx->prm.scalesPerOctave, ctx->keep_gauss, r0, n);
+      ctx->launches += 1;
+    }
+    prof_end(ctx);
+    if (!ok) {                                               // layout the DMMA kernel does not take: the whole octave, after the upload
+      CK(cudaStreamWaitEvent(ctx->L->stream, ctx->strip_ev[ctx->strip_chunks - 1], 0));
+      run_octave(ctx, 0, ctx->L->image.p, ctx->strip_dtype, ctx->strip_pitch);
+    }
+    ctx->strip_chunks = 0;
+  } else {
+    run_octave(ctx, octave, ctx->L->image.p, ctx->strip_dtype, ctx->strip_pitch);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->L->stream));
   ctx->strip_next_octave = octave + 1;
