@@ -80,6 +80,17 @@ static bool mm_encode_2d(CUtensorMap *m, CUtensorMapDataType ty, size_t esz, con
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Grid of a DMMA kernel over n_tiles tiles: one CTA per tile, or -- SIFT_B200_MMA_HALF_SM=1 -- one CTA per SM walking
+// over the tiles, so that a kernel holds half of every SM (its CTAs take half the registers) and the blur kernel of
+// another frame in flight runs beside it instead of after it.
+static int mm_grid(int n_tiles)
+{
+  static int n_sm = 0;
+  static const bool half_sm = getenv("SIFT_B200_MMA_HALF_SM") != nullptr;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  return (half_sm && n_tiles > n_sm) ? n_sm : n_tiles;
+}
+
 // =====================================================================================================
 // Octave 0: 2x nearest-neighbour upsample + all levels + DoG + seed of octave 1 in one kernel (polyphase).
 //
@@ -116,6 +127,7 @@ struct Mma0Args {
   long long dog_delta;                   // dog[s-1] = gauss[s] + dog_delta
   int use_tma;                           // interior source tiles arrive as one TMA box (u8 / f32 sources with a TMA-able pitch)
   int tile_y0;                           // first tile row of this launch (mosaic strips run octave 0 band by band behind their upload)
+  int tiles_x, n_tiles;                  // tiles per row / tiles of this launch
   int row_shift;                         // tiles start at source row -row_shift: keeps the 4-row blocks aligned with the
                                          // whole image's when this octave is a mosaic strip (bit-identical sums)
 };
@@ -230,25 +242,36 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
   double *Wf = smem + M0_S_DOUBLES + M0_T_DOUBLES;                       // [nlev][M0_MAXD][32] band fragments
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int a_tile = blockIdx.x * M0_SW, b_tile = ((int)blockIdx.y + A.tile_y0) * M0_SH - A.row_shift;
+  unsigned char *raw = reinterpret_cast<unsigned char *>(smem + M0_S_DOUBLES + M0_T_DOUBLES + A.nlev * M0_MAXD * 32);
+  if (tid == 0) mm_bar_init(&src_bar, 1);
+  if (tid < A.nlev) lvR[tid] = A.radius[tid];
+  for (int e = tid; e < A.nlev * M0_MAXD * 32; e += M0_THREADS) Wf[e] = __ldg(A.wfrag + e);
+  // everything of S beyond the 48 x 48 samples is read against zero weights only: keep it finite (written once)
+  for (int e = tid; e < M0_SCOLS * (M0_SPITCH - M0_SCOLS); e += M0_THREADS)
+    S[(e >> 2) * M0_SPITCH + M0_SCOLS + (e & 3)] = 0.0;
+  for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
+  __syncthreads();                                      // barrier initialised, level table and fragments staged
+
+  // The CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of this launch (one tile per CTA unless the
+  // host caps the grid: SIFT_B200_MMA_HALF_SM launches one CTA per SM so that another frame's kernel shares the SM).
+  unsigned tma_uses = 0;
+  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+  const int a_tile = (tile % A.tiles_x) * M0_SW, b_tile = (tile / A.tiles_x + A.tile_y0) * M0_SH - A.row_shift;
 
   // interior tiles: the 48 x 48 window of u8 / f32 source samples arrives as ONE TMA box in `raw` (the unit would
   // zero-fill outside the image where the reference clamps: border tiles are gathered with clamped loads below)
-  unsigned char *raw = reinterpret_cast<unsigned char *>(smem + M0_S_DOUBLES + M0_T_DOUBLES + A.nlev * M0_MAXD * 32);
   const bool by_tma = A.use_tma && a_tile >= M0_HALO && a_tile + M0_SW + M0_HALO <= A.src_w && b_tile >= M0_HALO &&
                       b_tile + M0_SH + M0_HALO <= A.src_h;                     // CTA-uniform
   if (by_tma && tid == 0) {
-    mm_bar_init(&src_bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // `raw` was read through the generic proxy (previous tile)
     // a box starts on a 16-byte boundary of its row (TMA requirement): u8 tiles take 16 columns of left halo
     // (box 64 x 48, the window starts at byte 8 of each row), f32 tiles the 8 they need (box 48 x 48)
     if (A.dtype == SIFT_U8) mm_tma_load_2d(raw, &src_map, &src_bar, a_tile - 16, b_tile - M0_HALO, 64u * M0_SCOLS);
     else mm_tma_load_2d(raw, &src_map, &src_bar, a_tile - M0_HALO, b_tile - M0_HALO, (unsigned)(M0_SCOLS * M0_SCOLS * 4));
   }
-  if (tid < A.nlev) lvR[tid] = A.radius[tid];
-  for (int e = tid; e < A.nlev * M0_MAXD * 32; e += M0_THREADS) Wf[e] = __ldg(A.wfrag + e);
   if (by_tma) {
-    __syncthreads();                                    // barrier initialisation visible
-    mm_bar_wait(&src_bar, 0);
+    mm_bar_wait(&src_bar, tma_uses & 1);
+    tma_uses++;
 #pragma unroll
     for (int i = 0; i < 9; i++) {
       const int e = tid + i * M0_THREADS;
@@ -280,11 +303,7 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
       for (int i = 0; i < 9; i++) S[so[i]] = mma0_sample(A, rowp[i], gxs[i]);
     }
   }
-  // everything else of S is read against zero weights only: keep it finite
-  for (int e = tid; e < M0_SCOLS * (M0_SPITCH - M0_SCOLS); e += M0_THREADS)
-    S[(e >> 2) * M0_SPITCH + M0_SCOLS + (e & 3)] = 0.0;
-  for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
-  __syncthreads();                                      // source tile, level table, fragments staged: the last CTA barrier
+  __syncthreads();                                      // source tile staged: the last CTA barrier of the tile
 
   // V-pass ownership of this warp: output rows 32 wy .. +31 (source rows 16 wy .. +15), columns 16 wx .. +15
   const int wy = warp >> 2, wx = warp & 3;
@@ -371,6 +390,8 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
     level(s, pa, pb);
     if (s + 1 < A.nlev) level(s + 1, pb, pa);
   }
+  if (tile + (int)gridDim.x < A.n_tiles) __syncthreads();   // every warp has left this tile: S and raw are free
+  }                                                     // tiles
 }
 
 // ---- host side of octave 0 ------------------------------------------------------------------------------
@@ -424,7 +445,9 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   A.tile_y0 = tile_rows < 0 ? 0 : tile_row0;
   const int n_rows = tile_rows < 0 ? all_rows : (tile_row0 + tile_rows <= all_rows ? tile_rows : all_rows - tile_row0);
   if (n_rows <= 0) return true;
-  dim3 grid((src_w + M0_SW - 1) / M0_SW, n_rows);
+  A.tiles_x = (src_w + M0_SW - 1) / M0_SW;
+  A.n_tiles = A.tiles_x * n_rows;
+  const int grid = mm_grid(A.n_tiles);
   cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
   CUtensorMap src_map;
   memset(&src_map, 0, sizeof src_map);
@@ -503,8 +526,14 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
   double *wsm = smem + MA_ROWS * A.tile_pitch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int x_tile = blockIdx.x * MA_COLS, y_tile = blockIdx.y * MA_ROWS;
   const int tp = A.tile_pitch;
+  if (tid == 0) mm_bar_init(&tile_bar, 1);
+  ms_stage_taps(weights, A, wsm);
+  __syncthreads();                                       // barrier initialised, taps staged
+  const int tiles_x = (A.w + MA_COLS - 1) / MA_COLS, n_tiles = tiles_x * ((A.h + MA_ROWS - 1) / MA_ROWS);
+  unsigned tma_uses = 0;
+  for (int tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+  const int x_tile = (tile_i % tiles_x) * MA_COLS, y_tile = (tile_i / tiles_x) * MA_ROWS;
 
   const int xl = x_tile - A.rmax;                        // first staged column (rmax is rounded up to even by the host)
   const bool by_tma = A.use_tma && xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h;      // CTA-uniform
@@ -512,7 +541,7 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
     // interior tile: ONE TMA box (32 rows x tile_pitch fp64 of the seed plane) lands dense in the tile, completion
     // on an mbarrier; border tiles need clamp-to-edge samples (the TMA unit would zero-fill) and are copied below
     if (tid == 0) {
-      mm_bar_init(&tile_bar, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was read through the generic proxy (previous tile)
       mm_tma_load_2d(tile, &src_map, &tile_bar, xl, y_tile, (unsigned)(MA_ROWS * tp * sizeof(double)));
     }
   } else if (xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h && (A.w & 1) == 0) {
@@ -530,10 +559,9 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  ms_stage_taps(weights, A, wsm);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();                                       // taps, copied tile, barrier initialisation visible
-  if (by_tma) mm_bar_wait(&tile_bar, 0);
+  __syncthreads();                                       // copied tile visible
+  if (by_tma) { mm_bar_wait(&tile_bar, tma_uses & 1); tma_uses++; }
 
   const int wr = warp >> 2, wc = warp & 3;
   const int y0 = y_tile + 16 * wr + g;                   // + 8 mb
@@ -573,6 +601,8 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
       }
     }
   }
+  if (tile_i + (int)gridDim.x < n_tiles) __syncthreads();   // every warp has left the tile before it is overwritten
+  }                                                      // tiles
 }
 
 // ---- pass B: CTA = 64 MB rows x 32 columns; warp w = rows 8 MB w .. (MB M blocks) x 32 columns (4 N blocks).
@@ -598,8 +628,11 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int x_tile = blockIdx.x * MB_COLS, y_tile = blockIdx.y * Y - A.row_shift;
   const int w = A.oct.w, h = A.oct.h;
+  ms_stage_taps<MSB_THREADS>(weights, A, wsm);
+  const int tiles_x = (w + MB_COLS - 1) / MB_COLS, n_tiles = tiles_x * ((h + A.row_shift + Y - 1) / Y);
+  for (int tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+  const int x_tile = (tile_i % tiles_x) * MB_COLS, y_tile = (tile_i / tiles_x) * Y - A.row_shift;
 
   auto stage = [&](const int li) {                       // all threads: rows y_tile - R .. of T_li into its buffer
     const int R = A.radius[li];
@@ -631,7 +664,6 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage(0);
-  ms_stage_taps<MSB_THREADS>(weights, A, wsm);
 
   const int y0 = y_tile + 8 * MB * warp + g;             // + 8 mb
   const int x0 = x_tile + 4 * t;                         // + 16 (nb >> 1) + 2 (nb & 1): first column of block nb
@@ -742,6 +774,8 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
       else emit(last, k >> 1, k & 1, ga, gb);
     }
   }
+  if (tile_i + (int)gridDim.x < n_tiles) __syncthreads();   // every warp has left the tile: the staging buffers are free
+  }                                                      // tiles
 }
 
 // ---- host side of octaves >= 1 ----------------------------------------------------------------------------
@@ -818,7 +852,7 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   A.row_shift = oct.y_top & 7;
   {
     const size_t smem = ms_smem_a(A);
-    dim3 grid((oct.w + MA_COLS - 1) / MA_COLS, (oct.h + MA_ROWS - 1) / MA_ROWS);
+    const int grid = mm_grid(((oct.w + MA_COLS - 1) / MA_COLS) * ((oct.h + MA_ROWS - 1) / MA_ROWS));
     CUtensorMap src_map;
     memset(&src_map, 0, sizeof src_map);
     A.use_tma = (mm_encode_2d(&src_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, oct.seed64, (size_t)oct.w * sizeof(double), oct.w, oct.h,
@@ -829,7 +863,7 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   const int mb = ms_pick_mb(A);
   const size_t smem = ms_smem_b(A, mb);
   const int ytile = 8 * MSB_WARPS * mb;
-  dim3 grid((oct.w + MB_COLS - 1) / MB_COLS, (oct.h + A.row_shift + ytile - 1) / ytile);
+  const int grid = mm_grid(((oct.w + MB_COLS - 1) / MB_COLS) * ((oct.h + A.row_shift + ytile - 1) / ytile));
   if (mb == 2) {
     cudaFuncSetAttribute(sep_b_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sep_b_mma_kernel<2><<<grid, MSB_THREADS, smem, st>>>(d_weights, A);
