@@ -109,6 +109,11 @@ static int mm_grid(int n_tiles)
 #define M0_SPITCH 52                     // = 4 (mod 16): lanes (g, t) -> g * pitch + t hit 16 distinct 8-byte banks per half warp
 #define M0_TW_DOUBLES (32 * 16)          // per-warp Ts: 32 rows x 16 columns
 #define M0_THREADS 256
+// 1: the two groups of four warps of a CTA take turns on the DMMA pipe (measured 0.124 against 0.131 ms per 1080p frame);
+// 0: free-running warps; 2: hand-over after the H pass (0.139).  M0_HALVES = 2: 16-warp CTAs, ring of four groups (0.141).
+#ifndef M0_PINGPONG
+#define M0_PINGPONG 1
+#endif
 #define M0_MAXD 5                        // chunks of 4 samples per 8 x K band: ceil((n + 3) / 4), n <= 17
 #define M0_S_DOUBLES (M0_SROWS * M0_SPITCH + 16)       // 2928: keeps everything behind it on 128-byte boundaries
 #define M0_T_DOUBLES (8 * M0_TW_DOUBLES)
@@ -164,7 +169,7 @@ __device__ __forceinline__ float m0_cvt(double x) { return (float)x; }
 template <int D>
 __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double *__restrict__ Tw,
                                            const double *__restrict__ wfs, const int clo0, const int warp,
-                                           const int lane, double (&acc)[4][2][2])
+                                           const int lane, double (&acc)[4][2][2], const int stage, const int n_stages)
 {
   constexpr int MBH = (4 * D + 12 + 7) / 8;             // 8-row blocks of H-pass rows: 3 (D <= 3) or 4
   const int g = lane >> 2, t = lane & 3;
@@ -172,6 +177,12 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
   double wf[D];
 #pragma unroll
   for (int d = 0; d < D; d++) wf[d] = wfs[d * 32 + lane];
+#if M0_PINGPONG
+  // The two halves of the CTA (warps 0-3 / 4-7: one warp of each per SM sub-partition) take turns on the DMMA pipe:
+  // a half blurs a level while the other converts and stores the level it has just finished.  Warps that share a
+  // pipe fairly finish their DMMA phases together and then idle it together; the hand-over keeps one of them on it.
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + stage) : "memory");
+#endif
   {
     // ---- H pass: base columns 16 wx .. + 15 (two N blocks = source positions 8 wx .. + 7), rows from the first
     //      row of this warp's vertical window
@@ -195,6 +206,9 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
         }
       }
     }
+#if M0_PINGPONG == 2
+    asm volatile("bar.arrive %0, 256;" ::"r"(1 + (stage + 1 == n_stages ? 0 : stage + 1)) : "memory");     // early hand-over
+#endif
     __syncwarp();                                       // the previous level's V pass has read Tw
     const int sw = 8 * (g & 1) + 2 * ((g >> 1) & 1);
     double *tp = Tw + g * 16;
@@ -229,33 +243,49 @@ __device__ __forceinline__ void mma0_level(const double *__restrict__ S, double 
       }
     }
   }
+#if M0_PINGPONG == 1
+  asm volatile("bar.arrive %0, 256;" ::"r"(1 + (stage + 1 == n_stages ? 0 : stage + 1)) : "memory");     // the next group may blur its level
+#endif
 }
 
-__global__ void __launch_bounds__(M0_THREADS, 2)
+// HV = tiles per CTA: 1 (8 warps, two CTAs per SM) or 2 (16 warps, one CTA per SM; each group of 8 warps owns a tile
+// with its own S / Ts / raw regions, the fragments are shared).  With M0_PINGPONG the 2 HV groups of four warps (one
+// warp per SM sub-partition each) take turns on the DMMA pipe in a ring.
+template <int HV>
+__global__ void __launch_bounds__(M0_THREADS * HV, 3 - HV)
 oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUtensorMap src_map)
 {
   extern __shared__ __align__(128) double smem[];
   __shared__ int lvR[SIFT_MAX_LEVELS];
-  __shared__ __align__(8) unsigned long long src_bar;
-  double *S = smem;                                     // [56][52] source tile v / 255 (rows / columns >= 48: zero)
-  double *Tw = smem + M0_S_DOUBLES + (threadIdx.x >> 5) * M0_TW_DOUBLES;   // this warp's horizontally blurred rows
-  double *Wf = smem + M0_S_DOUBLES + M0_T_DOUBLES;                       // [nlev][M0_MAXD][32] band fragments
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ __align__(8) unsigned long long src_bars[HV];
+  const int half = threadIdx.x / M0_THREADS;            // which tile of the CTA
+  const int tid = threadIdx.x % M0_THREADS, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  unsigned char *raw = reinterpret_cast<unsigned char *>(smem + M0_S_DOUBLES + M0_T_DOUBLES + A.nlev * M0_MAXD * 32);
+  const int stage = (int)threadIdx.x >> 7, n_stages = 2 * HV;          // groups of four warps
+  const int half_doubles = M0_S_DOUBLES + M0_T_DOUBLES + M0_RAW_DOUBLES;
+  double *S = smem + half * half_doubles;               // [56][52] source tile v / 255 (rows / columns >= 48: zero)
+  double *Tw = S + M0_S_DOUBLES + warp * M0_TW_DOUBLES; // this warp's horizontally blurred rows
+  unsigned char *raw = reinterpret_cast<unsigned char *>(S + M0_S_DOUBLES + M0_T_DOUBLES);
+  double *Wf = smem + HV * half_doubles;                // [nlev][M0_MAXD][32] band fragments
+  unsigned long long &src_bar = src_bars[half];
   if (tid == 0) mm_bar_init(&src_bar, 1);
-  if (tid < A.nlev) lvR[tid] = A.radius[tid];
-  for (int e = tid; e < A.nlev * M0_MAXD * 32; e += M0_THREADS) Wf[e] = __ldg(A.wfrag + e);
+  if ((int)threadIdx.x < A.nlev) lvR[threadIdx.x] = A.radius[threadIdx.x];
+  for (int e = threadIdx.x; e < A.nlev * M0_MAXD * 32; e += M0_THREADS * HV) Wf[e] = __ldg(A.wfrag + e);
   // everything of S beyond the 48 x 48 samples is read against zero weights only: keep it finite (written once)
   for (int e = tid; e < M0_SCOLS * (M0_SPITCH - M0_SCOLS); e += M0_THREADS)
     S[(e >> 2) * M0_SPITCH + M0_SCOLS + (e & 3)] = 0.0;
   for (int e = M0_SCOLS * M0_SPITCH + tid; e < M0_S_DOUBLES; e += M0_THREADS) S[e] = 0.0;
   __syncthreads();                                      // barrier initialised, level table and fragments staged
+#if M0_PINGPONG
+  if (stage == n_stages - 1) asm volatile("bar.arrive 1, 256;" ::: "memory");  // the first group starts
+#endif
 
   // The CTA walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of this launch (one tile per CTA unless the
   // host caps the grid: SIFT_B200_MMA_HALF_SM launches one CTA per SM so that another frame's kernel shares the SM).
   unsigned tma_uses = 0;
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+  for (int tile0 = blockIdx.x * HV; tile0 < A.n_tiles; tile0 += gridDim.x * HV) {
+  const bool live = tile0 + half < A.n_tiles;           // an odd tile count leaves the last CTA's second group without a tile:
+  const int tile = live ? tile0 + half : A.n_tiles - 1; // it blurs a copy of the last one and stores nothing
   const int a_tile = (tile % A.tiles_x) * M0_SW, b_tile = (tile / A.tiles_x + A.tile_y0) * M0_SH - A.row_shift;
 
   // interior tiles: the 48 x 48 window of u8 / f32 source samples arrives as ONE TMA box in `raw` (the unit would
@@ -311,7 +341,7 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
   const int x0 = 2 * a_tile + 16 * wx + 4 * t;          // first of this lane's four columns: block 0 holds x0, x0 + 1, block 1 x0 + 2, x0 + 3
   const int ow = A.oct.w, oh = A.oct.h;
   const size_t row8 = (size_t)8 * A.oct.pitch;
-  const bool interior = b_tile >= 0 && 2 * (b_tile + M0_SH) <= oh && 2 * (a_tile + M0_SW) <= ow;   // CTA-uniform
+  const bool interior = b_tile >= 0 && 2 * (b_tile + M0_SH) <= oh && 2 * (a_tile + M0_SW) <= ow;   // uniform over the group
   float *gthr = A.oct.gauss[0] + ((long long)y0 * A.oct.pitch + x0);      // this lane's first output of level 0
 
   // one level: both passes, then the epilogue -- G_s, D_{s-1} = G_{s-1} - G_s (sift.js:172) from the unrounded
@@ -323,14 +353,15 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
     const int D = (n + 6) >> 2;                         // chunks of the band: ceil((n + 3) / 4)
     const double *wfs = Wf + s * M0_MAXD * 32;
     switch (D) {                                        // CTA-uniform
-      case 2: mma0_level<2>(S, Tw, wfs, clo0, warp, lane, cur); break;
-      case 3: mma0_level<3>(S, Tw, wfs, clo0, warp, lane, cur); break;
-      case 4: mma0_level<4>(S, Tw, wfs, clo0, warp, lane, cur); break;
-      default: mma0_level<5>(S, Tw, wfs, clo0, warp, lane, cur); break;
+      case 2: mma0_level<2>(S, Tw, wfs, clo0, warp, lane, cur, stage, n_stages); break;
+      case 3: mma0_level<3>(S, Tw, wfs, clo0, warp, lane, cur, stage, n_stages); break;
+      case 4: mma0_level<4>(S, Tw, wfs, clo0, warp, lane, cur, stage, n_stages); break;
+      default: mma0_level<5>(S, Tw, wfs, clo0, warp, lane, cur, stage, n_stages); break;
     }
     const bool wg = A.keep_gauss != 0, wd = s > 0;
     float *gl = gthr + (long long)s * A.plane;
-    if (interior) {
+    if (!live) {
+    } else if (interior) {
       if (wg) {
         float *r = gl;
 #pragma unroll
@@ -362,7 +393,7 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
         }
       }
     }
-    if (A.has_next && s == A.spo && (g & 1) == 0) {     // in[2a][2b] (matrix2d.js:129): even rows, even columns
+    if (live && A.has_next && s == A.spo && (g & 1) == 0) {     // in[2a][2b] (matrix2d.js:129): even rows, even columns
 #pragma unroll
       for (int mb = 0; mb < 4; mb++) {
         const int y = y0 + 8 * mb;
@@ -390,7 +421,7 @@ oct0_mma_kernel(const __grid_constant__ Mma0Args A, const __grid_constant__ CUte
     level(s, pa, pb);
     if (s + 1 < A.nlev) level(s + 1, pb, pa);
   }
-  if (tile + (int)gridDim.x < A.n_tiles) __syncthreads();   // every warp has left this tile: S and raw are free
+  if (tile0 + (int)gridDim.x * HV < A.n_tiles) __syncthreads();   // every warp has left its tile: S and raw are free
   }                                                     // tiles
 }
 
@@ -440,23 +471,27 @@ bool launch_oct0_mma(cudaStream_t st, const void *src, int dtype, size_t src_pit
   for (int s = 0; s < nlev; s++) A.radius[s] = plans[s].radius;
   A.wfrag = d_frags;
   A.row_shift = (oct.y_top >> 1) & 3;
-  const size_t smem = (size_t)M0_SMEM_DOUBLES(nlev) * sizeof(double);
+#ifndef M0_HALVES
+#define M0_HALVES 1
+#endif
+  const size_t smem = ((size_t)M0_HALVES * (M0_S_DOUBLES + M0_T_DOUBLES + M0_RAW_DOUBLES) + (size_t)nlev * M0_MAXD * 32) * sizeof(double);
   const int all_rows = (src_h + A.row_shift + M0_SH - 1) / M0_SH;
   A.tile_y0 = tile_rows < 0 ? 0 : tile_row0;
   const int n_rows = tile_rows < 0 ? all_rows : (tile_row0 + tile_rows <= all_rows ? tile_rows : all_rows - tile_row0);
   if (n_rows <= 0) return true;
   A.tiles_x = (src_w + M0_SW - 1) / M0_SW;
   A.n_tiles = A.tiles_x * n_rows;
-  const int grid = mm_grid(A.n_tiles);
-  cudaFuncSetAttribute(oct0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
+  const int grid = mm_grid((A.n_tiles + M0_HALVES - 1) / M0_HALVES);
+  cudaFuncSetAttribute(oct0_mma_kernel<M0_HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // grows with the level count
   CUtensorMap src_map;
   memset(&src_map, 0, sizeof src_map);
   // the raw tile must start on a 128-byte boundary of shared memory: S, Ts and the fragments before it are whole multiples
   A.use_tma = 0;
-  if ((dtype == SIFT_U8 || dtype == SIFT_F32) && ((size_t)(M0_S_DOUBLES + M0_T_DOUBLES + nlev * M0_MAXD * 32) * sizeof(double)) % 128 == 0)
+  if ((dtype == SIFT_U8 || dtype == SIFT_F32) && ((size_t)(M0_S_DOUBLES + M0_T_DOUBLES) * sizeof(double)) % 128 == 0 &&
+      ((size_t)M0_RAW_DOUBLES * sizeof(double)) % 128 == 0)
     A.use_tma = (mm_encode_2d(&src_map, dtype == SIFT_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                               dtype == SIFT_U8 ? 1 : 4, src, src_pitch, src_w, src_h, dtype == SIFT_U8 ? 64 : M0_SCOLS, M0_SCOLS)) ? 1 : 0;
-  oct0_mma_kernel<<<grid, M0_THREADS, smem, st>>>(A, src_map);
+  oct0_mma_kernel<M0_HALVES><<<grid, M0_THREADS * M0_HALVES, smem, st>>>(A, src_map);
   return true;
 }
 
@@ -526,14 +561,8 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
   double *wsm = smem + MA_ROWS * A.tile_pitch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int x_tile = blockIdx.x * MA_COLS, y_tile = blockIdx.y * MA_ROWS;
   const int tp = A.tile_pitch;
-  if (tid == 0) mm_bar_init(&tile_bar, 1);
-  ms_stage_taps(weights, A, wsm);
-  __syncthreads();                                       // barrier initialised, taps staged
-  const int tiles_x = (A.w + MA_COLS - 1) / MA_COLS, n_tiles = tiles_x * ((A.h + MA_ROWS - 1) / MA_ROWS);
-  unsigned tma_uses = 0;
-  for (int tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
-  const int x_tile = (tile_i % tiles_x) * MA_COLS, y_tile = (tile_i / tiles_x) * MA_ROWS;
 
   const int xl = x_tile - A.rmax;                        // first staged column (rmax is rounded up to even by the host)
   const bool by_tma = A.use_tma && xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h;      // CTA-uniform
@@ -541,7 +570,7 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
     // interior tile: ONE TMA box (32 rows x tile_pitch fp64 of the seed plane) lands dense in the tile, completion
     // on an mbarrier; border tiles need clamp-to-edge samples (the TMA unit would zero-fill) and are copied below
     if (tid == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was read through the generic proxy (previous tile)
+      mm_bar_init(&tile_bar, 1);
       mm_tma_load_2d(tile, &src_map, &tile_bar, xl, y_tile, (unsigned)(MA_ROWS * tp * sizeof(double)));
     }
   } else if (xl >= 0 && xl + tp <= A.w && y_tile + MA_ROWS <= A.h && (A.w & 1) == 0) {
@@ -559,9 +588,10 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  ms_stage_taps(weights, A, wsm);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();                                       // copied tile visible
-  if (by_tma) { mm_bar_wait(&tile_bar, tma_uses & 1); tma_uses++; }
+  __syncthreads();                                       // taps, copied tile, barrier initialisation visible
+  if (by_tma) mm_bar_wait(&tile_bar, 0);
 
   const int wr = warp >> 2, wc = warp & 3;
   const int y0 = y_tile + 16 * wr + g;                   // + 8 mb
@@ -601,8 +631,6 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
       }
     }
   }
-  if (tile_i + (int)gridDim.x < n_tiles) __syncthreads();   // every warp has left the tile before it is overwritten
-  }                                                      // tiles
 }
 
 // ---- pass B: CTA = 64 MB rows x 32 columns; warp w = rows 8 MB w .. (MB M blocks) x 32 columns (4 N blocks).
@@ -628,11 +656,8 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
   double *wsm = buf1 + A.buf_rows[1] * MB_PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int x_tile = blockIdx.x * MB_COLS, y_tile = blockIdx.y * Y - A.row_shift;
   const int w = A.oct.w, h = A.oct.h;
-  ms_stage_taps<MSB_THREADS>(weights, A, wsm);
-  const int tiles_x = (w + MB_COLS - 1) / MB_COLS, n_tiles = tiles_x * ((h + A.row_shift + Y - 1) / Y);
-  for (int tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
-  const int x_tile = (tile_i % tiles_x) * MB_COLS, y_tile = (tile_i / tiles_x) * Y - A.row_shift;
 
   auto stage = [&](const int li) {                       // all threads: rows y_tile - R .. of T_li into its buffer
     const int R = A.radius[li];
@@ -664,6 +689,7 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage(0);
+  ms_stage_taps<MSB_THREADS>(weights, A, wsm);
 
   const int y0 = y_tile + 8 * MB * warp + g;             // + 8 mb
   const int x0 = x_tile + 4 * t;                         // + 16 (nb >> 1) + 2 (nb & 1): first column of block nb
@@ -774,8 +800,6 @@ sep_b_mma_kernel(const double *__restrict__ weights, const MmaSepArgs A)
       else emit(last, k >> 1, k & 1, ga, gb);
     }
   }
-  if (tile_i + (int)gridDim.x < n_tiles) __syncthreads();   // every warp has left the tile: the staging buffers are free
-  }                                                      // tiles
 }
 
 // ---- host side of octaves >= 1 ----------------------------------------------------------------------------
@@ -852,7 +876,7 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   A.row_shift = oct.y_top & 7;
   {
     const size_t smem = ms_smem_a(A);
-    const int grid = mm_grid(((oct.w + MA_COLS - 1) / MA_COLS) * ((oct.h + MA_ROWS - 1) / MA_ROWS));
+    dim3 grid((oct.w + MA_COLS - 1) / MA_COLS, (oct.h + MA_ROWS - 1) / MA_ROWS);
     CUtensorMap src_map;
     memset(&src_map, 0, sizeof src_map);
     A.use_tma = (mm_encode_2d(&src_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, oct.seed64, (size_t)oct.w * sizeof(double), oct.w, oct.h,
@@ -863,7 +887,7 @@ void launch_mma_sep(cudaStream_t st, const OctaveDev &oct, const OctaveDev *next
   const int mb = ms_pick_mb(A);
   const size_t smem = ms_smem_b(A, mb);
   const int ytile = 8 * MSB_WARPS * mb;
-  const int grid = mm_grid(((oct.w + MB_COLS - 1) / MB_COLS) * ((oct.h + A.row_shift + ytile - 1) / ytile));
+  dim3 grid((oct.w + MB_COLS - 1) / MB_COLS, (oct.h + A.row_shift + ytile - 1) / ytile);
   if (mb == 2) {
     cudaFuncSetAttribute(sep_b_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sep_b_mma_kernel<2><<<grid, MSB_THREADS, smem, st>>>(d_weights, A);
