@@ -39,7 +39,7 @@ FRAMES = 64                    # frames per GPU per step (distinct seeds)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, written by tools/ncu_traffic.py from the
 # `ncu --set full` captures of this round (roofline.traffic is read from this file by kernel name, null if absent)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")
-DOMINANT_KERNEL = "oct0_mma_kernel"
+DOMINANT_KERNEL = "oct0_mma_kernel<1>"
 # separable float64 blur of the reference radii: multiply-adds per input pixel (octave 0 polyphase-merged)
 # and the measured fp64 peak of this B200 (DFMA 36.5, DMMA 37.0 TFLOP/s: tools/micro/fp64_pipes.cu) -- the binding unit of the path
 FMA_PER_INPUT_PX = {4: 982.0, 6: 1048.0}
