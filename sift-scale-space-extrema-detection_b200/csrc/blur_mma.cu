@@ -549,6 +549,9 @@ __device__ __forceinline__ void ms_cp16(double *dst_smem, const double *src)
 #ifndef MSA_CTAS
 #define MSA_CTAS 2
 #endif
+#ifndef MSA_PINGPONG
+#define MSA_PINGPONG 0
+#endif
 #ifndef MSB_CTAS
 #define MSB_CTAS 2
 #endif
@@ -596,9 +599,17 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
   const int wr = warp >> 2, wc = warp & 3;
   const int y0 = y_tile + 16 * wr + g;                   // + 8 mb
   const int x0 = x_tile + 32 * wc + 2 * t;               // + 8 nb
+#if MSA_PINGPONG
+  // the two groups of four warps take turns on the DMMA pipe (see oct0_mma_kernel): a group blurs a level while the
+  // other stores the level it has just finished
+  if (wr == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
+#endif
   for (int li = 0; li < A.nlev; li++) {
     const int R = A.radius[li];
     const int D = (2 * R + 8 + 3) >> 2;                  // chunks of the band: ceil((taps + 7) / 4)
+#if MSA_PINGPONG
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + wr) : "memory");
+#endif
     const double *wp = wsm + A.wsm[li] + MS_WFRONT + t - g;        // fragment of chunk d: wp[4 d] (zero outside the taps)
     const double *sp = tile + (16 * wr + g) * tp + (A.rmax - R) + 32 * wc + t;
     double acc[2][4][2];
@@ -616,6 +627,9 @@ sep_a_mma_kernel(const double *__restrict__ weights, const __grid_constant__ Mma
         dmma884(acc[1][nb][0], acc[1][nb][1], a1, wv);
       }
     }
+#if MSA_PINGPONG
+    asm volatile("bar.arrive %0, 256;" ::"r"(1 + (wr ^ 1)) : "memory");
+#endif
     double *T = A.T[li];
 #pragma unroll
     for (int mb = 0; mb < 2; mb++) {
