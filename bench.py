@@ -449,7 +449,7 @@ def workload_config(n_gpus: int) -> dict:
                         f"(6 blur levels), sigma0={MIN_BLUR}, assumed blur {ASSUMED}, contrast 0.015 "
                         f"(reference constant), edge r=10, 2x-upsampled base octave",
             "frames_per_gpu_per_step": FRAMES, "sharding": f"images split by rank x{n_gpus}, no collective",
-            "frames_in_flight_per_gpu": LANES or "auto by frame size: 4 at 1920x1080, 6 at 1280x720 and 3840x2160, 8 at 512x512",
+            "frames_in_flight_per_gpu": LANES or "auto by frame size: 8 below 6 Mpixel (1920x1080, 1280x720, 512x512), 6 at 3840x2160",
             "l2": "no flush: one frame's pyramid (735 MB algorithmic) exceeds the 126 MB L2 and frames rotate"}
 
 

@@ -160,8 +160,7 @@ SIFT_API int sift_flush(sift_ctx *ctx);
  * levels >= 1).  Default 1: every level of the pyramid is materialised once, like the reference's reply. */
 SIFT_API int sift_set_keep_gaussian(sift_ctx *ctx, int keep);
 /* Frames in flight for sift_detect_device / sift_detect_batch: 1..8, or 0 (default; env SIFT_B200_LANES) = chosen
- * from the frame size -- 3 for frames of 1.5 Mpixel and more, up to 8 for small frames whose kernels do not fill the
- * GPU on their own. */
+ * from the frame size -- 8 for frames below 6 Mpixel, 6 above (fewer when the lanes' pyramids would exceed ~32 GB). */
 SIFT_API int sift_set_lanes(sift_ctx *ctx, int n_lanes);
 SIFT_API int64_t sift_kernel_launches(const sift_ctx *ctx); /* running total for the context */
 /* Generation of the pyramid the stage calls read (sift_get_level, sift_find_candidates, sift_refine ...): changes

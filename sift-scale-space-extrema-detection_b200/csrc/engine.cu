@@ -100,7 +100,7 @@ struct sift_ctx {
   bool fused0 = false;             // octave 0 runs the fused polyphase kernel
   int mma0_woff = -1;              // octave 0: per-lane band fragments of the DMMA kernel (blur_mma.cu), -1: not usable
   bool no_mma = false;             // SIFT_B200_NO_MMA=1: scalar-FMA blur kernels everywhere
-  bool mma_all = false;            // SIFT_B200_MMA_ALL=1: DMMA passes for every octave they support, whatever its size
+  bool mma_big_only = false;       // SIFT_B200_MMA_BIG_ONLY=1: octaves below 2^18 pixels keep the scalar two-pass kernels
   bool oct0_variant_forced = false;  // one of the octave-0 variant knobs is set: it wins over the DMMA kernel
   bool sep_variant_forced = false;   // one of the knobs of the scalar two-pass kernels is set: they win over the DMMA passes
   bool force_generic = false;      // SIFT_B200_FORCE_GENERIC=1: radius-generic two-pass kernels everywhere
@@ -554,9 +554,11 @@ static void run_octave(sift_ctx *ctx, int o, const void *d_image, int dtype, siz
   const int first = (o == 0) ? 0 : 1;
   const int hrows = (o == 0) ? ctx->in_h : od.h;
   prof_begin(ctx, o == 0 ? SIFT_PROF_BLUR_OCT0 : (o == 1 ? SIFT_PROF_BLUR_OCT1 : SIFT_PROF_BLUR_HIGH));
-  // small octaves: too few tiles for the DMMA passes to fill the SMs, the scalar two-pass kernels are faster there
+  // small octaves (< 2^18 pixels: 36-75 CTAs) run 20 % longer on the DMMA passes than on the scalar ones when a frame is
+  // alone on the GPU, but with frames in flight the whole path is 2-5 % faster with them (they leave more of the SMs to
+  // the other frames' kernels): DMMA everywhere; SIFT_B200_MMA_BIG_ONLY=1 keeps the scalar passes for small octaves
   if (o > 0 && !ctx->no_mma && !ctx->force_old && !ctx->force_generic && !ctx->sep_variant_forced &&
-      ((long long)od.w * od.h >= (1 << 18) || ctx->mma_all) && mma_sep_supported(ctx->plans[o], ctx->nlev, od.w, od.h)) {
+      ((long long)od.w * od.h >= (1 << 18) || !ctx->mma_big_only) && mma_sep_supported(ctx->plans[o], ctx->nlev, od.w, od.h)) {
     launch_mma_sep(st, od, next, ctx->d_weights, ctx->plans[o], (double *)ctx->L->tbuf.p, spo, ctx->keep_gauss);
     ctx->launches += 2;
     prof_end(ctx);
@@ -912,7 +914,7 @@ SIFT_API int sift_create(int device, sift_ctx **out)
   const char *fg = getenv("SIFT_B200_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
   { const char *nm = getenv("SIFT_B200_NO_MMA"); c->no_mma = nm && nm[0] == '1'; }
-  c->mma_all = getenv("SIFT_B200_MMA_ALL") != nullptr;
+  c->mma_big_only = getenv("SIFT_B200_MMA_BIG_ONLY") != nullptr;
   c->sep_variant_forced = getenv("SIFT_B200_NO_TMA") || getenv("SIFT_B200_NO_TMA_BLUR") || getenv("SIFT_B200_FIR_NO8");
   c->oct0_variant_forced = getenv("SIFT_B200_OCT0_WS") || getenv("SIFT_B200_OCT0_SMALL") || getenv("SIFT_B200_OCT0_BANDS") ||
                            getenv("SIFT_B200_FUSED0_LO") || getenv("SIFT_B200_FUSED0_HI1") || getenv("SIFT_B200_FUSED0_HI3");
@@ -971,7 +973,8 @@ static int auto_lanes(const sift_ctx *ctx)
   const long long px = (long long)ctx->in_w * ctx->in_h;
   // 1080p: 3 = 4 = 8 lanes (6 250 Mpixel/s); 720p: 5 500 (3) -> 5 880 (6); 512^2: 3 510 (3) -> 5 210 (8);
   // 3840x2160 / 6 octaves: 5 920 (3) -> 6 080 (6)
-  int lanes = px >= 6000000 ? 6 : (px >= 1500000 ? 4 : (px >= 700000 ? 6 : 8));
+  // with the DMMA kernels on every octave (second half of round 2): 1080p 6 860 (4) -> 7 030 (8); 720p 5 980 (4) -> 6 590 (8)
+  int lanes = px >= 6000000 ? 6 : 8;
   // a lane holds a whole pyramid (~240 bytes per input pixel): keep the lanes of large images within ~32 GB
   const long long per_lane = px * 240;
   while (lanes > 1 && per_lane * lanes > (32LL << 30)) lanes--;

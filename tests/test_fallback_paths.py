@@ -38,8 +38,8 @@ KNOBS = ["", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD", "SIFT_B200_NO_TMA
          "SIFT_B200_FUSED0_LO", "SIFT_B200_FIR_NO8", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_WS+SIFT_B200_NO_TMA_BLUR",
          "SIFT_B200_OCT0_SMALL", "SIFT_B200_OCT0_BANDS", "SIFT_B200_OCT0_BANDS+SIFT_B200_OCT0_BAND=64",
          # round 2, DMMA kernels are the default: the scalar-FMA kernels everywhere / the two scalar octave-0 tile
-         # kernels / DMMA passes on every octave whatever its size / DMMA kernels with copied instead of TMA-loaded tiles
-         "SIFT_B200_NO_MMA", "SIFT_B200_FUSED0_HI1", "SIFT_B200_FUSED0_HI3", "SIFT_B200_MMA_ALL", "SIFT_B200_MMA_NO_TMA"]
+         # kernels / scalar passes for the small octaves / DMMA kernels with copied instead of TMA-loaded tiles
+         "SIFT_B200_NO_MMA", "SIFT_B200_FUSED0_HI1", "SIFT_B200_FUSED0_HI3", "SIFT_B200_MMA_BIG_ONLY", "SIFT_B200_MMA_NO_TMA"]
 
 
 @pytest.mark.gpu

@@ -66,7 +66,7 @@ print("OK strips", len(km))
 """
 
 KNOBS = ["", "SIFT_B200_OCT0_WS", "SIFT_B200_OCT0_SMALL", "SIFT_B200_OCT0_BANDS", "SIFT_B200_FUSED0_LO", "SIFT_B200_NO_TMA_BLUR", "SIFT_B200_FORCE_GENERIC", "SIFT_B200_FORCE_OLD",
-         "SIFT_B200_NO_TMA", "SIFT_B200_NO_MMA", "SIFT_B200_FUSED0_HI1", "SIFT_B200_MMA_ALL"]
+         "SIFT_B200_NO_TMA", "SIFT_B200_NO_MMA", "SIFT_B200_FUSED0_HI1", "SIFT_B200_MMA_BIG_ONLY"]
 
 
 @pytest.mark.gpu
